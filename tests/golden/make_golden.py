@@ -1,0 +1,170 @@
+"""Generate the golden fixtures by running the REFERENCE ITSELF (this container only).
+
+    python tests/golden/make_golden.py          # needs /root/reference, writes tests/golden/*.pt
+
+Imports the reference's own model/encoder.py and model/decoder.py, loads synthetic
+weights (mmqg.synth.make_params) into them with load_state_dict, and drives them with the
+per-sample loop of train.py:153-177 (teacher forcing) and train.py:101-110 (greedy),
+exactly as train.py does: one TextEncoder.forward per token, one AttnDecoder.forward per
+step, CrossEntropyLoss per step summed, loss.backward().  Stored per case:
+  small cases  : weights, inputs, per-sample losses, mean loss, every gradient tensor
+                 (mean over samples), per-step logits / attention weights, greedy tokens.
+  full-dim case: (E=300, H=512, L=3, TM=283, AM=101; weights are regenerated from the seed,
+                 not stored) loss, per-tensor gradient norms, 64 sampled gradient entries
+                 per tensor, greedy tokens and top-1/top-2 margins.
+The fixtures travel to the GPU box; /root/reference does not.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "multi-modal-qg_b200"))
+sys.path.insert(0, "/root/reference")
+
+from mmqg.dims import Dims  # noqa: E402
+from mmqg.synth import make_params, make_batch  # noqa: E402
+from model.encoder import TextEncoder, VideoConvLstmEncoder  # noqa: E402  (reference)
+from model.decoder import AttnDecoder  # noqa: E402  (reference)
+
+CASES = {
+    "small_a": dict(dims=Dims(B=3, T_t=6, T_v=3, T_q=5, V=37, E=12, H=32, L=3, H_a=8, H_v=32, F_v=20, TM=9, AM=5),
+                    seed=11),
+    "small_b": dict(dims=Dims(B=2, T_t=5, T_v=2, T_q=4, V=29, E=10, H=16, L=2, H_a=6, H_v=24, F_v=14, TM=7, AM=4),
+                    seed=12),
+    "full_dim": dict(dims=Dims(B=2, T_t=12, T_v=4, T_q=5, V=1000, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048,
+                               TM=283, AM=101), seed=13),
+}
+
+
+def build_reference(d, params, dtype):
+    dev = torch.device("cpu")
+    emb = torch.nn.Embedding(d.V, d.E)
+    video = VideoConvLstmEncoder(3, 3, 1, d.H_v, d.F_v)              # only .lstm is on the path
+    text = TextEncoder(d.L, 0.0, d.H, d.E, emb, dev)
+    dec = AttnDecoder(d.L, 0.0, d.H, d.V, d.E, d.H_v, d.H_a, emb, d.TM, d.AM, dev)
+    for m in (emb, video, text, dec):
+        m.to(dtype)
+    emb.load_state_dict({"weight": params["emb.weight"].to(dtype)})
+    video.lstm.load_state_dict({k[len("video.lstm."):]: v.to(dtype) for k, v in params.items()
+                                if k.startswith("video.lstm.")})
+    text.lstm.load_state_dict({k[len("text.lstm."):]: v.to(dtype) for k, v in params.items()
+                               if k.startswith("text.lstm.")})
+    sd = {k[len("dec."):]: v.to(dtype) for k, v in params.items() if k.startswith("dec.")}
+    sd["emb_layer.weight"] = params["emb.weight"].to(dtype)
+    dec.load_state_dict(sd)
+    assert text.word_embeddings is emb and dec.emb_layer is emb
+    return emb, video, text, dec
+
+
+def named_grads(emb, video, text, dec):
+    out = {"emb.weight": emb.weight.grad}
+    for n, p in video.lstm.named_parameters():
+        out[f"video.lstm.{n}"] = p.grad
+    for n, p in text.lstm.named_parameters():
+        out[f"text.lstm.{n}"] = p.grad
+    for n, p in dec.named_parameters():
+        if not n.startswith("emb_layer"):
+            out[f"dec.{n}"] = p.grad
+    return {k: v.detach().clone() for k, v in out.items()}
+
+
+def encode_sample(d, video, text, ctx, frames, audio):
+    """train.py:153-166 with features in place of raw media."""
+    video_emb = video.lstm(frames.view(frames.shape[0], 1, -1))[0].squeeze(1)   # encoder.py:69,126
+    n_frames = video_emb.shape[0]
+    padded_audio = F.pad(audio, (0, 0, 0, d.AM - n_frames))
+    padded_video = F.pad(video_emb, (0, 0, 0, d.AM - n_frames))
+    hid = text.init_state(1)
+    hid = tuple(h.to(frames.dtype) for h in hid)
+    all_enc = torch.zeros(d.TM, text.hidden_dim, dtype=frames.dtype)
+    for ei in range(ctx.shape[0]):
+        out, hid = text(ctx[ei], hid)
+        all_enc[ei] = out[0, 0]
+    return n_frames, padded_audio, padded_video, hid, all_enc
+
+
+def run_case(name, d, seed, dtype=torch.float64):
+    params = make_params(d, seed=seed)
+    batch = make_batch(d, seed=seed + 1000)
+    emb, video, text, dec = build_reference(d, params, dtype)
+    crit = torch.nn.CrossEntropyLoss()
+    for m in (emb, video, text, dec):
+        m.zero_grad()
+    losses, step_logits, step_attn = [], [], []
+    with contextlib.redirect_stdout(io.StringIO()):                 # decoder.py:89,97 debug prints
+        for b in range(d.B):
+            ctx, tgt = batch["context"][b], batch["target"][b]
+            fr, au = batch["frames"][b].to(dtype), batch["audio"][b].to(dtype)
+            n_frames, pa, pv, hid, all_enc = encode_sample(d, video, text, ctx, fr, au)
+            dec_input = torch.tensor([[1]])
+            loss = 0
+            sl, sa = [], []
+            for di in range(d.T_q):                                 # train.py:171-175
+                out, hid, a_t, a_a, a_v = dec(dec_input, n_frames, d.T_t, pa, pv, hid, all_enc)
+                loss = loss + crit(out, tgt[di].view(-1))
+                dec_input = tgt[di]
+                sl.append(out.detach()[0])
+                sa.append(torch.cat([a_t.detach()[0], a_a.detach()[0], a_v.detach()[0]]))
+            (loss / d.B).backward()                                 # mean over samples of the per-sample loss
+            losses.append(loss.detach())
+            step_logits.append(torch.stack(sl))
+            step_attn.append(torch.stack(sa))
+    grads = named_grads(emb, video, text, dec)
+    fx = {"dims": d.asdict(), "seed": seed, "dtype": str(dtype),
+          "loss_per_sample": torch.stack(losses), "loss": torch.stack(losses).mean()}
+
+    # greedy decode on input-sensitive weights: biases x0.1, out weight x10
+    gparams = make_params(d, seed=seed, bias_scale=0.1, out_weight_scale=10.0)
+    emb, video, text, dec = build_reference(d, gparams, dtype)
+    for m in (video, text, dec):
+        m.eval()
+    max_len = d.T_q + 3
+    toks, margins = [], []
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        for b in range(d.B):
+            fr, au = batch["frames"][b].to(dtype), batch["audio"][b].to(dtype)
+            n_frames, pa, pv, hid, all_enc = encode_sample(d, video, text, batch["context"][b], fr, au)
+            dec_input = torch.tensor([[1]])
+            tk, mg = [], []
+            for di in range(max_len):                               # train.py:101-110
+                out, hid, *_ = dec(dec_input, n_frames, d.T_t, pa, pv, hid, all_enc)
+                word_index = torch.argmax(F.softmax(out, dim=1), dim=1, keepdim=True)
+                top2 = out.topk(2, 1).values[0]
+                tk.append(int(word_index))
+                mg.append(float(top2[0] - top2[1]))
+                dec_input = word_index.detach()
+            toks.append(tk)
+            margins.append(mg)
+    fx["greedy_tokens"] = torch.tensor(toks)
+    fx["greedy_margins"] = torch.tensor(margins)
+    fx["greedy_max_len"] = max_len
+
+    if name.startswith("small"):
+        fx["params"] = params
+        fx["batch"] = batch
+        fx["grads"] = grads
+        fx["step_logits"] = torch.stack(step_logits)              # (B,T_q,V)
+        fx["step_attn"] = torch.stack(step_attn)                  # (B,T_q,TM+2AM) text|audio|video
+    else:
+        g = torch.Generator().manual_seed(999)
+        fp = {}
+        for k, v in grads.items():
+            idx = torch.randint(0, v.numel(), (64,), generator=g)
+            fp[k] = {"norm": v.norm(), "idx": idx, "vals": v.flatten()[idx].clone()}
+        fx["grad_fingerprint"] = fp
+    path = os.path.join(HERE, f"{name}.pt")
+    torch.save(fx, path)
+    print(name, "loss", float(fx["loss"]), "greedy", fx["greedy_tokens"].tolist()[0][:8],
+          "min margin", float(fx["greedy_margins"].min()), os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    for name, c in CASES.items():
+        run_case(name, c["dims"], c["seed"])

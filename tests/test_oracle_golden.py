@@ -1,0 +1,86 @@
+"""The oracle is pinned against fixtures produced by the reference itself
+(tests/golden/make_golden.py): loss, every gradient, per-step logits / attention
+weights, greedy tokens.  CPU only."""
+import pytest
+import torch
+
+from conftest import load_golden
+from mmqg.dims import Dims
+from mmqg.synth import make_params, make_batch
+from oracle import mmqg_oracle as O
+from oracle import ref_loop as R
+
+
+@pytest.mark.parametrize("name", ["small_a", "small_b"])
+def test_oracle_matches_reference_small(name):
+    fx = load_golden(name)
+    d = Dims(**fx["dims"])
+    loss, grads = O.loss_and_grads(fx["params"], fx["batch"], d.L, d.TM, d.AM, torch.float64)
+    assert abs(float(loss) - float(fx["loss"])) < 1e-10 * abs(float(fx["loss"]))
+    assert set(grads) == set(fx["grads"])
+    for k, g in fx["grads"].items():
+        assert O.rel_err(grads[k], g) < 1e-9, k
+
+
+@pytest.mark.parametrize("name", ["small_a", "small_b"])
+def test_oracle_steps_match_reference(name):
+    fx = load_golden(name)
+    d = Dims(**fx["dims"])
+    p = {k: v.double() for k, v in fx["params"].items()}
+    b = {k: (v.double() if v.is_floating_point() else v) for k, v in fx["batch"].items()}
+    with torch.no_grad():
+        _, aux = O.teacher_forced_loss(p, b, d.L, d.TM, d.AM, return_steps=True)
+    for t, st in enumerate(aux["steps"]):
+        assert torch.allclose(st["logits"], fx["step_logits"][:, t], rtol=1e-9, atol=1e-11)
+        attn = torch.cat([st["a_txt"], st["a_aud"], st["a_vid"]], 1)
+        assert torch.allclose(attn, fx["step_attn"][:, t], rtol=1e-9, atol=1e-12)
+    # Q1: the length mask is a no-op -- padded slots carry probability mass
+    assert float(aux["steps"][0]["a_txt"][:, d.T_t:].sum()) > 0
+
+
+@pytest.mark.parametrize("name", ["small_a", "small_b", "full_dim"])
+def test_oracle_greedy_matches_reference(name):
+    fx = load_golden(name)
+    d = Dims(**fx["dims"])
+    gp = make_params(d, seed=fx["seed"], bias_scale=0.1, out_weight_scale=10.0)
+    batch = make_batch(d, seed=fx["seed"] + 1000)
+    toks, margins = O.greedy_decode(gp, batch, d.L, d.TM, d.AM, fx["greedy_max_len"], return_margins=True)
+    assert torch.equal(toks, fx["greedy_tokens"])
+    assert torch.allclose(margins, fx["greedy_margins"].double(), rtol=1e-6, atol=1e-9)
+
+
+def test_oracle_matches_reference_full_dim_fingerprint():
+    fx = load_golden("full_dim")
+    d = Dims(**fx["dims"])
+    params = make_params(d, seed=fx["seed"])
+    batch = make_batch(d, seed=fx["seed"] + 1000)
+    loss, grads = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
+    assert abs(float(loss) - float(fx["loss"])) < 1e-10 * abs(float(fx["loss"]))
+    for k, fp in fx["grad_fingerprint"].items():
+        g = grads[k]
+        assert abs(float(g.norm()) - float(fp["norm"])) <= 1e-9 * float(fp["norm"]) + 1e-300, k
+        assert torch.allclose(g.flatten()[fp["idx"]], fp["vals"], rtol=1e-8, atol=1e-12), k
+
+
+def test_ref_loop_port_matches_oracle():
+    """The per-sample port (stock torch.nn modules) and the batched restatement agree."""
+    fx = load_golden("small_a")
+    d = Dims(**fx["dims"])
+    loss, grads = R.batch_loss_and_grads(fx["params"], fx["batch"], d.L, torch.float64)
+    assert abs(loss - float(fx["loss"])) < 1e-10 * abs(float(fx["loss"]))
+    for k, g in fx["grads"].items():
+        assert O.rel_err(grads[k], g) < 1e-9, k
+    ref = R.RefModules(make_params(d, seed=fx["seed"], bias_scale=0.1, out_weight_scale=10.0), d.L, 0.0, torch.float64)
+    b = fx["batch"]
+    toks = ref.sample_greedy(b["context"][0], b["frames"][0].double(), b["audio"][0].double(), fx["greedy_max_len"])
+    assert toks == fx["greedy_tokens"][0].tolist()
+
+
+def test_oracle_fp32_noise_floor():
+    """fp32 oracle vs fp64 oracle: the self-noise the 1e-3 bar sits on."""
+    fx = load_golden("small_a")
+    d = Dims(**fx["dims"])
+    l32, g32 = O.loss_and_grads(fx["params"], fx["batch"], d.L, d.TM, d.AM, torch.float32)
+    assert abs(float(l32) - float(fx["loss"])) < 1e-5 * abs(float(fx["loss"]))
+    for k, g in fx["grads"].items():
+        assert O.rel_err(g32[k], g) < 1e-4, k
