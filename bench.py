@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the multi-modal-qg training hot path on B200 (contract: task statement (4)).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2]
+
+A "step" is one teacher-forced forward + backward of the encoder/decoder over one synthetic
+batch (BASELINE.json configs[1]: B=256 per GPU, T_t=100, T_v=10x2048, T_a=10x128, T_q=20,
+V=10k).  Rank 0 prints ONE JSON line.  Multi-GPU runs are launched with torch.distributed.run
+(one process per GPU, NCCL); the batch is sharded by sample, gradients are all-reduced in the
+order they become final, overlapped with the rest of the backward pass.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "multi-modal-qg_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+    ap.add_argument("--mode", default=os.environ.get("MMQG_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--cpu-samples", type=int, default=6, help="samples the CPU baseline leg times")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--probe", type=int, default=1, help="kernel class the roofline probe times (see mmqg.h)")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"], "tflops": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def flops_per_sample(d):
+    """Algorithmic FLOPs of one forward; train = 3x."""
+    G = 4 * d.H
+    text = d.T_t * 2 * G * ((d.E + d.H) + (d.L - 1) * 2 * d.H)
+    video = d.T_v * 2 * 4 * d.H_v * (d.F_v + d.H_v)
+    dec = d.T_q * (2 * (d.E + d.H) * (d.TM + 2 * d.AM) + 2 * (d.T_t * d.H + d.T_v * d.H_a + d.T_v * d.H_v)
+                   + 2 * G * ((d.E + d.H + d.H_a + d.H_v) + d.H + (d.L - 1) * 2 * d.H) + 2 * d.H * d.V)
+    return text + video + dec
+
+
+def cpu_reference_samples_per_s(d, n_samples, seed=0):
+    """The reference's per-sample train iteration (train.py:149-177: zero_grad, encoder,
+    teacher-forced decoder, loss.backward()) on the host cores, via the oracle's per-sample
+    port (stock torch.nn modules, same call granularity).  The reference itself cannot
+    travel to the GPU box (/root/reference is absent there), hence kind = "port"."""
+    from mmqg.dims import Dims
+    from mmqg.synth import make_batch, make_params
+    from oracle.ref_loop import RefModules, train_samples
+    dd = Dims(**{**d.asdict(), "B": n_samples})
+    params = make_params(dd, seed=seed)
+    batch = make_batch(dd, seed=1234)
+    ref = RefModules(params, dd.L, dropout_p=0.0)
+    ref.train()
+    train_samples(ref, batch, 1)                       # warm-up (oneDNN primitive caches)
+    t0 = time.perf_counter()
+    train_samples(ref, batch, n_samples)
+    dt = time.perf_counter() - t0
+    return n_samples / dt, dt
+
+
+def run_reference(args, d, rank, world):
+    """--impl reference: the CPU path timed on the host cores, same metric/config keys."""
+    if rank != 0:
+        return
+    per_step = max(1, args.cpu_samples // 2)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_samples_per_s(d, 1)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        sps, dt = cpu_reference_samples_per_s(d, per_step)
+        t_total += dt
+        n_total += per_step
+    v = n_total / t_total
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "train samples/sec (fwd+bwd)", "value": v, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(d, args, world),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} samples per step x {args.steps} steps of the per-sample reference loop "
+                                   f"(train.py:149-177 semantics, stock torch.nn modules) at the config's lengths; "
+                                   f"per-sample cost is independent of B"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(d, args, world):
+    return {"workload": f"BASELINE.json configs[{args.config - 1}]: teacher-forced train step fwd+bwd, "
+                        f"B={d.B}/GPU T_t={d.T_t} T_v={d.T_v}x{d.F_v} T_a={d.T_v}x{d.H_a} T_q={d.T_q} V={d.V} "
+                        f"E={d.E} H={d.H} L={d.L} TM={d.TM} AM={d.AM}",
+            "global_batch": d.B * world, "per_gpu_batch": d.B, "parallelism": f"dp{world}",
+            "dropout_p": 0.0, "mode": args.mode,
+            "l2": "working set (2 GB activations + 111 MB weights per step) exceeds the 126 MB L2; no flush needed"}
+
+
+def main():
+    args = parse()
+    from mmqg.dims import config as cfg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    d = cfg(args.config, args.batch)
+
+    if args.impl == "reference":
+        run_reference(args, d, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from mmqg import _cabi
+    from mmqg.engine import TrainEngine, launch_count
+    from mmqg.synth import make_batch, make_params
+    from mmqg.dp import GradReducer
+
+    params = make_params(d, seed=0)
+    eng = TrainEngine(d, params, device=dev, mode=args.mode)
+    host = make_batch(d, seed=1234 + rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    dbatch = eng.to_device(host)
+    reducer = GradReducer(eng, world) if world > 1 else None
+    gscale = 1.0 / world
+
+    def one_step(b):
+        if reducer:
+            loss = eng.step(b, grad_scale=gscale, on_phase=reducer.on_phase)
+            reducer.finish()
+        else:
+            loss = eng.step(b)
+        return loss
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(dbatch)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM -------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = launch_count()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_step(dbatch)
+    e1.record()
+    barrier()
+    launches = launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end from pinned host buffers ---------------------------
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    dst = {k: torch.empty_like(v) for k, v in dbatch.items()}
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    host_loss = 0.0
+    for _ in range(args.steps):
+        for k in dst:
+            dst[k].copy_(pinned[k], non_blocking=True)
+        loss = one_step(dst)
+        host_loss = float(loss.item())                      # device -> host read of the step's result
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline probe of the dominant kernel class (separate pass, same step) ---------
+    roof = None
+    if rank == 0:
+        L = _cabi.lib()
+        _cabi.check(L.mmqg_probe_start(args.probe))
+        for _ in range(2):
+            eng.step(dbatch)                              # local only: no collectives in the probe pass
+        torch.cuda.synchronize()
+        tms, n, fl, by = C.c_double(), C.c_ulonglong(), C.c_double(), C.c_double()
+        _cabi.check(L.mmqg_probe_stop(C.byref(tms), C.byref(n), C.byref(fl), C.byref(by)))
+        pk = peaks()
+        names = {1: "per-timestep recurrent GEMM (gemm_f32_kernel, B x 4H x H class)", 2: "hoisted whole-sequence GEMM",
+                 3: "lstm_pointwise", 4: "attention step", 5: "nll_rows", 6: "embedding"}
+        if n.value and tms.value > 0:
+            if args.probe in (1, 2):
+                ach = fl.value / (tms.value * 1e-3) / 1e12
+                roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+                        "frac": ach / pk["tflops"], "traffic": None}
+            else:
+                ach = by.value / (tms.value * 1e-3) / 1e9
+                roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / pk["hbm_gbs"], "traffic": None}
+            roof.update({"kernel": names.get(args.probe), "launches_per_step": n.value // 2,
+                         "avg_launch_us": 1e3 * tms.value / n.value,
+                         "share_of_step": (tms.value / 2) / (ms / args.steps),
+                         "peak_source": pk["source"] + (" (sustained bf16 cuBLAS; this kernel is fp32 SIMT)"
+                                                        if args.probe in (1, 2) and args.mode == "fp32" else "")})
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    sps = d.B * world * args.steps / (ms * 1e-3)
+    sps_e2e = d.B * world * args.steps / (ms_e2e * 1e-3)
+    f_train = 3 * flops_per_sample(d)
+    line = {
+        "metric": "train samples/sec (fwd+bwd)", "value": sps, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
+        "config": workload_config(d, args, world),
+        "clocks": clocks,
+        "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": host_loss},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "step_tensor_frac": (f_train * sps / world) / 1e12 / peaks()["tflops"],
+        "algorithmic_gflop_per_sample": f_train / 1e9,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = cpu_reference_samples_per_s(d, args.cpu_samples)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_samples} samples of the same workload through the per-sample "
+                                          f"reference loop (train.py:149-177 semantics, stock torch.nn modules), "
+                                          f"{dt:.1f} s; host has {os.cpu_count()} cpus"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

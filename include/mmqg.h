@@ -1,0 +1,208 @@
+/*
+ * mmqg.h -- C ABI of libmmqg.so: the B200 (sm_100a) implementation of the
+ * multi-modal-qg training hot path.
+ *
+ * The reference has no native layer and no FFI: its "plugin API"
+ * for this path is the set of torch.nn.Module classes in model/encoder.py and
+ * model/decoder.py.  This header is therefore the boundary a maintainer of the
+ * reference would bind from Python with ctypes (INTEGRATION.md shows the stub); each
+ * entry point names the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer into caller-owned memory
+ *     (e.g. tensor.data_ptr()); the library never allocates, frees or retains them.
+ *   - scratch memory comes from a caller-provided workspace whose size is returned by
+ *     the matching *_workspace_bytes() function.
+ *   - `stream` is a cudaStream_t passed as void*.  All work is enqueued asynchronously
+ *     on it; there are no hidden synchronisations and no internal streams.
+ *   - return value: 0 = enqueued OK, otherwise an mmqg_status; mmqg_last_error()
+ *     gives a thread-local message.
+ *   - parameters are fp32 in PyTorch layout: LSTM weights (4H, in) row-major with gate
+ *     blocks i,f,g,o; Linear weights (out, in) (SURVEY.md section 8b state_dict contract).
+ *   - tokens are int64 (reference utils/custom_transforms.py:25).
+ */
+#ifndef MMQG_H
+#define MMQG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMQG_ABI_VERSION 1
+#define MMQG_MAX_LAYERS 4
+
+typedef enum {
+  MMQG_OK = 0,
+  MMQG_ERR_BAD_ARG = 1,      /* null pointer, non-positive size, unsupported shape */
+  MMQG_ERR_WORKSPACE = 2,    /* workspace too small */
+  MMQG_ERR_CUDA = 3,         /* a CUDA runtime call failed; see mmqg_last_error() */
+  MMQG_ERR_ARCH = 4          /* device is not sm_100 */
+} mmqg_status;
+
+/* precision modes (SURVEY.md section 8d "Precision modes") */
+#define MMQG_MODE_FP32 0     /* fp32 storage, fp32 FMA accumulation: the parity mode   */
+#define MMQG_MODE_BF16 1     /* bf16 operands on tcgen05 tensor cores, fp32 accumulate */
+
+/* Shapes (SURVEY.md section 8 symbol table; reference config.py:64-87). */
+typedef struct {
+  int B, T_t, T_v, T_q, V;
+  int E, H, L, H_a, H_v, F_v, TM, AM;
+} mmqg_dims;
+
+/* All learnable tensors on the path.  Index order of attn_*: 0=text, 1=audio, 2=video
+ * (the order AttnDecoder.forward returns the weights, reference decoder.py:107). */
+typedef struct {
+  float* emb;                                   /* (V,E)   train.py:236, shared          */
+  float* text_w_ih[MMQG_MAX_LAYERS];            /* (4H,E|H)   encoder.py:91              */
+  float* text_w_hh[MMQG_MAX_LAYERS];            /* (4H,H)                                */
+  float* text_b_ih[MMQG_MAX_LAYERS];            /* (4H)                                  */
+  float* text_b_hh[MMQG_MAX_LAYERS];
+  float* vid_w_ih;                              /* (4H_v,F_v) encoder.py:54              */
+  float* vid_w_hh;                              /* (4H_v,H_v)                            */
+  float* vid_b_ih;
+  float* vid_b_hh;
+  float* attn_w[3];                             /* (TM|AM|AM, E+H) decoder.py:64-66      */
+  float* attn_b[3];
+  float* dec_w_ih[MMQG_MAX_LAYERS];             /* (4H, E+H+H_a+H_v | H) decoder.py:69   */
+  float* dec_w_hh[MMQG_MAX_LAYERS];
+  float* dec_b_ih[MMQG_MAX_LAYERS];
+  float* dec_b_hh[MMQG_MAX_LAYERS];
+  float* out_w;                                 /* (V,H)   decoder.py:70                 */
+  float* out_b;                                 /* (V)                                   */
+} mmqg_tensors;                                 /* used for parameters and for gradients */
+
+/* One uniform-length batch (features in place of raw media). */
+typedef struct {
+  const int64_t* context;    /* (B,T_t)      token ids            train.py:164-165 */
+  const int64_t* target;     /* (B,T_q)      question + <end>     train.py:174-175 */
+  const float* frames;       /* (B,T_v,F_v)  frame features       encoder.py:69    */
+  const float* audio;        /* (B,T_v,H_a)  VGGish features      encoder.py:122   */
+} mmqg_batch;
+
+int mmqg_abi_version(void);
+const char* mmqg_last_error(void);
+/* 0 if device `dev` can run this library (compute capability 10.x), else MMQG_ERR_ARCH. */
+int mmqg_device_ok(int dev);
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
+unsigned long long mmqg_launch_count(void);
+
+/* Timing probe for bench.py's roofline figure: CUDA events are recorded around every launch
+ * of ONE kernel class on the launching stream.  Classes: 1 per-timestep recurrent products,
+ * 2 hoisted whole-sequence products, 3 LSTM cell pointwise, 4 attention step, 5 loss rows,
+ * 6 embedding gather/scatter.  mmqg_probe_stop() waits for the recorded events and returns
+ * the summed kernel time, the number of launches and the algorithmic FLOPs / bytes the
+ * launches were booked with.  Not for use under CUDA-graph capture. */
+int mmqg_probe_start(int kernel_class);
+int mmqg_probe_stop(double* total_ms, unsigned long long* launches, double* flops, double* bytes);
+
+/* ---- whole-path entry points (what bench.py and the sequence-level modules call) ---- */
+
+size_t mmqg_train_workspace_bytes(const mmqg_dims* d, int mode);
+
+/* Teacher-forced forward over the whole batch: encoder (reference encoder.py:95-100,69;
+ * train.py:153-166), T_q decoder steps (decoder.py:74-107) and the summed batch-mean
+ * cross entropy (train.py:171-175).  loss_out: device float[1] = sum_t mean_b NLL.
+ * If want_grads != 0 the loss head also produces d loss/d h_top, d out_w, d out_b
+ * (logits are produced and consumed in row chunks and never stored in full);
+ * grad_scale multiplies every gradient (use B_local/B_global for data parallelism,
+ * 1.0 otherwise).  dropout_p is torch.nn.LSTM's inter-layer dropout (0 disables). */
+int mmqg_train_forward(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,
+                       void* workspace, size_t workspace_bytes, float* loss_out,
+                       int want_grads, mmqg_tensors* grads, float grad_scale,
+                       float dropout_p, unsigned long long seed, int mode, void* stream);
+
+/* Backward of the same step (reference train.py:177).  `phase` selects which gradient
+ * groups to produce, in the order they become final, so the caller can start the
+ * all-reduce of one group while the next is computed:
+ *   1 decoder (attention Linears, decoder LSTM; also d/d memories, d/d encoder state)
+ *   2 video LSTM      3 text LSTM + shared embedding
+ * Phases must be called in order 1,2,3 (2 and 3 are independent of each other).
+ * Every gradient tensor is overwritten, not accumulated (the reference zeroes grads
+ * every iteration, train.py:149-151). */
+int mmqg_train_backward(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,
+                        void* workspace, size_t workspace_bytes, mmqg_tensors* grads,
+                        int phase, float dropout_p, unsigned long long seed, int mode, void* stream);
+
+size_t mmqg_greedy_workspace_bytes(const mmqg_dims* d, int max_len, int mode);
+
+/* Greedy decode (reference train.py:101-110, evaluate.py:70-80): encoder pass, then
+ * max_len decoder steps feeding back argmax(logits) (lowest index on ties).
+ * tokens_out: device int64 (B,max_len).  d->T_q is ignored. */
+int mmqg_greedy_decode(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,
+                       void* workspace, size_t workspace_bytes, int64_t* tokens_out, int max_len,
+                       int mode, void* stream);
+
+/* ---- building blocks (what the step-wise drop-in modules call) ---- */
+
+/* C(M,N) = alpha * op(A) op(B) [+ op(A2) op(B2)] + beta * Cin + bias(N).
+ * Row-major with leading dimensions.  transA: A is stored (K,M); transB: B is stored
+ * (N,K) (the PyTorch Linear / LSTM weight layout).  A2/B2 (K2 > 0) extend the
+ * reduction with a second operand pair, e.g. x W_ih^T + h W_hh^T (replaces the addmm
+ * pairs inside aten::lstm and decoder.py:78,84,92,106). */
+typedef struct {
+  const float* A; const float* B; int lda, ldb, K;
+  const float* A2; const float* B2; int lda2, ldb2, K2;
+  float* C; int ldc;
+  const float* Cin; int ldcin;
+  const float* bias;
+  int M, N;
+  float alpha, beta;
+  int transA, transB;
+  int split_k; long long c_split_stride;   /* split_k>1: slice z writes C + z*stride */
+} mmqg_gemm_args;
+int mmqg_gemm_f32(const mmqg_gemm_args* a, void* stream);
+
+/* out(n,:) = emb(idx(n),:) for n < N (embedding lookup, encoder.py:96, decoder.py:75). */
+int mmqg_embedding_gather(const float* emb, const int64_t* idx, float* out, int N, int E, int V, void* stream);
+/* demb(idx(n),:) += dx(n,:)  (dense embedding gradient). */
+int mmqg_embedding_scatter_add(float* demb, const int64_t* idx, const float* dx, int N, int E, int V, void* stream);
+
+/* LSTM cell pointwise part: gates (B,4H) hold the pre-activations x W_ih^T + h W_hh^T + b
+ * (blocks i,f,g,o) and are overwritten with the activated gates; c_prev may be NULL (zeros).
+ * c' = s(f) c + s(i) tanh(g);  h' = s(o) tanh(c').  h2 (optional) receives a second copy
+ * of h' with its own leading dimension (the attention-memory row, train.py:166). */
+int mmqg_lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc,
+                            float* h_out, int ldh, float* h2, int ldh2, int B, int H, void* stream);
+
+/* Backward of the pointwise part.  dh = sum of up to three addends (dh0 with n0 split-K
+ * partials spaced s0 apart, dh1, dh2; NULL = absent).  dc (B,H) is read as d loss/d c'
+ * (NULL = zeros) and overwritten with d loss/d c_prev.  acts (activated gates) are
+ * overwritten with d loss/d pre-activations. */
+int mmqg_lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
+                            const float* dh0, int ldh0, int n0, long long s0,
+                            const float* dh1, int ldh1, int n1, long long s1, const float* dh2, int ldh2,
+                            float* dc, int lddc, int dc_is_zero, int B, int H, void* stream);
+
+/* Three location-attention heads of one decoder step (decoder.py:78-97): scores (B,ld)
+ * hold q W^T + b for the slots [text TM | audio AM | video AM]; they are overwritten
+ * with the three softmaxes (over ALL slots of each head: the reference's length mask
+ * is a no-op).  ctx (B, H+H_a+H_v) = [a_txt M_txt ; a_aud M_aud ;
+ * a_vid M_vid] (decoder.py:99 order).  Memories are (B,TM,H), (B,AM,H_a), (B,AM,H_v);
+ * only the first T_t / T_v rows are read (the rest are zero padding, train.py:155-160). */
+int mmqg_attn_fwd(float* scores, int lds, const float* M_txt, const float* M_aud, const float* M_vid,
+                  float* ctx, int ldctx, int B, int TM, int AM, int H, int H_a, int H_v, int T_t, int T_v,
+                  void* stream);
+/* Backward: attn (B,ld) softmax outputs are overwritten with d loss/d scores; dM_txt /
+ * dM_vid (same shapes as the memories) are accumulated into (+=).  */
+int mmqg_attn_bwd(float* attn, int lds, const float* dctx, int lddctx,
+                  const float* M_txt, const float* M_aud, const float* M_vid,
+                  float* dM_txt, float* dM_vid, int B, int TM, int AM, int H, int H_a, int H_v,
+                  int T_t, int T_v, void* stream);
+
+/* Row-wise cross entropy of logits (R,V): nll(r) = logsumexp - logits(r,target(r))
+ * (train.py:174 CrossEntropyLoss).  If dlogits_scale != 0 the logits are overwritten
+ * with dlogits_scale * (softmax - onehot). */
+int mmqg_nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_stride, float* nll,
+                  int R, int V, float dlogits_scale, void* stream);
+/* tokens(r) = argmax_v logits(r,v), lowest index on ties (train.py:107-108). */
+int mmqg_argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int R, int V, void* stream);
+/* out(n) = sum_m X(m,n)  (bias gradients). */
+int mmqg_colsum(const float* X, int ldx, float* out, int M, int N, float beta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMQG_H */

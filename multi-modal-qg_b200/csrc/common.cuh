@@ -1,0 +1,77 @@
+// Shared helpers for libmmqg.so (error reporting, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <type_traits>
+#include <atomic>
+#include "../../include/mmqg.h"
+
+namespace mmqg {
+
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+int set_err(int code, const char* fmt, ...);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Kernel classes for launch accounting / the timing probe (probe.cu, mmqg_probe_start()).
+enum KernelClass {
+  KC_OTHER = 0,
+  KC_GEMM_STEP = 1,   // per-timestep recurrent products (B x 4H x H and their backward twins)
+  KC_GEMM_SEQ = 2,    // hoisted whole-sequence products (input projections, weight gradients, loss head)
+  KC_POINTWISE = 3,   // LSTM cell update / its gradient
+  KC_ATTN = 4,        // fused attention step forward / backward
+  KC_LOSS = 5,        // log-softmax + NLL (+ dlogits) over a row chunk
+  KC_EMBED = 6,       // embedding gather / scatter-add
+  KC_COUNT = 7
+};
+extern thread_local int tl_gemm_class;    // class the next gemm_f32() launch is booked under
+void probe_open(int cls, cudaStream_t st, double flops, double bytes);
+void probe_close(cudaStream_t st);
+struct StepGemmScope {                    // RAII: GEMMs issued inside are per-timestep products
+  int prev;
+  StepGemmScope() : prev(tl_gemm_class) { tl_gemm_class = KC_GEMM_STEP; }
+  ~StepGemmScope() { tl_gemm_class = prev; }
+};
+// Place directly before a launch on stream `st`; MMQG_LAUNCH_CHECK() closes it.
+#define MMQG_PROBE(cls, flops, bytes) ::mmqg::probe_open((cls), st, (double)(flops), (double)(bytes))
+
+// Call after every kernel launch: counts it and turns a launch error into a status.
+#define MMQG_LAUNCH_CHECK()                                                              \
+  do {                                                                                   \
+    ::mmqg::probe_close(st);                                                             \
+    ::mmqg::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
+    cudaError_t e_ = cudaGetLastError();                                                 \
+    if (e_ != cudaSuccess)                                                               \
+      return ::mmqg::set_err(MMQG_ERR_CUDA, "%s:%d launch failed: %s", __FILE__, __LINE__, \
+                             cudaGetErrorString(e_));                                    \
+  } while (0)
+
+#define MMQG_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return ::mmqg::set_err(MMQG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,   \
+                             cudaGetErrorString(e_));                                    \
+  } while (0)
+
+#define MMQG_REQUIRE(cond, ...)                                                          \
+  do {                                                                                   \
+    if (!(cond)) return ::mmqg::set_err(MMQG_ERR_BAD_ARG, __VA_ARGS__);                  \
+  } while (0)
+
+#define MMQG_TRY(call)                                                                   \
+  do {                                                                                   \
+    int s_ = (call);                                                                     \
+    if (s_ != 0) return s_;                                                              \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace mmqg

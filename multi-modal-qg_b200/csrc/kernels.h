@@ -1,0 +1,38 @@
+// Internal (non-ABI) declarations shared by the translation units of libmmqg.so.
+#pragma once
+#include "common.cuh"
+
+namespace mmqg {
+
+int gemm_f32(const mmqg_gemm_args& a, cudaStream_t st);
+
+int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
+                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st);
+int lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
+                       const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,
+                       const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, int B, int H,
+                       cudaStream_t st);
+int embedding_gather(const float* emb, const int64_t* idx, float* out, int ldo, int N, int E, int V, cudaStream_t st);
+int embedding_scatter_add(float* demb, const int64_t* idx, const float* dx, int N, int E, int V, cudaStream_t st);
+int nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_stride, float* nll, int R, int V,
+             float scale, cudaStream_t st);
+int argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int64_t* tokens2, int R, int V,
+                cudaStream_t st);
+int colsum(const float* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
+int add2(const float* a, const float* b, float* y, int n, cudaStream_t st);
+int build_indices(const int64_t* ctx, const int64_t* tgt, int64_t* idx_ctx, int64_t* idx_dec, int64_t* tgt_tm, int B,
+                  int T_t, int T_q, cudaStream_t st);
+int sum_scale(const float* x, int n, float scale, float* out, cudaStream_t st);
+int fill_i64(int64_t* p, int n, int64_t v, cudaStream_t st);
+
+struct AttnShape { int B, TM, AM, H, H_a, H_v, T_t, T_v; };
+int attn_fwd(float* scores, int lds, const float* M_txt, const float* M_aud, const float* M_vid, float* ctx,
+             int ldctx, const AttnShape& s, cudaStream_t st);
+int attn_bwd(const float* attn, float* ds_out, int lds, const float* dctx, int lddctx, const float* M_txt,
+             const float* M_aud, const float* M_vid, float* dM_txt, float* dM_vid, const AttnShape& s,
+             cudaStream_t st);
+// Hoisted memory gradients: dM_txt(b,j,:) = sum_t attn(t,b,j) dctx(t,b,txt part), same for video.
+int attn_dmem(const float* attn_all, int lds, const float* dctx_all, int lddctx, float* dM_txt, float* dM_vid, int T_q,
+              const AttnShape& s, cudaStream_t st);
+
+}  // namespace mmqg

@@ -1,0 +1,373 @@
+// Elementwise / row-wise kernels of the hot path (HBM- or L2-bound; fp32).
+//   lstm_pointwise_{fwd,bwd}  : the cell update of aten::lstm (reference encoder.py:69,98, decoder.py:104)
+//   embedding gather/scatter  : encoder.py:96, decoder.py:75 and embedding_dense_backward
+//   nll_rows / argmax_rows    : train.py:174 (CrossEntropyLoss), train.py:107-108 (greedy)
+//   colsum                    : bias gradients
+#include "common.cuh"
+
+namespace mmqg {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ----------------------------------------------------------------------------------------
+__global__ void lstm_pointwise_fwd_kernel(float* __restrict__ gates, int ldg, const float* __restrict__ c_prev,
+                                          int ldcp, float* __restrict__ c_out, int ldc, float* __restrict__ h_out,
+                                          int ldh, float* __restrict__ h2, int ldh2, int B, int H) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int b = idx / H, j = idx % H;
+  float* g = gates + (size_t)b * ldg;
+  float i = sigmoidf_acc(g[j]);
+  float f = sigmoidf_acc(g[H + j]);
+  float gg = tanhf(g[2 * H + j]);
+  float o = sigmoidf_acc(g[3 * H + j]);
+  float cp = c_prev ? c_prev[(size_t)b * ldcp + j] : 0.f;
+  float c = f * cp + i * gg;
+  float h = o * tanhf(c);
+  g[j] = i; g[H + j] = f; g[2 * H + j] = gg; g[3 * H + j] = o;
+  c_out[(size_t)b * ldc + j] = c;
+  h_out[(size_t)b * ldh + j] = h;
+  if (h2) h2[(size_t)b * ldh2 + j] = h;
+}
+
+__global__ void lstm_pointwise_bwd_kernel(float* __restrict__ acts, int ldg, const float* __restrict__ c_prev,
+                                          int ldcp, const float* __restrict__ c_new, int ldc,
+                                          const float* __restrict__ dh0, int ldh0, int n0, long long s0,
+                                          const float* __restrict__ dh1, int ldh1, int n1, long long s1, const float* __restrict__ dh2,
+                                          int ldh2, float* __restrict__ dc, int lddc, int dc_is_zero, int B, int H) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int b = idx / H, j = idx % H;
+  float dh = 0.f;
+  if (dh0)
+    for (int s = 0; s < n0; ++s) dh += dh0[(size_t)s * s0 + (size_t)b * ldh0 + j];
+  if (dh1)
+    for (int s = 0; s < n1; ++s) dh += dh1[(size_t)s * s1 + (size_t)b * ldh1 + j];
+  if (dh2) dh += dh2[(size_t)b * ldh2 + j];
+  float* a = acts + (size_t)b * ldg;
+  float i = a[j], f = a[H + j], gg = a[2 * H + j], o = a[3 * H + j];
+  float cp = c_prev ? c_prev[(size_t)b * ldcp + j] : 0.f;
+  float tc = tanhf(c_new[(size_t)b * ldc + j]);
+  float dct = (dc_is_zero ? 0.f : dc[(size_t)b * lddc + j]) + dh * o * (1.f - tc * tc);
+  a[j] = dct * gg * i * (1.f - i);
+  a[H + j] = dct * cp * f * (1.f - f);
+  a[2 * H + j] = dct * i * (1.f - gg * gg);
+  a[3 * H + j] = dh * tc * o * (1.f - o);
+  dc[(size_t)b * lddc + j] = dct * f;
+}
+
+// ----------------------------------------------------------------------------------------
+__global__ void embedding_gather_kernel(const float* __restrict__ emb, const int64_t* __restrict__ idx,
+                                        float* __restrict__ out, int ldo, int N, int E, int V) {
+  int n = blockIdx.x;
+  long long w = idx[n];
+  w = w < 0 ? 0 : (w >= V ? V - 1 : w);
+  const float* src = emb + (size_t)w * E;
+  float* dst = out + (size_t)n * ldo;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+}
+
+__global__ void embedding_scatter_add_kernel(float* __restrict__ demb, const int64_t* __restrict__ idx,
+                                             const float* __restrict__ dx, int N, int E, int V) {
+  int n = blockIdx.x;
+  long long w = idx[n];
+  w = w < 0 ? 0 : (w >= V ? V - 1 : w);
+  float* dst = demb + (size_t)w * E;
+  const float* src = dx + (size_t)n * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dst + e, src[e]);
+}
+
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide reductions for 256-thread blocks; result broadcast to every thread.
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = fmaxf(r, sh[w]);
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) r += sh[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) nll_rows_kernel(float* __restrict__ logits, int ldl,
+                                                       const int64_t* __restrict__ targets, long long tgt_stride,
+                                                       float* __restrict__ nll, int R, int V, float scale) {
+  __shared__ float sh[8];
+  int r = blockIdx.x;
+  float* x = logits + (size_t)r * ldl;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += 256) m = fmaxf(m, x[v]);
+  m = block_max(m, sh);
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) s += expf(x[v] - m);
+  s = block_sum(s, sh);
+  float lse = m + logf(s);
+  long long t = targets[(size_t)r * tgt_stride];
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  if (threadIdx.x == 0) nll[r] = lse - x[t];
+  if (scale != 0.f) {
+    __syncthreads();
+    for (int v = threadIdx.x; v < V; v += 256) {
+      float p = expf(x[v] - lse);
+      x[v] = scale * (p - (v == t ? 1.f : 0.f));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ logits, int ldl,
+                                                          int64_t* __restrict__ tokens, long long tok_stride,
+                                                          int64_t* __restrict__ tokens2, int R, int V) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  int r = blockIdx.x;
+  const float* x = logits + (size_t)r * ldl;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    float y = x[v];
+    if (y > bv || (y == bv && v < bi)) { bv = y; bi = v; }
+  }
+  sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      float ov = sv[threadIdx.x + o]; int oi = si[threadIdx.x + o];
+      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+        sv[threadIdx.x] = ov; si[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int64_t w = si[0] == 0x7fffffff ? 0 : si[0];
+    tokens[(size_t)r * tok_stride] = w;
+    if (tokens2) tokens2[r] = w;
+  }
+}
+
+// out(n) = beta*out(n) + sum_m X(m,n).  Block = 32 columns x 8 row lanes.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out,
+                                                     float* __restrict__ out2, int M, int N, float beta) {
+  __shared__ float sh[8][33];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int n = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (n < N)
+    for (int m = ty; m < M; m += 8) s += X[(size_t)m * ldx + n];
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][tx];
+    t += (beta != 0.f ? beta * out[n] : 0.f);
+    out[n] = t;
+    if (out2) out2[n] = t;
+  }
+}
+
+// y(n) = a(n) + b(n)
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] + b[i];
+}
+
+// Time-major token index arrays from the batch-major inputs (reference train.py:164-175):
+//   idx_ctx(t*B+b) = context(b,t);  idx_dec(t*B+b) = t==0 ? <start> : target(b,t-1);  tgt_tm(t*B+b) = target(b,t)
+__global__ void build_indices_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict__ tgt,
+                                     int64_t* __restrict__ idx_ctx, int64_t* __restrict__ idx_dec,
+                                     int64_t* __restrict__ tgt_tm, int B, int T_t, int T_q) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * T_t) {
+    int t = i / B, b = i % B;
+    idx_ctx[i] = ctx[(size_t)b * T_t + t];
+  }
+  if (tgt && i < B * T_q) {
+    int t = i / B, b = i % B;
+    idx_dec[i] = t == 0 ? 1 : tgt[(size_t)b * T_q + t - 1];
+    tgt_tm[i] = tgt[(size_t)b * T_q + t];
+  }
+}
+
+__global__ void fill_i64_kernel(int64_t* p, int n, int64_t v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// loss = scale * sum_r nll(r), single block, fixed order (deterministic).
+__global__ void __launch_bounds__(256) sum_scale_kernel(const float* __restrict__ x, int n, float scale,
+                                                        float* __restrict__ out) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += x[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+// ---------------------------------------------------------------------------- host wrappers
+int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
+                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st) {
+  MMQG_REQUIRE(gates && c_out && h_out && B > 0 && H > 0, "lstm_pointwise_fwd: bad args");
+  int n = B * H;
+  MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (c_prev ? 11 : 10) + (h2 ? 4.0 * n : 0));
+  lstm_pointwise_fwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(gates, ldg, c_prev, ldcp, c_out, ldc, h_out, ldh, h2,
+                                                               ldh2, B, H);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
+                       const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,
+                       const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, int B, int H,
+                       cudaStream_t st) {
+  MMQG_REQUIRE(acts && c_new && dc && B > 0 && H > 0, "lstm_pointwise_bwd: bad args");
+  int n = B * H;
+  MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (10 + (c_prev ? 1 : 0) + (dh0 ? n0 : 0) + (dh1 ? n1 : 0) + (dh2 ? 1 : 0)));
+  lstm_pointwise_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(acts, ldg, c_prev, ldcp, c_new, ldc, dh0, ldh0, n0, s0,
+                                                               dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, B, H);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int embedding_gather(const float* emb, const int64_t* idx, float* out, int ldo, int N, int E, int V, cudaStream_t st) {
+  MMQG_REQUIRE(emb && idx && out && N > 0 && E > 0 && V > 0 && ldo >= E, "embedding_gather: bad args");
+  MMQG_PROBE(KC_EMBED, 0, 8.0 * N * E);
+  embedding_gather_kernel<<<N, 128, 0, st>>>(emb, idx, out, ldo, N, E, V);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int embedding_scatter_add(float* demb, const int64_t* idx, const float* dx, int N, int E, int V, cudaStream_t st) {
+  MMQG_REQUIRE(demb && idx && dx && N > 0 && E > 0 && V > 0, "embedding_scatter_add: bad args");
+  MMQG_PROBE(KC_EMBED, 0, 12.0 * N * E);
+  embedding_scatter_add_kernel<<<N, 128, 0, st>>>(demb, idx, dx, N, E, V);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_stride, float* nll, int R, int V,
+             float scale, cudaStream_t st) {
+  MMQG_REQUIRE(logits && targets && nll && R > 0 && V > 0, "nll_rows: bad args");
+  MMQG_PROBE(KC_LOSS, 0, 4.0 * R * V * (scale != 0.f ? 2 : 1));
+  nll_rows_kernel<<<R, 256, 0, st>>>(logits, ldl, targets, tgt_stride, nll, R, V, scale);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int64_t* tokens2, int R, int V,
+                cudaStream_t st) {
+  MMQG_REQUIRE(logits && tokens && R > 0 && V > 0, "argmax_rows: bad args");
+  argmax_rows_kernel<<<R, 256, 0, st>>>(logits, ldl, tokens, tok_stride, tokens2, R, V);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int colsum(const float* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st) {
+  MMQG_REQUIRE(X && out && M > 0 && N > 0, "colsum: bad args");
+  colsum_kernel<<<ceil_div(N, 32), 256, 0, st>>>(X, ldx, out, out2, M, N, beta);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int add2(const float* a, const float* b, float* y, int n, cudaStream_t st) {
+  add2_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, y, n);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int build_indices(const int64_t* ctx, const int64_t* tgt, int64_t* idx_ctx, int64_t* idx_dec, int64_t* tgt_tm, int B,
+                  int T_t, int T_q, cudaStream_t st) {
+  int n = B * (T_t > T_q ? T_t : T_q);
+  build_indices_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ctx, tgt, idx_ctx, idx_dec, tgt_tm, B, T_t, T_q);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int fill_i64(int64_t* p, int n, int64_t v, cudaStream_t st) {
+  fill_i64_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p, n, v);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int sum_scale(const float* x, int n, float scale, float* out, cudaStream_t st) {
+  sum_scale_kernel<<<1, 256, 0, st>>>(x, n, scale, out);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmqg
+
+using namespace mmqg;
+
+extern "C" {
+
+int mmqg_abi_version(void) { return MMQG_ABI_VERSION; }
+const char* mmqg_last_error(void) { return g_err; }
+unsigned long long mmqg_launch_count(void) { return g_launches.load(); }
+
+int mmqg_device_ok(int dev) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return set_err(MMQG_ERR_CUDA, "cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
+  if (prop.major != 10) return set_err(MMQG_ERR_ARCH, "device %d is sm_%d%d; libmmqg is built for sm_100a only", dev,
+                                        prop.major, prop.minor);
+  return 0;
+}
+
+int mmqg_embedding_gather(const float* emb, const int64_t* idx, float* out, int N, int E, int V, void* stream) {
+  return embedding_gather(emb, idx, out, E, N, E, V, as_stream(stream));
+}
+int mmqg_embedding_scatter_add(float* demb, const int64_t* idx, const float* dx, int N, int E, int V, void* stream) {
+  return embedding_scatter_add(demb, idx, dx, N, E, V, as_stream(stream));
+}
+int mmqg_lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
+                            int ldh, float* h2, int ldh2, int B, int H, void* stream) {
+  return lstm_pointwise_fwd(gates, ldg, c_prev, ldcp, c_out, ldc, h_out, ldh, h2, ldh2, B, H, as_stream(stream));
+}
+int mmqg_lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
+                            const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,
+                            const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, int B, int H,
+                            void* stream) {
+  return lstm_pointwise_bwd(acts, ldg, c_prev, ldcp, c_new, ldc, dh0, ldh0, n0, s0, dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc,
+                            dc_is_zero, B, H, as_stream(stream));
+}
+int mmqg_nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_stride, float* nll, int R, int V,
+                  float dlogits_scale, void* stream) {
+  return nll_rows(logits, ldl, targets, tgt_stride, nll, R, V, dlogits_scale, as_stream(stream));
+}
+int mmqg_argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int R, int V, void* stream) {
+  return argmax_rows(logits, ldl, tokens, tok_stride, nullptr, R, V, as_stream(stream));
+}
+int mmqg_colsum(const float* X, int ldx, float* out, int M, int N, float beta, void* stream) {
+  return colsum(X, ldx, out, nullptr, M, N, beta, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+"""Batch data parallelism: one process per GPU, NCCL all-reduce of the gradient buckets in
+the order they become final, overlapped with the rest of the backward pass.
+
+The reference has no parallelism at all; samples are independent on
+this path, so the batch is sharded by sample with every parameter replicated and the only
+exchange step is the gradient sum.  Each rank scales its gradients by
+B_local/B_global inside the kernels (grad_scale), so the all-reduce is a plain SUM.
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradReducer:
+    def __init__(self, engine, world_size, group=None):
+        self.buckets = engine.grad_buckets
+        self.world = world_size
+        self.group = group
+        self.works = []
+
+    def on_phase(self, i):
+        """Called right after gradient group i has been enqueued on the compute stream.
+        ProcessGroupNCCL orders the collective after that work on its own stream, so it runs
+        under the kernels of the next backward phase (NVLink5/NVSwitch, one flat ring/NVLS)."""
+        self.works.append(dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Make the compute stream wait for the outstanding all-reduces."""
+        for w in self.works:
+            w.wait()
+        self.works.clear()
+
+
+def shard_batch(batch: dict, rank: int, world: int) -> dict:
+    """Contiguous per-rank slice of a global batch (samples are independent)."""
+    out = {}
+    for k, v in batch.items():
+        n = v.shape[0]
+        assert n % world == 0, f"global batch {n} not divisible by {world} ranks"
+        per = n // world
+        out[k] = v[rank * per:(rank + 1) * per].contiguous()
+    return out

@@ -1,0 +1,143 @@
+"""Sequence-level host API over libmmqg.so: one call per train step / greedy decode.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic runs in libmmqg.so.
+`TrainEngine.step()` is the batched equivalent of one iteration of the reference's hot
+loop (train.py:149-177: zero_grad, encoder, teacher-forced decoder, loss.backward()),
+`TrainEngine.greedy()` of train.py:81-110 / evaluate.py:45-104.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from .dims import Dims, param_shapes
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class TrainEngine:
+    """Holds the parameters, gradients and workspace of one replica on one GPU."""
+
+    def __init__(self, dims: Dims, params: dict, device="cuda", mode="fp32", dropout_p=0.0):
+        self.lib = _cabi.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.MmqgError("TrainEngine needs a CUDA device; there is no CPU fallback")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _cabi.check(self.lib.mmqg_device_ok(idx))
+        self.d = dims
+        self.mode = {"fp32": _cabi.MODE_FP32, "bf16": _cabi.MODE_BF16}[mode]
+        self.dropout_p = float(dropout_p)
+        shapes = param_shapes(dims)
+        self.params, self.grads = {}, {}
+        for name, shape in shapes.items():
+            t = params[name]
+            if tuple(t.shape) != tuple(shape):
+                raise _cabi.MmqgError(f"{name}: shape {tuple(t.shape)} != {shape}")
+            self.params[name] = t.detach().to(self.device, torch.float32).contiguous()
+        # Gradients live in four flat buckets, one per readiness group,
+        # so the data-parallel all-reduce is one NCCL call per group; self.grads are views.
+        self.grad_buckets = []
+        for g in range(4):
+            names = [n for n in shapes if grad_group(n) == g]
+            offs, total = {}, 0
+            for n in names:
+                offs[n] = total
+                total += (self.params[n].numel() + 63) // 64 * 64
+            flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+            for n in names:
+                self.grads[n] = flat[offs[n]:offs[n] + self.params[n].numel()].view(shapes[n])
+            self.grad_buckets.append(flat)
+        self._cd = _cabi.c_dims(dims)
+        self._cp = _cabi.c_tensors(self.params, dims.L)
+        self._cg = _cabi.c_tensors(self.grads, dims.L)
+        nbytes = self.lib.mmqg_train_workspace_bytes(C.byref(self._cd), self.mode)
+        if nbytes == 0:
+            raise _cabi.MmqgError(self.lib.mmqg_last_error().decode())
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._greedy_ws = None
+        self.seed = 0
+
+    # -- batches -------------------------------------------------------------------------
+    def to_device(self, batch: dict, non_blocking=False) -> dict:
+        out = {}
+        for k, v in batch.items():
+            want = torch.int64 if k in ("context", "target") else torch.float32
+            out[k] = v.to(self.device, want, non_blocking=non_blocking).contiguous()
+        return out
+
+    def _cbatch(self, b):
+        d = self.d
+        assert tuple(b["context"].shape) == (d.B, d.T_t) and tuple(b["frames"].shape) == (d.B, d.T_v, d.F_v)
+        assert tuple(b["audio"].shape) == (d.B, d.T_v, d.H_a)
+        for k, v in b.items():
+            assert v.is_cuda and v.is_contiguous(), k
+        tgt = b.get("target")
+        return _cabi.MmqgBatch(b["context"].data_ptr(), 0 if tgt is None else tgt.data_ptr(),
+                               b["frames"].data_ptr(), b["audio"].data_ptr())
+
+    # -- train step ----------------------------------------------------------------------
+    def forward(self, batch, want_grads=True, grad_scale=1.0):
+        cb = self._cbatch(batch)
+        assert tuple(batch["target"].shape) == (self.d.B, self.d.T_q)
+        _cabi.check(self.lib.mmqg_train_forward(
+            C.byref(self._cd), C.byref(self._cp), C.byref(cb), self.ws.data_ptr(), self.ws.numel(),
+            self.loss.data_ptr(), int(want_grads), C.byref(self._cg), float(grad_scale), self.dropout_p,
+            self.seed, self.mode, _stream_ptr()))
+        return self.loss
+
+    def backward(self, batch, phase):
+        cb = self._cbatch(batch)
+        _cabi.check(self.lib.mmqg_train_backward(
+            C.byref(self._cd), C.byref(self._cp), C.byref(cb), self.ws.data_ptr(), self.ws.numel(),
+            C.byref(self._cg), int(phase), self.dropout_p, self.seed, self.mode, _stream_ptr()))
+
+    def step(self, batch, grad_scale=1.0, on_phase=None):
+        """forward + full backward.  Gradients land in self.grads (overwritten).  on_phase(i)
+        is called after the gradient group i (0 loss head, 1 decoder, 2 video, 3 text+emb)
+        has been enqueued -- the hook the data-parallel all-reduce uses."""
+        loss = self.forward(batch, True, grad_scale)
+        if on_phase:
+            on_phase(0)
+        for ph in (1, 2, 3):
+            self.backward(batch, ph)
+            if on_phase:
+                on_phase(ph)
+        return loss
+
+    # -- greedy decode ---------------------------------------------------------------------
+    def greedy(self, batch, max_len):
+        cb = self._cbatch(batch)
+        key = int(max_len)
+        if self._greedy_ws is None or self._greedy_ws[0] != key:
+            n = self.lib.mmqg_greedy_workspace_bytes(C.byref(self._cd), key, self.mode)
+            if n == 0:
+                raise _cabi.MmqgError(self.lib.mmqg_last_error().decode())
+            ws = self.ws if n <= self.ws.numel() else torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._greedy_ws = (key, ws)
+        ws = self._greedy_ws[1]
+        toks = torch.empty(self.d.B, key, dtype=torch.int64, device=self.device)
+        _cabi.check(self.lib.mmqg_greedy_decode(
+            C.byref(self._cd), C.byref(self._cp), C.byref(cb), ws.data_ptr(), ws.numel(), toks.data_ptr(), key,
+            self.mode, _stream_ptr()))
+        return toks
+
+
+def grad_group(name: str) -> int:
+    """Readiness group of a gradient tensor: 0 loss head (final after the forward's fused
+    loss head), 1 attention Linears + decoder LSTM, 2 video LSTM, 3 text LSTM + the shared
+    embedding (final last: decoder- and encoder-side scatter-adds both land in it)."""
+    if name.startswith("dec.out_layer."):
+        return 0
+    if name.startswith("dec."):
+        return 1
+    if name.startswith("video."):
+        return 2
+    return 3
+
+
+def launch_count():
+    return int(_cabi.lib().mmqg_launch_count())

@@ -1,0 +1,163 @@
+"""Tensor-level wrappers of the libmmqg.so building blocks (include/mmqg.h, second half).
+
+Each function takes CUDA float32 tensors, passes raw pointers / leading dimensions to the
+C ABI on torch's current stream, and returns torch tensors.  They raise on CPU tensors:
+there is no fallback path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import MmqgGemmArgs, check, lib
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _cabi.MmqgError("mmqg ops need CUDA tensors (no CPU fallback)")
+        if t.dtype not in (torch.float32, torch.int64):
+            raise _cabi.MmqgError(f"unsupported dtype {t.dtype}")
+        if t.dim() >= 1 and t.stride(-1) != 1 and t.numel() > 1:
+            raise _cabi.MmqgError("innermost dimension must be contiguous")
+
+
+def _ld(t):
+    return t.stride(0) if t.dim() == 2 and t.shape[0] > 1 else t.shape[-1]
+
+
+def gemm(A, B, transA=False, transB=False, out=None, A2=None, B2=None, Cin=None, beta=1.0, bias=None,
+         alpha=1.0, split_k=1):
+    """out = alpha*(op(A)op(B) [+ op(A2)op(B2)]) + beta*Cin + bias.  2-D row-major views
+    with arbitrary row stride are accepted.  split_k>1 returns the (split_k,M,N) partials."""
+    _chk(A, B, A2, B2, Cin, bias, out)
+    M = A.shape[1] if transA else A.shape[0]
+    K = A.shape[0] if transA else A.shape[1]
+    N = B.shape[0] if transB else B.shape[1]
+    assert (B.shape[1] if transB else B.shape[0]) == K
+    if out is None:
+        out = torch.empty((split_k, M, N) if split_k > 1 else (M, N), device=A.device, dtype=torch.float32)
+    a = MmqgGemmArgs()
+    a.A, a.B, a.lda, a.ldb, a.K = A.data_ptr(), B.data_ptr(), _ld(A), _ld(B), K
+    if A2 is not None:
+        K2 = A2.shape[0] if transA else A2.shape[1]
+        a.A2, a.B2, a.lda2, a.ldb2, a.K2 = A2.data_ptr(), B2.data_ptr(), _ld(A2), _ld(B2), K2
+    a.C = out.data_ptr()
+    a.ldc = _ld(out[0]) if split_k > 1 else _ld(out)
+    if Cin is not None:
+        a.Cin, a.ldcin = Cin.data_ptr(), _ld(Cin)
+    if bias is not None:
+        a.bias = bias.data_ptr()
+    a.M, a.N, a.alpha, a.beta = M, N, alpha, beta
+    a.transA, a.transB, a.split_k = int(transA), int(transB), split_k
+    a.c_split_stride = out.stride(0) if split_k > 1 else 0
+    check(lib().mmqg_gemm_f32(C.byref(a), _st()))
+    return out
+
+
+def embedding_gather(emb, idx):
+    _chk(emb, idx)
+    idx = idx.reshape(-1).contiguous()
+    out = torch.empty(idx.numel(), emb.shape[1], device=emb.device, dtype=torch.float32)
+    check(lib().mmqg_embedding_gather(emb.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), emb.shape[1],
+                                      emb.shape[0], _st()))
+    return out
+
+
+def embedding_scatter_add(demb, idx, dx):
+    _chk(demb, idx, dx)
+    idx = idx.reshape(-1).contiguous()
+    dx = dx.contiguous()
+    check(lib().mmqg_embedding_scatter_add(demb.data_ptr(), idx.data_ptr(), dx.data_ptr(), idx.numel(),
+                                           demb.shape[1], demb.shape[0], _st()))
+    return demb
+
+
+def lstm_pointwise_fwd(gates, c_prev, h2=None):
+    """gates (B,4H) pre-activations, overwritten with the activated gates.  Returns (h, c)."""
+    _chk(gates, c_prev, h2)
+    Bn, G = gates.shape
+    H = G // 4
+    c = torch.empty(Bn, H, device=gates.device, dtype=torch.float32)
+    h = torch.empty_like(c)
+    check(lib().mmqg_lstm_pointwise_fwd(gates.data_ptr(), _ld(gates), _cabi.ptr(c_prev),
+                                        0 if c_prev is None else _ld(c_prev), c.data_ptr(), H, h.data_ptr(), H,
+                                        _cabi.ptr(h2), 0 if h2 is None else _ld(h2), Bn, H, _st()))
+    return h, c
+
+
+def lstm_pointwise_bwd(acts, c_prev, c_new, dh_parts, dh1, dh2, dc):
+    """acts (B,4H) activated gates -> overwritten with d/d pre-activations; dc (B,H) d/dc' ->
+    overwritten with d/dc_prev (dc None = zeros, a fresh buffer is returned).
+    dh_parts: (n,B,H) partial sums or None; dh1, dh2: (B,H) or None."""
+    _chk(acts, c_prev, c_new, dh_parts, dh1, dh2, dc)
+    Bn, G = acts.shape
+    H = G // 4
+    zero = dc is None
+    if zero:
+        dc = torch.empty(Bn, H, device=acts.device, dtype=torch.float32)
+    n0 = 0 if dh_parts is None else dh_parts.shape[0]
+    s0 = 0 if dh_parts is None else dh_parts.stride(0)
+    check(lib().mmqg_lstm_pointwise_bwd(
+        acts.data_ptr(), _ld(acts), _cabi.ptr(c_prev), 0 if c_prev is None else _ld(c_prev), c_new.data_ptr(),
+        _ld(c_new), _cabi.ptr(dh_parts), H, n0, s0, _cabi.ptr(dh1), 0 if dh1 is None else _ld(dh1), 1, 0,
+        _cabi.ptr(dh2), 0 if dh2 is None else _ld(dh2), dc.data_ptr(), _ld(dc), int(zero), Bn, H, _st()))
+    return acts, dc
+
+
+def attn_fwd(scores, M_txt, M_aud, M_vid, T_t, T_v, ctx=None):
+    """scores (B,S[+pad]) -> softmaxes in place; returns ctx (B,H+H_a+H_v)."""
+    _chk(scores, M_txt, M_aud, M_vid, ctx)
+    Bn, TM, H = M_txt.shape
+    AM, H_a = M_aud.shape[1:]
+    H_v = M_vid.shape[2]
+    if ctx is None:
+        ctx = torch.empty(Bn, H + H_a + H_v, device=scores.device, dtype=torch.float32)
+    check(lib().mmqg_attn_fwd(scores.data_ptr(), _ld(scores), M_txt.data_ptr(), M_aud.data_ptr(), M_vid.data_ptr(),
+                              ctx.data_ptr(), _ld(ctx), Bn, TM, AM, H, H_a, H_v, T_t, T_v, _st()))
+    return ctx
+
+
+def attn_bwd(attn, dctx, M_txt, M_aud, M_vid, dM_txt, dM_vid, T_t, T_v):
+    """attn (B,S) softmax outputs -> overwritten with d/d scores; dM_* accumulated (+=)."""
+    _chk(attn, dctx, M_txt, M_aud, M_vid, dM_txt, dM_vid)
+    Bn, TM, H = M_txt.shape
+    AM, H_a = M_aud.shape[1:]
+    H_v = M_vid.shape[2]
+    check(lib().mmqg_attn_bwd(attn.data_ptr(), _ld(attn), dctx.data_ptr(), _ld(dctx), M_txt.data_ptr(),
+                              M_aud.data_ptr(), M_vid.data_ptr(), _cabi.ptr(dM_txt), _cabi.ptr(dM_vid), Bn, TM, AM, H,
+                              H_a, H_v, T_t, T_v, _st()))
+    return attn
+
+
+def nll_rows(logits, targets, dlogits_scale=0.0):
+    _chk(logits, targets)
+    R, V = logits.shape
+    targets = targets.reshape(-1).contiguous()
+    nll = torch.empty(R, device=logits.device, dtype=torch.float32)
+    check(lib().mmqg_nll_rows(logits.data_ptr(), _ld(logits), targets.data_ptr(), 1, nll.data_ptr(), R, V,
+                              float(dlogits_scale), _st()))
+    return nll
+
+
+def argmax_rows(logits):
+    _chk(logits)
+    R, V = logits.shape
+    tok = torch.empty(R, device=logits.device, dtype=torch.int64)
+    check(lib().mmqg_argmax_rows(logits.data_ptr(), _ld(logits), tok.data_ptr(), 1, R, V, _st()))
+    return tok
+
+
+def colsum(X, out=None, beta=0.0):
+    _chk(X, out)
+    M, N = X.shape
+    if out is None:
+        out = torch.empty(N, device=X.device, dtype=torch.float32)
+    check(lib().mmqg_colsum(X.data_ptr(), _ld(X), out.data_ptr(), M, N, float(beta), _st()))
+    return out

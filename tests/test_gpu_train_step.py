@@ -1,0 +1,140 @@
+"""Whole-path parity on the GPU: loss, every gradient tensor and greedy tokens of the CUDA
+path (through the C ABI) against (1) the golden fixtures produced by the reference itself
+and (2) the CPU oracle on the same seeded inputs.  Bars (north_star): <= 1e-3 relative on
+the fp32 loss and on every gradient tensor; greedy tokens exact."""
+import pytest
+import torch
+
+from conftest import load_golden
+from mmqg.dims import Dims
+from mmqg.synth import make_batch, make_params
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from mmqg import engine
+    return engine
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def run_step(engine, d, params, batch):
+    eng = engine.TrainEngine(d, params, mode="fp32")
+    db = eng.to_device(batch)
+    loss = eng.step(db)
+    torch.cuda.synchronize()
+    return eng, float(loss), {k: v.clone() for k, v in eng.grads.items()}
+
+
+@pytest.mark.parametrize("name", ["small_a", "small_b"])
+def test_step_matches_reference_golden(eng_mod, name):
+    fx = load_golden(name)
+    d = Dims(**fx["dims"])
+    eng, loss, grads = run_step(eng_mod, d, fx["params"], fx["batch"])
+    assert abs(loss - float(fx["loss"])) < TOL * abs(float(fx["loss"]))
+    worst = max((rel(grads[k], g), k) for k, g in fx["grads"].items())
+    assert worst[0] < TOL, worst
+    # a second step on the same engine reproduces the first (grads overwritten, not accumulated)
+    loss2 = float(eng.step(eng.to_device(fx["batch"])))
+    torch.cuda.synchronize()
+    assert abs(loss2 - loss) < 1e-6 * abs(loss)
+    for k in grads:
+        assert rel(eng.grads[k], grads[k]) < 1e-5, k
+
+
+def test_step_matches_reference_full_dim_fingerprint(eng_mod):
+    fx = load_golden("full_dim")
+    d = Dims(**fx["dims"])
+    params = make_params(d, seed=fx["seed"])
+    batch = make_batch(d, seed=fx["seed"] + 1000)
+    _, loss, grads = run_step(eng_mod, d, params, batch)
+    assert abs(loss - float(fx["loss"])) < TOL * abs(float(fx["loss"]))
+    for k, fp in fx["grad_fingerprint"].items():
+        g = grads[k].double().cpu()
+        n = float(fp["norm"])
+        assert abs(float(g.norm()) - n) < TOL * n, k
+        err = (g.flatten()[fp["idx"]] - fp["vals"]).norm() / fp["vals"].norm().clamp_min(1e-30)
+        # sampled entries: relative to the tensor's RMS so tiny entries do not dominate
+        rms = n / g.numel() ** 0.5
+        assert float((g.flatten()[fp["idx"]] - fp["vals"]).abs().max()) < 5 * TOL * max(rms, float(fp["vals"].abs().max())), (k, float(err))
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=8, T_t=17, T_v=5, T_q=7, V=1003, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101),
+    dict(B=5, T_t=9, T_v=3, T_q=4, V=211, E=52, H=64, L=2, H_a=20, H_v=48, F_v=36, TM=11, AM=6),
+    dict(B=70, T_t=6, T_v=2, T_q=3, V=4100, E=20, H=128, L=1, H_a=8, H_v=64, F_v=12, TM=8, AM=3),
+])
+def test_step_matches_oracle(eng_mod, cfg):
+    from oracle import mmqg_oracle as O
+    d = Dims(**cfg)
+    params = make_params(d, seed=21)
+    batch = make_batch(d, seed=22)
+    loss_ref, grads_ref = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
+    _, loss, grads = run_step(eng_mod, d, params, batch)
+    assert abs(loss - float(loss_ref)) < TOL * abs(float(loss_ref))
+    worst = max((rel(grads[k], g), k) for k, g in grads_ref.items())
+    assert worst[0] < TOL, worst
+
+
+def test_grad_scale_and_loss_only(eng_mod):
+    fx = load_golden("small_a")
+    d = Dims(**fx["dims"])
+    eng = eng_mod.TrainEngine(d, fx["params"], mode="fp32")
+    db = eng.to_device(fx["batch"])
+    loss = float(eng.forward(db, want_grads=False))
+    assert abs(loss - float(fx["loss"])) < TOL * abs(float(fx["loss"]))
+    eng.step(db, grad_scale=0.25)
+    torch.cuda.synchronize()
+    for k, g in fx["grads"].items():
+        assert rel(eng.grads[k], 0.25 * g) < TOL, k
+
+
+@pytest.mark.parametrize("name", ["small_a", "small_b", "full_dim"])
+def test_greedy_matches_reference_golden(eng_mod, name):
+    fx = load_golden(name)
+    d = Dims(**fx["dims"])
+    gp = make_params(d, seed=fx["seed"], bias_scale=0.1, out_weight_scale=10.0)
+    batch = make_batch(d, seed=fx["seed"] + 1000)
+    eng = eng_mod.TrainEngine(d, gp, mode="fp32")
+    toks = eng.greedy(eng.to_device(batch), fx["greedy_max_len"]).cpu()
+    want = fx["greedy_tokens"]
+    # a token may legitimately differ only where the reference's own top-1/top-2 margin is
+    # below fp32 resolution of the logits; the fixtures' minimum margins are >= 1e-3.
+    assert float(fx["greedy_margins"].min()) > 5e-4
+    assert torch.equal(toks, want), (toks.tolist(), want.tolist())
+
+
+def test_greedy_matches_oracle_larger_batch(eng_mod):
+    from oracle import mmqg_oracle as O
+    d = Dims(B=24, T_t=15, T_v=4, T_q=1, V=997, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101)
+    gp = make_params(d, seed=31, bias_scale=0.1, out_weight_scale=10.0)
+    batch = make_batch(d, seed=32)
+    want, margins = O.greedy_decode(gp, batch, d.L, d.TM, d.AM, 12, return_margins=True)
+    eng = eng_mod.TrainEngine(d, gp, mode="fp32")
+    toks = eng.greedy(eng.to_device(batch), 12).cpu()
+    # compare each row up to the first step whose oracle margin is within fp32 noise
+    safe = (margins > 1e-4).long().cumprod(1).bool()
+    assert safe.float().mean() > 0.9
+    assert torch.equal(toks[safe], want[safe])
+    assert len({tuple(r) for r in want.tolist()}) > 1     # sequences are input-dependent
+
+
+def test_errors_are_loud(eng_mod):
+    from mmqg import _cabi
+    fx = load_golden("small_a")
+    d = Dims(**fx["dims"])
+    with pytest.raises(_cabi.MmqgError):
+        eng_mod.TrainEngine(d, fx["params"], device="cpu")
+    eng = eng_mod.TrainEngine(d, fx["params"], mode="fp32")
+    bad = dict(fx["batch"])
+    with pytest.raises(AssertionError):
+        eng.step({k: v for k, v in bad.items()})          # CPU tensors are rejected
