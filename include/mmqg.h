@@ -155,6 +155,26 @@ typedef struct {
 } mmqg_gemm_args;
 int mmqg_gemm_f32(const mmqg_gemm_args* a, void* stream);
 
+/* The same contraction on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32
+ * accumulation in tensor memory, operands staged by TMA).  A, B (and A2, B2) are bf16.
+ *   a_mn_major = 0: A stored (M,K) row-major;  1: A stored (K,M) row-major
+ *   b_mn_major = 0: B stored (N,K) row-major (PyTorch weight layout);  1: B stored (K,N)
+ * Base pointers must be 16-byte aligned and leading dimensions multiples of 8 elements.
+ * C is fp32 (c_bf16 = 0) or bf16 (c_bf16 = 1); Cin and bias are fp32.  split_k > 1 writes
+ * fp32 partial results C + z * c_split_stride that the caller sums. */
+typedef struct {
+  const void* A; const void* B; int lda, ldb, K;
+  const void* A2; const void* B2; int lda2, ldb2, K2;
+  int a_mn_major, b_mn_major;
+  void* C; int ldc; int c_bf16;
+  const float* Cin; int ldcin;
+  const float* bias;
+  int M, N;
+  float alpha, beta;
+  int split_k; long long c_split_stride;
+} mmqg_gemm_bf16_args;
+int mmqg_gemm_bf16(const mmqg_gemm_bf16_args* a, void* stream);
+
 /* out(n,:) = emb(idx(n),:) for n < N (embedding lookup, encoder.py:96, decoder.py:75). */
 int mmqg_embedding_gather(const float* emb, const int64_t* idx, float* out, int N, int E, int V, void* stream);
 /* demb(idx(n),:) += dx(n,:)  (dense embedding gradient). */

@@ -5,6 +5,7 @@
 namespace mmqg {
 
 int gemm_f32(const mmqg_gemm_args& a, cudaStream_t st);
+int gemm_bf16(const mmqg_gemm_bf16_args& a, cudaStream_t st);
 
 int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
                        int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st);

@@ -40,6 +40,15 @@ class MmqgGemmArgs(C.Structure):
                 ("transA", C.c_int), ("transB", C.c_int), ("split_k", C.c_int), ("c_split_stride", C.c_longlong)]
 
 
+class MmqgGemmBf16Args(C.Structure):
+    _fields_ = [("A", _fp), ("B", _fp), ("lda", C.c_int), ("ldb", C.c_int), ("K", C.c_int),
+                ("A2", _fp), ("B2", _fp), ("lda2", C.c_int), ("ldb2", C.c_int), ("K2", C.c_int),
+                ("a_mn_major", C.c_int), ("b_mn_major", C.c_int),
+                ("C", _fp), ("ldc", C.c_int), ("c_bf16", C.c_int), ("Cin", _fp), ("ldcin", C.c_int), ("bias", _fp),
+                ("M", C.c_int), ("N", C.c_int), ("alpha", C.c_float), ("beta", C.c_float),
+                ("split_k", C.c_int), ("c_split_stride", C.c_longlong)]
+
+
 # every symbol include/mmqg.h declares: name -> (restype, argtypes)
 _i, _ll, _f, _sz, _ull = C.c_int, C.c_longlong, C.c_float, C.c_size_t, C.c_ulonglong
 _P = C.POINTER
@@ -58,6 +67,7 @@ SYMBOLS = {
     "mmqg_greedy_workspace_bytes": (_sz, [_P(MmqgDims), _i, _i]),
     "mmqg_greedy_decode": (_i, [_P(MmqgDims), _P(MmqgTensors), _P(MmqgBatch), _fp, _sz, _fp, _i, _i, _fp]),
     "mmqg_gemm_f32": (_i, [_P(MmqgGemmArgs), _fp]),
+    "mmqg_gemm_bf16": (_i, [_P(MmqgGemmBf16Args), _fp]),
     "mmqg_embedding_gather": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp]),
     "mmqg_embedding_scatter_add": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp]),
     "mmqg_lstm_pointwise_fwd": (_i, [_fp, _i, _fp, _i, _fp, _i, _fp, _i, _fp, _i, _i, _i, _fp]),

@@ -22,7 +22,7 @@ def _chk(*ts):
             continue
         if not t.is_cuda:
             raise _cabi.MmqgError("mmqg ops need CUDA tensors (no CPU fallback)")
-        if t.dtype not in (torch.float32, torch.int64):
+        if t.dtype not in (torch.float32, torch.int64, torch.bfloat16):
             raise _cabi.MmqgError(f"unsupported dtype {t.dtype}")
         if t.dim() >= 1 and t.stride(-1) != 1 and t.numel() > 1:
             raise _cabi.MmqgError("innermost dimension must be contiguous")
@@ -58,6 +58,37 @@ def gemm(A, B, transA=False, transB=False, out=None, A2=None, B2=None, Cin=None,
     a.transA, a.transB, a.split_k = int(transA), int(transB), split_k
     a.c_split_stride = out.stride(0) if split_k > 1 else 0
     check(lib().mmqg_gemm_f32(C.byref(a), _st()))
+    return out
+
+
+def gemm_bf16(A, B, a_mn_major=False, b_mn_major=False, out=None, out_dtype=torch.float32, A2=None, B2=None,
+              Cin=None, beta=1.0, bias=None, alpha=1.0, split_k=1):
+    """tcgen05 GEMM on bf16 operands.  A: (M,K) or, if a_mn_major, (K,M); B: (N,K) or, if
+    b_mn_major, (K,N).  Returns fp32 or bf16 (out_dtype); split_k>1 returns fp32 partials."""
+    _chk(A, B, A2, B2, Cin, bias, out)
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    M = A.shape[1] if a_mn_major else A.shape[0]
+    K = A.shape[0] if a_mn_major else A.shape[1]
+    N = B.shape[1] if b_mn_major else B.shape[0]
+    assert (B.shape[0] if b_mn_major else B.shape[1]) == K
+    if out is None:
+        out = torch.empty((split_k, M, N) if split_k > 1 else (M, N), device=A.device, dtype=out_dtype)
+    a = _cabi.MmqgGemmBf16Args()
+    a.A, a.B, a.lda, a.ldb, a.K = A.data_ptr(), B.data_ptr(), _ld(A), _ld(B), K
+    if A2 is not None:
+        a.A2, a.B2, a.lda2, a.ldb2 = A2.data_ptr(), B2.data_ptr(), _ld(A2), _ld(B2)
+        a.K2 = A2.shape[0] if a_mn_major else A2.shape[1]
+    a.a_mn_major, a.b_mn_major = int(a_mn_major), int(b_mn_major)
+    a.C = out.data_ptr()
+    a.ldc = _ld(out[0]) if split_k > 1 else _ld(out)
+    a.c_bf16 = int(out.dtype == torch.bfloat16)
+    if Cin is not None:
+        a.Cin, a.ldcin = Cin.data_ptr(), _ld(Cin)
+    if bias is not None:
+        a.bias = bias.data_ptr()
+    a.M, a.N, a.alpha, a.beta, a.split_k = M, N, alpha, beta, split_k
+    a.c_split_stride = out.stride(0) if split_k > 1 else 0
+    check(lib().mmqg_gemm_bf16(C.byref(a), _st()))
     return out
 
 
