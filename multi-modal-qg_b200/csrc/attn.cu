@@ -9,6 +9,7 @@
 //
 // Q1: the reference's length mask is a no-op, so each softmax runs over
 // ALL TM / AM slots; only the context sums are bounded by T_t / T_v (padded rows are 0).
+#include <cuda_bf16.h>
 #include "kernels.h"
 
 namespace mmqg {
@@ -77,6 +78,11 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(float* __restrict__ score
         acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
       }
       *reinterpret_cast<float4*>(out + dst) = acc;
+      if (s.ctx16) {
+        __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(s.ctx16) + (size_t)b * s.ldctx16 + dst;
+        o16[0] = __float2bfloat16_rn(acc.x); o16[1] = __float2bfloat16_rn(acc.y);
+        o16[2] = __float2bfloat16_rn(acc.z); o16[3] = __float2bfloat16_rn(acc.w);
+      }
     }
   } else {
     for (int o = tid; o < s.H + s.H_a + s.H_v; o += 256) {
@@ -87,6 +93,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(float* __restrict__ score
       float acc = 0.f;
       for (int j = 0; j < n; ++j) acc = fmaf(w[j], base[(size_t)j * ld + h], acc);
       out[o] = acc;
+      if (s.ctx16) reinterpret_cast<__nv_bfloat16*>(s.ctx16)[(size_t)b * s.ldctx16 + o] = __float2bfloat16_rn(acc);
     }
   }
 }
@@ -129,7 +136,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* attn, float*
     float dot = 0.f;
     for (int j = lane; j < len; j += 32) dot = fmaf(a[off + j], da[off + j], dot);
     dot = wsum(dot);
-    for (int j = lane; j < len; j += 32) ds[off + j] = a[off + j] * (da[off + j] - dot);
+    for (int j = lane; j < len; j += 32) {
+      float v = a[off + j] * (da[off + j] - dot);
+      ds[off + j] = v;
+      if (s.ds16) reinterpret_cast<__nv_bfloat16*>(s.ds16)[(size_t)b * s.ldds16 + off + j] = __float2bfloat16_rn(v);
+    }
   }
   if (dM_txt) {
     float* d = dM_txt + (size_t)b * s.TM * s.H;

@@ -233,7 +233,7 @@ extern "C" {
 
 size_t mmqg_train_workspace_bytes(const mmqg_dims* d, int mode) {
   if (check_dims(d) != 0) return 0;
-  (void)mode;
+  if (mode == MMQG_MODE_BF16) return check_dims_bf16(*d) == 0 ? train_workspace_bytes_bf16(*d, d->T_q) : 0;
   return carve(*d, d->T_q, nullptr).bytes;
 }
 
@@ -251,10 +251,13 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   MMQG_TRY(check_tensors(d, params, "params"));
   MMQG_REQUIRE(batch && batch->context && batch->target && batch->frames && batch->audio, "batch: null pointer");
   MMQG_REQUIRE(workspace && loss_out, "null workspace / loss_out");
-  MMQG_REQUIRE(mode == MMQG_MODE_FP32, "mode %d not available in this build of the train path", mode);
+  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
   MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: inter-layer dropout is not implemented yet (use 0)", dropout_p);
   (void)seed;
   if (want_grads) MMQG_TRY(check_tensors(d, grads, "grads"));
+  if (mode == MMQG_MODE_BF16)
+    return train_forward_bf16(d, *params, *batch, workspace, workspace_bytes, loss_out, want_grads, grads, grad_scale,
+                              as_stream(stream));
   Ws w = carve(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
@@ -322,10 +325,12 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   MMQG_TRY(check_tensors(d, grads, "grads"));
   MMQG_REQUIRE(batch && batch->frames, "batch: null pointer");
   MMQG_REQUIRE(workspace, "null workspace");
-  MMQG_REQUIRE(mode == MMQG_MODE_FP32, "mode %d not available in this build of the train path", mode);
+  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
   MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: not implemented yet", dropout_p);
   MMQG_REQUIRE(phase >= 1 && phase <= 3, "phase %d not in 1..3", phase);
   (void)seed;
+  if (mode == MMQG_MODE_BF16)
+    return train_backward_bf16(d, *params, *batch, workspace, workspace_bytes, *grads, phase, as_stream(stream));
   Ws w = carve(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);

@@ -1,0 +1,394 @@
+// bf16 mode of the whole-path orchestration (see engine.cu for the fp32 twin and the
+// reference line map).  Same control flow and time-major layouts; every contraction runs on
+// tcgen05 tensor cores through gemm_bf16 with bf16 operands and fp32 accumulation:
+//   * weights are re-packed to bf16 once per step (derived caches of the fp32 parameters;
+//     the decoder's W_ih_l0 and the three attention Linears are split into their embedding
+//     and state/context column blocks so every TMA base is 16-byte aligned),
+//   * h sequences, gathered embeddings, contexts, gate gradients and dlogits are bf16,
+//   * pre-activations / activated gates, cell state, attention memories, softmax, losses and
+//     every gradient tensor handed back to the caller are fp32.
+// dX = dG W reuses the packed (4H,in) weight as an MN-major B operand and dW = dG^T X takes
+// both operands MN-major, so no transposed copies are ever made.
+#include "kernels.h"
+
+namespace mmqg {
+
+static const int kSplitB = 4;
+typedef uint16_t b16;   // storage type for bf16 buffers on the host side of this file
+
+struct Carver16 {
+  char* base; size_t off;
+  template <typename T> T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Ws16 {
+  int64_t *idx_ctx, *idx_dec, *tgt_tm, *idx_cur;
+  float *bsum_text[MMQG_MAX_LAYERS], *bsum_dec[MMQG_MAX_LAYERS], *bsum_vid, *attn_b_cat, *attn_dw_cat, *attn_db_cat;
+  b16 *wt_ih[MMQG_MAX_LAYERS], *wt_hh[MMQG_MAX_LAYERS], *wv_ih, *wv_hh;
+  b16 *wd_e, *wd_c, *wd_ih[MMQG_MAX_LAYERS], *wd_hh[MMQG_MAX_LAYERS], *wa_e, *wa_h, *wo;
+  b16 *x0, *frames16, *hs_text[MMQG_MAX_LAYERS], *hs_v, *e_dec, *ds16, *ctx16, *hs_dec[MMQG_MAX_LAYERS], *dlogits16;
+  b16 *dg_text[MMQG_MAX_LAYERS], *dg_v, *dg_dec[MMQG_MAX_LAYERS];
+  float *acts_text[MMQG_MAX_LAYERS], *cs_text[MMQG_MAX_LAYERS], *m_txt, *m_aud, *m_vid, *acts_v, *cs_v;
+  float *attn_all, *ds_all, *ctx_tmp, *acts_dec[MMQG_MAX_LAYERS], *cs_dec[MMQG_MAX_LAYERS], *logits, *nll, *dhtop;
+  float *dh_rec[MMQG_MAX_LAYERS], *dc[MMQG_MAX_LAYERS], *dx_above, *dq_h, *dctx_all, *dm_txt, *dm_vid, *de_dec;
+  float *dh_rec_enc, *dh_rec_vid, *dx_text, *dc_v;
+  int Sp, Ep, Vp, Rc;
+  size_t bytes;
+};
+
+static int vocab_chunk_rows16(int R, int V) {
+  long long rc = (16ll << 20) / (V > 0 ? V : 1);
+  rc = rc / 128 * 128;
+  if (rc < 128) rc = 128;
+  if (rc > R) rc = R;
+  return (int)rc;
+}
+
+static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
+  Ws16 w{};
+  Carver16 c{reinterpret_cast<char*>(base), 0};
+  const size_t B = d.B, H = d.H, G = 4 * (size_t)d.H, Hv = d.H_v, Gv = 4 * (size_t)d.H_v;
+  const int S = d.TM + 2 * d.AM;
+  w.Sp = (S + 7) / 8 * 8;
+  w.Ep = (d.E + 7) / 8 * 8;
+  w.Vp = (d.V + 7) / 8 * 8;
+  const size_t Sp = w.Sp, Ep = w.Ep, Q = d.E + d.H, C = (size_t)d.H + d.H_a + d.H_v;
+  const size_t R = (size_t)T_q * B, Rt = (size_t)d.T_t * B, Rv = (size_t)d.T_v * B;
+  w.Rc = vocab_chunk_rows16((int)R, d.V);
+  w.idx_ctx = c.take<int64_t>(Rt); w.idx_dec = c.take<int64_t>(R); w.tgt_tm = c.take<int64_t>(R);
+  w.idx_cur = c.take<int64_t>(B);
+  for (int l = 0; l < d.L; ++l) { w.bsum_text[l] = c.take<float>(G); w.bsum_dec[l] = c.take<float>(G); }
+  w.bsum_vid = c.take<float>(Gv);
+  w.attn_b_cat = c.take<float>(Sp); w.attn_dw_cat = c.take<float>(Sp * Q); w.attn_db_cat = c.take<float>(Sp);
+  for (int l = 0; l < d.L; ++l) {
+    w.wt_ih[l] = c.take<b16>(G * (l == 0 ? Ep : H)); w.wt_hh[l] = c.take<b16>(G * H);
+    w.wd_ih[l] = l == 0 ? nullptr : c.take<b16>(G * H); w.wd_hh[l] = c.take<b16>(G * H);
+  }
+  w.wv_ih = c.take<b16>(Gv * d.F_v); w.wv_hh = c.take<b16>(Gv * Hv);
+  w.wd_e = c.take<b16>(G * Ep); w.wd_c = c.take<b16>(G * C);
+  w.wa_e = c.take<b16>(Sp * Ep); w.wa_h = c.take<b16>(Sp * H);
+  w.wo = c.take<b16>((size_t)d.V * H);
+  w.x0 = c.take<b16>(Rt * Ep);
+  w.frames16 = c.take<b16>(B * d.T_v * d.F_v);
+  for (int l = 0; l < d.L; ++l) {
+    w.acts_text[l] = c.take<float>(Rt * G);
+    w.hs_text[l] = c.take<b16>((Rt + B) * H);
+    w.cs_text[l] = c.take<float>((Rt + B) * H);
+    w.dg_text[l] = c.take<b16>(Rt * G);
+  }
+  w.m_txt = c.take<float>(B * d.TM * H); w.m_aud = c.take<float>(B * d.AM * d.H_a); w.m_vid = c.take<float>(B * d.AM * Hv);
+  w.acts_v = c.take<float>(Rv * Gv); w.hs_v = c.take<b16>((Rv + B) * Hv); w.cs_v = c.take<float>((Rv + B) * Hv);
+  w.dg_v = c.take<b16>(Rv * Gv);
+  w.e_dec = c.take<b16>(R * Ep);
+  w.attn_all = c.take<float>(R * Sp); w.ds_all = c.take<float>(R * Sp); w.ds16 = c.take<b16>(R * Sp);
+  w.ctx_tmp = c.take<float>(B * C); w.ctx16 = c.take<b16>(R * C);
+  for (int l = 0; l < d.L; ++l) {
+    w.acts_dec[l] = c.take<float>(R * G);
+    w.hs_dec[l] = c.take<b16>((R + B) * H);
+    w.cs_dec[l] = c.take<float>((R + B) * H);
+    w.dg_dec[l] = c.take<b16>(R * G);
+  }
+  w.logits = c.take<float>((size_t)w.Rc * d.V);
+  w.dlogits16 = c.take<b16>((size_t)w.Rc * w.Vp);
+  w.nll = c.take<float>(R); w.dhtop = c.take<float>(R * H);
+  for (int l = 0; l < d.L; ++l) { w.dh_rec[l] = c.take<float>(kSplitB * B * H); w.dc[l] = c.take<float>(B * H); }
+  w.dx_above = c.take<float>(kSplitB * B * H); w.dq_h = c.take<float>(kSplitB * B * H);
+  w.dctx_all = c.take<float>(R * C);
+  w.dm_txt = c.take<float>(B * d.TM * H); w.dm_vid = c.take<float>(B * d.AM * Hv);
+  w.de_dec = c.take<float>(R * d.E);
+  w.dh_rec_enc = c.take<float>(kSplitB * B * H); w.dh_rec_vid = c.take<float>(kSplitB * B * Hv);
+  w.dx_text = c.take<float>(Rt * (d.E > d.H ? d.E : d.H));
+  w.dc_v = c.take<float>(B * Hv);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+size_t train_workspace_bytes_bf16(const mmqg_dims& d, int T_q) { return carve16(d, T_q, nullptr).bytes; }
+
+int check_dims_bf16(const mmqg_dims& d) {
+  MMQG_REQUIRE(d.H % 8 == 0 && d.H_v % 8 == 0 && d.H_a % 8 == 0 && d.F_v % 8 == 0,
+               "bf16 mode needs H, H_v, H_a, F_v to be multiples of 8 (TMA 16-byte rows); got %d %d %d %d", d.H, d.H_v,
+               d.H_a, d.F_v);
+  return 0;
+}
+
+// gemm_bf16 call helper ---------------------------------------------------------------------
+struct Tc {
+  mmqg_gemm_bf16_args a;
+  // A: (M,K) K-major unless amn (then stored (K,M)); B: (N,K) K-major unless bmn (then stored (K,N)).
+  Tc(const void* A, int lda, bool amn, const void* Bm, int ldb, bool bmn, int M, int N, int K, float* C, int ldc) {
+    a = mmqg_gemm_bf16_args{};
+    a.A = A; a.lda = lda; a.a_mn_major = amn; a.B = Bm; a.ldb = ldb; a.b_mn_major = bmn;
+    a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.alpha = 1.f; a.beta = 0.f; a.split_k = 1;
+  }
+  Tc& second(const void* A2, int lda2, const void* B2, int ldb2, int K2) {
+    a.A2 = A2; a.lda2 = lda2; a.B2 = B2; a.ldb2 = ldb2; a.K2 = K2; return *this;
+  }
+  Tc& accumulate(bool on) { if (on) { a.Cin = reinterpret_cast<const float*>(a.C); a.ldcin = a.ldc; a.beta = 1.f; } return *this; }
+  Tc& bias(const float* b) { a.bias = b; return *this; }
+  Tc& split(int s, long long stride) { a.split_k = s; a.c_split_stride = stride; return *this; }
+  int run(cudaStream_t st) { return gemm_bf16(a, st); }
+};
+
+static AttnShape attn_shape16(const mmqg_dims& d) { return AttnShape{d.B, d.TM, d.AM, d.H, d.H_a, d.H_v, d.T_t, d.T_v}; }
+
+// fp32 parameters -> packed bf16 caches + summed biases + concatenated attention bias
+static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cudaStream_t st) {
+  const int H = d.H, G = 4 * d.H, Hv = d.H_v, Gv = 4 * d.H_v, E = d.E, Ep = w.Ep, Q = d.E + d.H;
+  const int C = d.H + d.H_a + d.H_v, X0 = E + C, Sp = w.Sp;
+  for (int l = 0; l < d.L; ++l) {
+    const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
+    MMQG_TRY(cvt_f32_bf16_2d(P.text_w_ih[l], I, w.wt_ih[l], Ip, G, I, Ip, st));
+    MMQG_TRY(cvt_f32_bf16_2d(P.text_w_hh[l], H, w.wt_hh[l], H, G, H, H, st));
+    MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_hh[l], H, w.wd_hh[l], H, G, H, H, st));
+    if (l > 0) MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[l], H, w.wd_ih[l], H, G, H, H, st));
+    MMQG_TRY(add2(P.text_b_ih[l], P.text_b_hh[l], w.bsum_text[l], G, st));
+    MMQG_TRY(add2(P.dec_b_ih[l], P.dec_b_hh[l], w.bsum_dec[l], G, st));
+  }
+  MMQG_TRY(cvt_f32_bf16_2d(P.vid_w_ih, d.F_v, w.wv_ih, d.F_v, Gv, d.F_v, d.F_v, st));
+  MMQG_TRY(cvt_f32_bf16_2d(P.vid_w_hh, Hv, w.wv_hh, Hv, Gv, Hv, Hv, st));
+  MMQG_TRY(add2(P.vid_b_ih, P.vid_b_hh, w.bsum_vid, Gv, st));
+  MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[0], X0, w.wd_e, Ep, G, E, Ep, st));
+  MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[0] + E, X0, w.wd_c, C, G, C, C, st));
+  MMQG_CUDA(cudaMemsetAsync(w.wa_e, 0, sizeof(b16) * (size_t)Sp * Ep, st));
+  MMQG_CUDA(cudaMemsetAsync(w.wa_h, 0, sizeof(b16) * (size_t)Sp * H, st));
+  MMQG_CUDA(cudaMemsetAsync(w.attn_b_cat, 0, sizeof(float) * Sp, st));
+  const int off[3] = {0, d.TM, d.TM + d.AM}, len[3] = {d.TM, d.AM, d.AM};
+  for (int i = 0; i < 3; ++i) {
+    MMQG_TRY(cvt_f32_bf16_2d(P.attn_w[i], Q, w.wa_e + (size_t)off[i] * Ep, Ep, len[i], E, Ep, st));
+    MMQG_TRY(cvt_f32_bf16_2d(P.attn_w[i] + E, Q, w.wa_h + (size_t)off[i] * H, H, len[i], H, H, st));
+    MMQG_CUDA(cudaMemcpyAsync(w.attn_b_cat + off[i], P.attn_b[i], sizeof(float) * len[i], cudaMemcpyDeviceToDevice, st));
+  }
+  MMQG_TRY(cvt_f32_bf16_2d(P.out_w, H, w.wo, H, d.V, H, H, st));
+  return 0;
+}
+
+static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, Ws16& w, cudaStream_t st) {
+  const int B = d.B, H = d.H, G = 4 * d.H, Hv = d.H_v, Gv = 4 * d.H_v;
+  MMQG_CUDA(cudaMemcpy2DAsync(w.m_aud, sizeof(float) * (size_t)d.AM * d.H_a, bt.audio,
+                              sizeof(float) * (size_t)d.T_v * d.H_a, sizeof(float) * (size_t)d.T_v * d.H_a, B,
+                              cudaMemcpyDeviceToDevice, st));
+  // video LSTM (encoder.py:69)
+  MMQG_TRY(cvt_f32_bf16_2d(bt.frames, d.F_v, w.frames16, d.F_v, (long long)B * d.T_v, d.F_v, d.F_v, st));
+  for (int t = 0; t < d.T_v; ++t) {
+    StepGemmScope step_scope;
+    float* acts = w.acts_v + (size_t)t * B * Gv;
+    Tc g(w.frames16 + (size_t)t * d.F_v, d.T_v * d.F_v, false, w.wv_ih, d.F_v, false, B, Gv, d.F_v, acts, Gv);
+    g.bias(w.bsum_vid);
+    if (t > 0) g.second(w.hs_v + (size_t)t * B * Hv, Hv, w.wv_hh, Hv, Hv);
+    MMQG_TRY(g.run(st));
+    MMQG_TRY(lstm_pointwise_fwd_bf16(acts, Gv, t > 0 ? w.cs_v + (size_t)t * B * Hv : nullptr, Hv,
+                                     w.cs_v + (size_t)(t + 1) * B * Hv, Hv, w.hs_v + (size_t)(t + 1) * B * Hv, Hv,
+                                     w.m_vid + (size_t)t * Hv, d.AM * Hv, B, Hv, st));
+  }
+  // text LSTM stack (encoder.py:95-100): hoisted input projection per layer, recurrent part per step
+  MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_ctx, w.x0, w.Ep, d.T_t * B, d.E, w.Ep, d.V, st));
+  for (int l = 0; l < d.L; ++l) {
+    const b16* X = l == 0 ? w.x0 : w.hs_text[l - 1] + (size_t)B * H;
+    const int Ip = l == 0 ? w.Ep : H;
+    MMQG_TRY(Tc(X, Ip, false, w.wt_ih[l], Ip, false, d.T_t * B, G, Ip, w.acts_text[l], G).bias(w.bsum_text[l]).run(st));
+    for (int t = 0; t < d.T_t; ++t) {
+      StepGemmScope step_scope;
+      float* acts = w.acts_text[l] + (size_t)t * B * G;
+      if (t > 0)
+        MMQG_TRY(Tc(w.hs_text[l] + (size_t)t * B * H, H, false, w.wt_hh[l], H, false, B, G, H, acts, G).accumulate(true).run(st));
+      MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr, H,
+                                       w.cs_text[l] + (size_t)(t + 1) * B * H, H, w.hs_text[l] + (size_t)(t + 1) * B * H, H,
+                                       l == d.L - 1 ? w.m_txt + (size_t)t * H : nullptr, d.TM * H, B, H, st));
+    }
+  }
+  // decoder state slab 0 := encoder final state (train.py:169)
+  const size_t n = (size_t)B * H;
+  for (int l = 0; l < d.L; ++l) {
+    MMQG_CUDA(cudaMemcpyAsync(w.hs_dec[l], w.hs_text[l] + (size_t)d.T_t * n, sizeof(b16) * n, cudaMemcpyDeviceToDevice, st));
+    MMQG_CUDA(cudaMemcpyAsync(w.cs_dec[l], w.cs_text[l] + (size_t)d.T_t * n, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                       size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
+                       cudaStream_t st) {
+  MMQG_TRY(check_dims_bf16(d));
+  Ws16 w = carve16(d, d.T_q, workspace);
+  if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
+  const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, R = d.T_q * B, Sp = w.Sp, Ep = w.Ep;
+
+  MMQG_TRY(build_indices(bt.context, bt.target, w.idx_ctx, w.idx_dec, w.tgt_tm, B, d.T_t, d.T_q, st));
+  MMQG_TRY(pack_weights(d, P, w, st));
+  MMQG_TRY(encoder_forward16(d, P, bt, w, st));
+
+  // decoder: hoisted embedding-column products over all teacher-forced steps
+  MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_dec, w.e_dec, Ep, R, d.E, Ep, d.V, st));
+  MMQG_TRY(Tc(w.e_dec, Ep, false, w.wd_e, Ep, false, R, G, Ep, w.acts_dec[0], G).bias(w.bsum_dec[0]).run(st));
+  MMQG_TRY(Tc(w.e_dec, Ep, false, w.wa_e, Ep, false, R, Sp, Ep, w.attn_all, Sp).bias(w.attn_b_cat).run(st));
+  AttnShape as = attn_shape16(d);
+  as.ldctx16 = C;
+  for (int t = 0; t < d.T_q; ++t) {
+    StepGemmScope step_scope;
+    const b16* htop_prev = w.hs_dec[d.L - 1] + (size_t)t * B * H;
+    float* sc = w.attn_all + (size_t)t * B * Sp;
+    b16* ctx = w.ctx16 + (size_t)t * B * C;
+    MMQG_TRY(Tc(htop_prev, H, false, w.wa_h, H, false, B, Sp, H, sc, Sp).accumulate(true).run(st));
+    as.ctx16 = ctx;
+    MMQG_TRY(attn_fwd(sc, Sp, w.m_txt, w.m_aud, w.m_vid, w.ctx_tmp, C, as, st));
+    for (int l = 0; l < d.L; ++l) {
+      float* acts = w.acts_dec[l] + (size_t)t * B * G;
+      const b16* hprev = w.hs_dec[l] + (size_t)t * B * H;
+      if (l == 0)
+        MMQG_TRY(Tc(ctx, C, false, w.wd_c, C, false, B, G, C, acts, G).second(hprev, H, w.wd_hh[0], H, H).accumulate(true).run(st));
+      else
+        MMQG_TRY(Tc(w.hs_dec[l - 1] + (size_t)(t + 1) * B * H, H, false, w.wd_ih[l], H, false, B, G, H, acts, G)
+                     .second(hprev, H, w.wd_hh[l], H, H).bias(w.bsum_dec[l]).run(st));
+      MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
+                                       w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st));
+    }
+  }
+  // loss head in row chunks: logits (fp32, chunk only) -> NLL (+ bf16 dlogits -> dH, dW_out, db_out)
+  const b16* htop = w.hs_dec[d.L - 1] + (size_t)B * H;
+  const float dscale = want_grads ? grad_scale / (float)B : 0.f;
+  for (int r0 = 0, first = 1; r0 < R; r0 += w.Rc, first = 0) {
+    const int rc = R - r0 < w.Rc ? R - r0 : w.Rc;
+    MMQG_TRY(Tc(htop + (size_t)r0 * H, H, false, w.wo, H, false, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(st));
+    MMQG_TRY(nll_rows_bf16(w.logits, d.V, w.tgt_tm + r0, w.nll + r0, rc, d.V, dscale, want_grads ? w.dlogits16 : nullptr,
+                           w.Vp, st));
+    if (want_grads) {
+      MMQG_TRY(Tc(w.dlogits16, w.Vp, false, w.wo, H, true, rc, H, d.V, w.dhtop + (size_t)r0 * H, H).run(st));
+      MMQG_TRY(Tc(w.dlogits16, w.Vp, true, htop + (size_t)r0 * H, H, true, d.V, H, rc, grads->out_w, H).accumulate(!first).run(st));
+      MMQG_TRY(colsum_bf16(w.dlogits16, w.Vp, grads->out_b, nullptr, rc, d.V, first ? 0.f : 1.f, st));
+    }
+  }
+  MMQG_TRY(sum_scale(w.nll, R, 1.0f / (float)B, loss_out, st));
+  return 0;
+}
+
+int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                        size_t workspace_bytes, mmqg_tensors& Gd, int phase, cudaStream_t st) {
+  MMQG_TRY(check_dims_bf16(d));
+  Ws16 w = carve16(d, d.T_q, workspace);
+  if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
+  const int B = d.B, H = d.H, G = 4 * d.H, E = d.E, Ep = w.Ep, Q = d.E + d.H, C = d.H + d.H_a + d.H_v, X0 = E + C;
+  const int R = d.T_q * B, Sp = w.Sp, L = d.L;
+  const long long ps = (long long)B * H;
+  AttnShape as = attn_shape16(d);
+  as.ldds16 = Sp;
+
+  if (phase == 1) {
+    MMQG_CUDA(cudaMemsetAsync(w.ds_all, 0, sizeof(float) * (size_t)R * Sp, st));
+    MMQG_CUDA(cudaMemsetAsync(w.ds16, 0, sizeof(b16) * (size_t)R * Sp, st));
+    for (int t = d.T_q - 1; t >= 0; --t) {
+      StepGemmScope step_scope;
+      const bool last = t == d.T_q - 1;
+      for (int l = L - 1; l >= 0; --l) {
+        const float* acts = w.acts_dec[l] + (size_t)t * B * G;
+        b16* dg = w.dg_dec[l] + (size_t)t * B * G;
+        const float* dh0 = last ? nullptr : w.dh_rec[l];
+        const float* dh1 = nullptr; int n1 = 0;
+        const float* dh2 = nullptr;
+        if (l == L - 1) {
+          dh2 = w.dhtop + (size_t)t * B * H;
+          if (!last) { dh1 = w.dq_h; n1 = kSplitB; }
+        } else {
+          dh1 = w.dx_above; n1 = kSplitB;
+        }
+        MMQG_TRY(lstm_pointwise_bwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H,
+                                         H, dh0, H, kSplitB, ps, dh1, H, n1, ps, dh2, H, w.dc[l], H, last ? 1 : 0, dg, G, B,
+                                         H, st));
+        MMQG_TRY(Tc(dg, G, false, w.wd_hh[l], H, true, B, H, G, w.dh_rec[l], H).split(kSplitB, ps).run(st));
+        if (l > 0)
+          MMQG_TRY(Tc(dg, G, false, w.wd_ih[l], H, true, B, H, G, w.dx_above, H).split(kSplitB, ps).run(st));
+        else
+          MMQG_TRY(Tc(dg, G, false, w.wd_c, C, true, B, C, G, w.dctx_all + (size_t)t * B * C, C).run(st));
+      }
+      float* ds = w.ds_all + (size_t)t * B * Sp;
+      as.ds16 = w.ds16 + (size_t)t * B * Sp;
+      MMQG_TRY(attn_bwd(w.attn_all + (size_t)t * B * Sp, ds, Sp, w.dctx_all + (size_t)t * B * C, C, w.m_txt, w.m_aud, w.m_vid,
+                        nullptr, nullptr, as, st));
+      MMQG_TRY(Tc(as.ds16, Sp, false, w.wa_h, H, true, B, H, Sp, w.dq_h, H).split(kSplitB, ps).run(st));
+    }
+    for (int l = 0; l < L; ++l) {
+      const b16* dG = w.dg_dec[l];
+      MMQG_TRY(Tc(dG, G, true, w.hs_dec[l], H, true, G, H, R, Gd.dec_w_hh[l], H).run(st));
+      if (l > 0) {
+        MMQG_TRY(Tc(dG, G, true, w.hs_dec[l - 1] + (size_t)B * H, H, true, G, H, R, Gd.dec_w_ih[l], H).run(st));
+      } else {
+        MMQG_TRY(Tc(dG, G, true, w.e_dec, Ep, true, G, E, R, Gd.dec_w_ih[0], X0).run(st));
+        MMQG_TRY(Tc(dG, G, true, w.ctx16, C, true, G, C, R, Gd.dec_w_ih[0] + E, X0).run(st));
+      }
+      MMQG_TRY(colsum_bf16(dG, G, Gd.dec_b_ih[l], Gd.dec_b_hh[l], R, G, 0.f, st));
+    }
+    MMQG_TRY(attn_dmem(w.attn_all, Sp, w.dctx_all, C, w.dm_txt, w.dm_vid, d.T_q, as, st));
+    MMQG_TRY(Tc(w.ds16, Sp, true, w.e_dec, Ep, true, Sp, E, R, w.attn_dw_cat, Q).run(st));
+    MMQG_TRY(Tc(w.ds16, Sp, true, w.hs_dec[L - 1], H, true, Sp, H, R, w.attn_dw_cat + E, Q).run(st));
+    MMQG_TRY(colsum(w.ds_all, Sp, w.attn_db_cat, nullptr, R, Sp, 0.f, st));
+    const int off[3] = {0, d.TM, d.TM + d.AM}, len[3] = {d.TM, d.AM, d.AM};
+    for (int i = 0; i < 3; ++i) {
+      MMQG_CUDA(cudaMemcpyAsync(Gd.attn_w[i], w.attn_dw_cat + (size_t)off[i] * Q, sizeof(float) * (size_t)len[i] * Q,
+                                cudaMemcpyDeviceToDevice, st));
+      MMQG_CUDA(cudaMemcpyAsync(Gd.attn_b[i], w.attn_db_cat + off[i], sizeof(float) * len[i], cudaMemcpyDeviceToDevice, st));
+    }
+    MMQG_TRY(Tc(w.dg_dec[0], G, false, w.wd_e, Ep, true, R, E, G, w.de_dec, E).second(w.ds16, Sp, w.wa_e, Ep, Sp).run(st));
+    MMQG_CUDA(cudaMemsetAsync(Gd.emb, 0, sizeof(float) * (size_t)d.V * E, st));
+    MMQG_TRY(embedding_scatter_add(Gd.emb, w.idx_dec, w.de_dec, R, E, d.V, st));
+    return 0;
+  }
+
+  if (phase == 2) {
+    const int Hv = d.H_v, Gv = 4 * d.H_v;
+    const long long pv = (long long)B * Hv;
+    for (int t = d.T_v - 1; t >= 0; --t) {
+      StepGemmScope step_scope;
+      const bool last = t == d.T_v - 1;
+      b16* dg = w.dg_v + (size_t)t * B * Gv;
+      MMQG_TRY(lstm_pointwise_bwd_bf16(w.acts_v + (size_t)t * B * Gv, Gv, t > 0 ? w.cs_v + (size_t)t * B * Hv : nullptr, Hv,
+                                       w.cs_v + (size_t)(t + 1) * B * Hv, Hv, last ? nullptr : w.dh_rec_vid, Hv, kSplitB, pv,
+                                       nullptr, 0, 0, 0, w.dm_vid + (size_t)t * Hv, d.AM * Hv, w.dc_v, Hv, last ? 1 : 0, dg,
+                                       Gv, B, Hv, st));
+      if (t > 0) MMQG_TRY(Tc(dg, Gv, false, w.wv_hh, Hv, true, B, Hv, Gv, w.dh_rec_vid, Hv).split(kSplitB, pv).run(st));
+    }
+    if (d.T_v > 1)
+      MMQG_TRY(Tc(w.dg_v + (size_t)B * Gv, Gv, true, w.hs_v + (size_t)B * Hv, Hv, true, Gv, Hv, (d.T_v - 1) * B, Gd.vid_w_hh, Hv).run(st));
+    else
+      MMQG_CUDA(cudaMemsetAsync(Gd.vid_w_hh, 0, sizeof(float) * (size_t)Gv * Hv, st));
+    for (int t = 0; t < d.T_v; ++t)
+      MMQG_TRY(Tc(w.dg_v + (size_t)t * B * Gv, Gv, true, w.frames16 + (size_t)t * d.F_v, d.T_v * d.F_v, true, Gv, d.F_v, B,
+                  Gd.vid_w_ih, d.F_v).accumulate(t > 0).run(st));
+    MMQG_TRY(colsum_bf16(w.dg_v, Gv, Gd.vid_b_ih, Gd.vid_b_hh, d.T_v * B, Gv, 0.f, st));
+    return 0;
+  }
+
+  for (int l = L - 1; l >= 0; --l) {
+    const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
+    for (int t = d.T_t - 1; t >= 0; --t) {
+      StepGemmScope step_scope;
+      const bool last = t == d.T_t - 1;
+      b16* dg = w.dg_text[l] + (size_t)t * B * G;
+      const float* dh0 = last ? w.dh_rec[l] : w.dh_rec_enc;
+      const float* dh1 = (last && l == L - 1) ? w.dq_h : nullptr;
+      const float* dh2 = l == L - 1 ? w.dm_txt + (size_t)t * H : w.dx_text + (size_t)t * B * H;
+      const int ldh2 = l == L - 1 ? d.TM * H : H;
+      MMQG_TRY(lstm_pointwise_bwd_bf16(w.acts_text[l] + (size_t)t * B * G, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr,
+                                       H, w.cs_text[l] + (size_t)(t + 1) * B * H, H, dh0, H, kSplitB, ps, dh1, H, kSplitB, ps,
+                                       dh2, ldh2, w.dc[l], H, 0, dg, G, B, H, st));
+      if (t > 0) MMQG_TRY(Tc(dg, G, false, w.wt_hh[l], H, true, B, H, G, w.dh_rec_enc, H).split(kSplitB, ps).run(st));
+    }
+    const b16* dG = w.dg_text[l];
+    const b16* X = l == 0 ? w.x0 : w.hs_text[l - 1] + (size_t)B * H;
+    MMQG_TRY(Tc(dG, G, true, X, Ip, true, G, I, d.T_t * B, Gd.text_w_ih[l], I).run(st));
+    if (d.T_t > 1)
+      MMQG_TRY(Tc(dG + (size_t)B * G, G, true, w.hs_text[l] + (size_t)B * H, H, true, G, H, (d.T_t - 1) * B, Gd.text_w_hh[l], H).run(st));
+    else
+      MMQG_CUDA(cudaMemsetAsync(Gd.text_w_hh[l], 0, sizeof(float) * (size_t)G * H, st));
+    MMQG_TRY(colsum_bf16(dG, G, Gd.text_b_ih[l], Gd.text_b_hh[l], d.T_t * B, G, 0.f, st));
+    MMQG_TRY(Tc(dG, G, false, w.wt_ih[l], Ip, true, d.T_t * B, I, G, w.dx_text, I).run(st));
+  }
+  MMQG_TRY(embedding_scatter_add(Gd.emb, w.idx_ctx, w.dx_text, d.T_t * B, E, d.V, st));
+  return 0;
+}
+
+}  // namespace mmqg

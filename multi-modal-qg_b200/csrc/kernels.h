@@ -26,7 +26,35 @@ int build_indices(const int64_t* ctx, const int64_t* tgt, int64_t* idx_ctx, int6
 int sum_scale(const float* x, int n, float scale, float* out, cudaStream_t st);
 int fill_i64(int64_t* p, int n, int64_t v, cudaStream_t st);
 
-struct AttnShape { int B, TM, AM, H, H_a, H_v, T_t, T_v; };
+struct AttnShape {
+  int B, TM, AM, H, H_a, H_v, T_t, T_v;
+  // bf16 mode: optional bf16 copies of the outputs that feed tensor-core GEMMs
+  void* ctx16; int ldctx16;     // attn_fwd: contexts
+  void* ds16; int ldds16;       // attn_bwd: d loss / d scores
+};
+
+// bf16-mode elementwise kernels (pointwise_bf16.cu)
+int cvt_f32_bf16_2d(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
+                    int cols_dst, cudaStream_t st);
+int embedding_gather_bf16(const float* emb, const int64_t* idx, void* out, int ldo, int N, int E, int E_pad, int V,
+                          cudaStream_t st);
+int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, void* h_out,
+                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st);
+int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
+                            const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1,
+                            long long s1, const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, void* dg,
+                            int lddg, int B, int H, cudaStream_t st);
+int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
+// bf16-mode orchestration (engine_bf16.cu)
+size_t train_workspace_bytes_bf16(const mmqg_dims& d, int T_q);
+int check_dims_bf16(const mmqg_dims& d);
+int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                       size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
+                       cudaStream_t st);
+int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                        size_t workspace_bytes, mmqg_tensors& Gd, int phase, cudaStream_t st);
+int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* nll, int R, int V, float scale,
+                  void* dlogits, int lddl, cudaStream_t st);
 int attn_fwd(float* scores, int lds, const float* M_txt, const float* M_aud, const float* M_vid, float* ctx,
              int ldctx, const AttnShape& s, cudaStream_t st);
 int attn_bwd(const float* attn, float* ds_out, int lds, const float* dctx, int lddctx, const float* M_txt,

@@ -1,0 +1,207 @@
+// Elementwise / row-wise kernels of the bf16 mode: same arithmetic as pointwise.cu (fp32 math,
+// fp32 cell state and reductions) but the tensors that feed tensor-core GEMMs are written as
+// bf16 (h sequences, gate gradients, gathered embeddings, dlogits, packed weights).
+#include <cuda_bf16.h>
+#include "kernels.h"
+
+namespace mmqg {
+
+typedef __nv_bfloat16 bf16;
+
+// dst(r, c) = bf16(src(r, c)) for c < cols, 0 for cols <= c < cols_dst  (weight packing, input conversion)
+__global__ void cvt_f32_bf16_2d_kernel(const float* __restrict__ src, long long ld_src, bf16* __restrict__ dst,
+                                       long long ld_dst, long long rows, int cols, int cols_dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = rows * cols_dst;
+  if (i >= total) return;
+  long long r = i / cols_dst;
+  int c = (int)(i % cols_dst);
+  float v = c < cols ? src[r * ld_src + c] : 0.f;
+  dst[r * ld_dst + c] = __float2bfloat16_rn(v);
+}
+
+__global__ void embedding_gather_bf16_kernel(const float* __restrict__ emb, const int64_t* __restrict__ idx,
+                                             bf16* __restrict__ out, int ldo, int N, int E, int E_pad, int V) {
+  int n = blockIdx.x;
+  long long w = idx[n];
+  w = w < 0 ? 0 : (w >= V ? V - 1 : w);
+  const float* src = emb + (size_t)w * E;
+  bf16* dst = out + (size_t)n * ldo;
+  for (int e = threadIdx.x; e < E_pad; e += blockDim.x) dst[e] = __float2bfloat16_rn(e < E ? src[e] : 0.f);
+}
+
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void lstm_pointwise_fwd_bf16_kernel(float* __restrict__ gates, int ldg, const float* __restrict__ c_prev,
+                                               int ldcp, float* __restrict__ c_out, int ldc, bf16* __restrict__ h_out,
+                                               int ldh, float* __restrict__ h2, int ldh2, int B, int H) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int b = idx / H, j = idx % H;
+  float* g = gates + (size_t)b * ldg;
+  float i = sigm(g[j]), f = sigm(g[H + j]), gg = tanhf(g[2 * H + j]), o = sigm(g[3 * H + j]);
+  float cp = c_prev ? c_prev[(size_t)b * ldcp + j] : 0.f;
+  float c = f * cp + i * gg;
+  float h = o * tanhf(c);
+  g[j] = i; g[H + j] = f; g[2 * H + j] = gg; g[3 * H + j] = o;
+  c_out[(size_t)b * ldc + j] = c;
+  h_out[(size_t)b * ldh + j] = __float2bfloat16_rn(h);
+  if (h2) h2[(size_t)b * ldh2 + j] = h;
+}
+
+__global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, int ldg, const float* __restrict__ c_prev,
+                                               int ldcp, const float* __restrict__ c_new, int ldc,
+                                               const float* __restrict__ dh0, int ldh0, int n0, long long s0,
+                                               const float* __restrict__ dh1, int ldh1, int n1, long long s1,
+                                               const float* __restrict__ dh2, int ldh2, float* __restrict__ dc, int lddc,
+                                               int dc_is_zero, bf16* __restrict__ dg, int lddg, int B, int H) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int b = idx / H, j = idx % H;
+  float dh = 0.f;
+  if (dh0)
+    for (int s = 0; s < n0; ++s) dh += dh0[(size_t)s * s0 + (size_t)b * ldh0 + j];
+  if (dh1)
+    for (int s = 0; s < n1; ++s) dh += dh1[(size_t)s * s1 + (size_t)b * ldh1 + j];
+  if (dh2) dh += dh2[(size_t)b * ldh2 + j];
+  const float* a = acts + (size_t)b * ldg;
+  float i = a[j], f = a[H + j], gg = a[2 * H + j], o = a[3 * H + j];
+  float cp = c_prev ? c_prev[(size_t)b * ldcp + j] : 0.f;
+  float tc = tanhf(c_new[(size_t)b * ldc + j]);
+  float dct = (dc_is_zero ? 0.f : dc[(size_t)b * lddc + j]) + dh * o * (1.f - tc * tc);
+  bf16* d = dg + (size_t)b * lddg;
+  d[j] = __float2bfloat16_rn(dct * gg * i * (1.f - i));
+  d[H + j] = __float2bfloat16_rn(dct * cp * f * (1.f - f));
+  d[2 * H + j] = __float2bfloat16_rn(dct * i * (1.f - gg * gg));
+  d[3 * H + j] = __float2bfloat16_rn(dh * tc * o * (1.f - o));
+  dc[(size_t)b * lddc + j] = dct * f;
+}
+
+// out(n) = sum_m X(m,n), X bf16.  grid (ceil(N/32), nsplit); partial sums atomically added when nsplit > 1
+// (out must then be zeroed by the caller); block = 32 columns x 8 row lanes.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ X, int ldx, float* __restrict__ out,
+                                                          float* __restrict__ out2, int M, int N, float beta) {
+  __shared__ float sh[8][33];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int n = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (n < N)
+    for (int m = ty; m < M; m += 8) s += __bfloat162float(X[(size_t)m * ldx + n]);
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][tx];
+    if (beta != 0.f) t += beta * out[n];
+    out[n] = t;
+    if (out2) out2[n] = t;
+  }
+}
+
+__device__ __forceinline__ float wmax_(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float wsum_(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Row-wise log-softmax + NLL on fp32 logits; dlogits = scale*(softmax - onehot) written as bf16.
+__global__ void __launch_bounds__(256) nll_rows_bf16_kernel(const float* __restrict__ logits, int ldl,
+                                                            const int64_t* __restrict__ targets,
+                                                            float* __restrict__ nll, int R, int V, float scale,
+                                                            bf16* __restrict__ dl, int lddl) {
+  __shared__ float sh[8];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + (size_t)r * ldl;
+  float m = -INFINITY;
+  for (int v = tid; v < V; v += 256) m = fmaxf(m, x[v]);
+  m = wmax_(m);
+  if ((tid & 31) == 0) sh[tid >> 5] = m;
+  __syncthreads();
+  m = sh[0];
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, sh[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int v = tid; v < V; v += 256) s += expf(x[v] - m);
+  s = wsum_(s);
+  if ((tid & 31) == 0) sh[tid >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < 8; ++w) s += sh[w];
+  const float lse = m + logf(s);
+  long long t = targets[r];
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  if (tid == 0) nll[r] = lse - x[t];
+  if (dl) {
+    bf16* d = dl + (size_t)r * lddl;
+    for (int v = tid; v < V; v += 256) d[v] = __float2bfloat16_rn(scale * (expf(x[v] - lse) - (v == t ? 1.f : 0.f)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+int cvt_f32_bf16_2d(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
+                    int cols_dst, cudaStream_t st) {
+  MMQG_REQUIRE(src && dst && rows > 0 && cols > 0 && cols_dst >= cols, "cvt_f32_bf16_2d: bad args");
+  long long total = rows * cols_dst;
+  cvt_f32_bf16_2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, ld_src, reinterpret_cast<bf16*>(dst), ld_dst,
+                                                                       rows, cols, cols_dst);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int embedding_gather_bf16(const float* emb, const int64_t* idx, void* out, int ldo, int N, int E, int E_pad, int V,
+                          cudaStream_t st) {
+  MMQG_REQUIRE(emb && idx && out && N > 0 && ldo >= E_pad && E_pad >= E, "embedding_gather_bf16: bad args");
+  MMQG_PROBE(KC_EMBED, 0, 6.0 * N * E);
+  embedding_gather_bf16_kernel<<<N, 128, 0, st>>>(emb, idx, reinterpret_cast<bf16*>(out), ldo, N, E, E_pad, V);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, void* h_out,
+                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st) {
+  MMQG_REQUIRE(gates && c_out && h_out && B > 0 && H > 0, "lstm_pointwise_fwd_bf16: bad args");
+  int n = B * H;
+  MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (c_prev ? 10 : 9) + 2.0 * n + (h2 ? 4.0 * n : 0));
+  lstm_pointwise_fwd_bf16_kernel<<<ceil_div(n, 256), 256, 0, st>>>(gates, ldg, c_prev, ldcp, c_out, ldc,
+                                                                    reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
+                            const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1,
+                            long long s1, const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, void* dg,
+                            int lddg, int B, int H, cudaStream_t st) {
+  MMQG_REQUIRE(acts && c_new && dc && dg && B > 0 && H > 0, "lstm_pointwise_bwd_bf16: bad args");
+  int n = B * H;
+  MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (6 + (c_prev ? 1 : 0) + (dh0 ? n0 : 0) + (dh1 ? n1 : 0) + (dh2 ? 1 : 0)) + 8.0 * n);
+  lstm_pointwise_bwd_bf16_kernel<<<ceil_div(n, 256), 256, 0, st>>>(acts, ldg, c_prev, ldcp, c_new, ldc, dh0, ldh0, n0, s0,
+                                                                    dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero,
+                                                                    reinterpret_cast<bf16*>(dg), lddg, B, H);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st) {
+  MMQG_REQUIRE(X && out && M > 0 && N > 0, "colsum_bf16: bad args");
+  colsum_bf16_kernel<<<ceil_div(N, 32), 256, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, out, out2, M, N, beta);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* nll, int R, int V, float scale,
+                  void* dlogits, int lddl, cudaStream_t st) {
+  MMQG_REQUIRE(logits && targets && nll && R > 0 && V > 0, "nll_rows_bf16: bad args");
+  MMQG_PROBE(KC_LOSS, 0, 4.0 * R * V + (dlogits ? 2.0 * R * V : 0));
+  nll_rows_bf16_kernel<<<R, 256, 0, st>>>(logits, ldl, targets, nll, R, V, scale, reinterpret_cast<bf16*>(dlogits), lddl);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmqg
