@@ -26,7 +26,8 @@ enum KernelClass {
   KC_ATTN = 4,        // fused attention step forward / backward
   KC_LOSS = 5,        // log-softmax + NLL (+ dlogits) over a row chunk
   KC_EMBED = 6,       // embedding gather / scatter-add
-  KC_COUNT = 7
+  KC_LSTM_PERSIST = 7,  // persistent recurrent-cell kernels (one launch per layer and direction)
+  KC_COUNT = 8
 };
 extern thread_local int tl_gemm_class;    // class the next gemm_f32() launch is booked under
 void probe_open(int cls, cudaStream_t st, double flops, double bytes);

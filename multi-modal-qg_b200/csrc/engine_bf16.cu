@@ -37,6 +37,11 @@ struct Ws16 {
   float *attn_all, *ds_all, *ctx_tmp, *acts_dec[MMQG_MAX_LAYERS], *cs_dec[MMQG_MAX_LAYERS], *logits, *nll, *dhtop;
   float *dh_rec[MMQG_MAX_LAYERS], *dc[MMQG_MAX_LAYERS], *dx_above, *dq_h, *dctx_all, *dm_txt, *dm_vid, *de_dec;
   float *dh_rec_enc, *dh_rec_vid, *dx_text, *dc_v;
+  // persistent recurrent kernels: gate-slice packed W_hh (forward) and W_hh^T (backward),
+  // arrival counters, and the summed d loss / d h_final handed to the text encoder
+  b16 *wtp_f[MMQG_MAX_LAYERS], *wtp_b[MMQG_MAX_LAYERS], *wvp_f, *wvp_b;
+  uint32_t* flags;
+  float* dh_last;
   int Sp, Ep, Vp, Rc;
   size_t bytes;
 };
@@ -104,6 +109,10 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.dh_rec_enc = c.take<float>(kSplitB * B * H); w.dh_rec_vid = c.take<float>(kSplitB * B * Hv);
   w.dx_text = c.take<float>(Rt * (d.E > d.H ? d.E : d.H));
   w.dc_v = c.take<float>(B * Hv);
+  for (int l = 0; l < d.L; ++l) { w.wtp_f[l] = c.take<b16>(G * H); w.wtp_b[l] = c.take<b16>(G * H); }
+  w.wvp_f = c.take<b16>(Gv * Hv); w.wvp_b = c.take<b16>(Gv * Hv);
+  w.flags = c.take<uint32_t>((size_t)((d.T_t > d.T_v ? d.T_t : d.T_v) + 1) * ((B + 127) / 128));
+  w.dh_last = c.take<float>(B * H);
   w.bytes = align_up(c.off, 256);
   return w;
 }
@@ -137,6 +146,19 @@ struct Tc {
 
 static AttnShape attn_shape16(const mmqg_dims& d) { return AttnShape{d.B, d.TM, d.AM, d.H, d.H_a, d.H_v, d.T_t, d.T_v}; }
 
+// The encoders run on the persistent recurrent kernels when the shape allows it (lstm_persist.cu);
+// MMQG_PERSIST=0 forces the one-GEMM-plus-pointwise-launch-per-step path (for A/B comparison).
+static bool persist_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMQG_PERSIST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+static bool persist_text(const mmqg_dims& d) { return persist_enabled() && lstm_persist_ok(d.B, d.H); }
+static bool persist_video(const mmqg_dims& d) { return persist_enabled() && lstm_persist_ok(d.B, d.H_v); }
+
 // fp32 parameters -> packed bf16 caches + summed biases + concatenated attention bias
 static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cudaStream_t st) {
   const int H = d.H, G = 4 * d.H, Hv = d.H_v, Gv = 4 * d.H_v, E = d.E, Ep = w.Ep, Q = d.E + d.H;
@@ -165,6 +187,9 @@ static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cuda
     MMQG_CUDA(cudaMemcpyAsync(w.attn_b_cat + off[i], P.attn_b[i], sizeof(float) * len[i], cudaMemcpyDeviceToDevice, st));
   }
   MMQG_TRY(cvt_f32_bf16_2d(P.out_w, H, w.wo, H, d.V, H, H, st));
+  if (persist_text(d))
+    for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_whh(P.text_w_hh[l], w.wtp_f[l], w.wtp_b[l], H, st));
+  if (persist_video(d)) MMQG_TRY(pack_whh(P.vid_w_hh, w.wvp_f, w.wvp_b, Hv, st));
   return 0;
 }
 
@@ -175,6 +200,16 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
                               cudaMemcpyDeviceToDevice, st));
   // video LSTM (encoder.py:69)
   MMQG_TRY(cvt_f32_bf16_2d(bt.frames, d.F_v, w.frames16, d.F_v, (long long)B * d.T_v, d.F_v, d.F_v, st));
+  if (persist_video(d)) {
+    // hoisted input projection (frames are batch-major: one product per frame index), then ONE
+    // persistent launch for all T_v recurrent steps
+    for (int t = 0; t < d.T_v; ++t)
+      MMQG_TRY(Tc(w.frames16 + (size_t)t * d.F_v, d.T_v * d.F_v, false, w.wv_ih, d.F_v, false, B, Gv, d.F_v,
+                  w.acts_v + (size_t)t * B * Gv, Gv).bias(w.bsum_vid).run(st));
+    MMQG_CUDA(cudaMemsetAsync(w.hs_v, 0, sizeof(b16) * (size_t)B * Hv, st));
+    MMQG_CUDA(cudaMemsetAsync(w.cs_v, 0, sizeof(float) * (size_t)B * Hv, st));
+    MMQG_TRY(lstm_seq_fwd_persist(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags, d.T_v, B, Hv, st));
+  } else
   for (int t = 0; t < d.T_v; ++t) {
     StepGemmScope step_scope;
     float* acts = w.acts_v + (size_t)t * B * Gv;
@@ -192,6 +227,13 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
     const b16* X = l == 0 ? w.x0 : w.hs_text[l - 1] + (size_t)B * H;
     const int Ip = l == 0 ? w.Ep : H;
     MMQG_TRY(Tc(X, Ip, false, w.wt_ih[l], Ip, false, d.T_t * B, G, Ip, w.acts_text[l], G).bias(w.bsum_text[l]).run(st));
+    if (persist_text(d)) {
+      MMQG_CUDA(cudaMemsetAsync(w.hs_text[l], 0, sizeof(b16) * (size_t)B * H, st));
+      MMQG_CUDA(cudaMemsetAsync(w.cs_text[l], 0, sizeof(float) * (size_t)B * H, st));
+      MMQG_TRY(lstm_seq_fwd_persist(w.acts_text[l], w.cs_text[l], w.hs_text[l], w.wtp_f[l], l == d.L - 1 ? w.m_txt : nullptr,
+                                    (long long)d.TM * H, w.flags, d.T_t, B, H, st));
+      continue;
+    }
     for (int t = 0; t < d.T_t; ++t) {
       StepGemmScope step_scope;
       float* acts = w.acts_text[l] + (size_t)t * B * G;
@@ -341,6 +383,10 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
   if (phase == 2) {
     const int Hv = d.H_v, Gv = 4 * d.H_v;
     const long long pv = (long long)B * Hv;
+    if (persist_video(d)) {
+      MMQG_TRY(lstm_seq_bwd_persist(w.acts_v, w.cs_v, w.dg_v, w.wvp_b, w.dm_vid, Hv, (long long)d.AM * Hv, nullptr, nullptr,
+                                    w.flags, d.T_v, B, Hv, st));
+    } else
     for (int t = d.T_v - 1; t >= 0; --t) {
       StepGemmScope step_scope;
       const bool last = t == d.T_v - 1;
@@ -364,6 +410,15 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
 
   for (int l = L - 1; l >= 0; --l) {
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
+    if (persist_text(d)) {
+      // d loss / d h_final = the decoder's gradient w.r.t. its initial state (train.py:169) plus,
+      // for the top layer, the step-0 attention query; d loss / d c_final sits in dc[l].
+      MMQG_TRY(sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, w.dh_last, B * H, st));
+      const float* ext = l == L - 1 ? w.dm_txt : w.dx_text;
+      const long long ts = l == L - 1 ? H : (long long)B * H, ld = l == L - 1 ? (long long)d.TM * H : H;
+      MMQG_TRY(lstm_seq_bwd_persist(w.acts_text[l], w.cs_text[l], w.dg_text[l], w.wtp_b[l], ext, ts, ld, w.dh_last, w.dc[l],
+                                    w.flags, d.T_t, B, H, st));
+    } else
     for (int t = d.T_t - 1; t >= 0; --t) {
       StepGemmScope step_scope;
       const bool last = t == d.T_t - 1;

@@ -109,55 +109,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(&accum_full);      // accumulator complete
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> global ----
+    // ---- epilogue: TMEM -> registers -> smem transpose -> coalesced global ----
+    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  Writing
+    // rows straight to global would touch 32 different lines per instruction, so every
+    // 32x32 block goes through a padded per-warp staging tile (the operand ring is free once
+    // accum_full fires) and leaves with lanes along the columns: 128 contiguous bytes per
+    // warp store, and the same for the Cin reads.
     const int q = warp & 3;
-    const int row = 32 * q + lane;
-    const int m = m0 + row;
     mbar_wait(&accum_full, 0);
     tc_fence_after_sync();
     const bool lead = blockIdx.z == 0;
     float* Cf = reinterpret_cast<float*>(p.C) + (size_t)blockIdx.z * p.c_split_stride;
     __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+    float* stg = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    const int mrow0 = m0 + 32 * q;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c * 32, v);
       tmem_ld_wait();
-      if (m < p.M) {
-        const int nb = n0 + c * 32;
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = p.alpha * v[j];
-          if (lead && nb + j < p.N) {
-            if (p.Cin) x += p.beta * p.Cin[(size_t)m * p.ldcin + nb + j];
-            if (p.bias) x += p.bias[nb + j];
-          }
-          v[j] = x;
-        }
-        if (p.c_bf16) {
-          __nv_bfloat16* dst = Cb + (size_t)m * p.ldc + nb;
-          if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+      __syncwarp();
+      const int n = n0 + c * 32 + lane;
+      if (n < p.N) {
+        const float bias = (lead && p.bias) ? p.bias[n] : 0.f;
+        const int rows = min(32, p.M - mrow0);
+        const bool use_cin = lead && p.Cin != nullptr;
+        // rows in batches of 8: all Cin loads of a batch are issued before its stores (C may
+        // alias Cin, so the compiler cannot hoist the loads across stores itself)
+        for (int r0 = 0; r0 < rows; r0 += 8) {
+          float cin[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
-              u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(dst + j) = u;
+          for (int i = 0; i < 8; ++i)
+            cin[i] = (use_cin && r0 + i < rows) ? p.Cin[(size_t)(mrow0 + r0 + i) * p.ldcin + n] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (r0 + i < rows) {
+              const size_t m = (size_t)(mrow0 + r0 + i);
+              const float x = p.alpha * stg[(r0 + i) * 33 + lane] + bias + p.beta * cin[i];
+              if (p.c_bf16) Cb[m * p.ldc + n] = __float2bfloat16_rn(x);
+              else Cf[m * p.ldc + n] = x;
             }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
-          }
-        } else {
-          float* dst = Cf + (size_t)m * p.ldc + nb;
-          if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) dst[j] = v[j];
           }
         }
       }
@@ -250,7 +244,14 @@ int gemm_bf16(const mmqg_gemm_bf16_args& g, cudaStream_t st) {
   p.Cin = g.Cin; p.ldcin = g.ldcin; p.beta = g.beta; p.alpha = g.alpha; p.bias = g.bias;
   p.split_k = g.split_k > 1 ? g.split_k : 1; p.c_split_stride = g.c_split_stride;
   MMQG_REQUIRE(p.split_k == 1 || !g.c_bf16, "gemm_bf16: split-K partials are fp32");
-  MMQG_REQUIRE(p.split_k <= p.nk1 + p.nk2, "gemm_bf16: split_k %d exceeds the %d k-blocks", p.split_k, p.nk1 + p.nk2);
+  if (p.split_k > p.nk1 + p.nk2) {
+    // fewer k-blocks than requested slices: the surplus partial tiles are defined as zero
+    const int used = p.nk1 + p.nk2;
+    MMQG_REQUIRE(g.ldc == g.N, "gemm_bf16: clamped split-K needs contiguous partials");
+    MMQG_CUDA(cudaMemsetAsync(reinterpret_cast<float*>(g.C) + (size_t)used * g.c_split_stride, 0,
+                              sizeof(float) * (size_t)(p.split_k - used) * g.c_split_stride, st));
+    p.split_k = used;
+  }
   MMQG_PROBE(tl_gemm_class, 2.0 * g.M * g.N * ((double)g.K + g.K2),
              2.0 * ((double)g.M + g.N) * ((double)g.K + g.K2) + (g.c_bf16 ? 2.0 : 4.0) * g.M * g.N);
   if (!amn && !bmn) return launch_tc<BN, false, false>(ta, tb, ta2, tb2, p, st);

@@ -45,6 +45,15 @@ int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int
                             long long s1, const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, void* dg,
                             int lddg, int B, int H, cudaStream_t st);
 int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
+// persistent recurrent-cell kernels (lstm_persist.cu)
+bool lstm_persist_ok(int B, int H);
+int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st);
+int sum_partials(const float* a, int na, const float* b, int nb, long long stride, float* y, int n, cudaStream_t st);
+int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, long long mem_ld,
+                         uint32_t* flags, int T, int B, int H, cudaStream_t st);
+int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
+                         long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
+                         int T, int B, int H, cudaStream_t st);
 // bf16-mode orchestration (engine_bf16.cu)
 size_t train_workspace_bytes_bf16(const mmqg_dims& d, int T_q);
 int check_dims_bf16(const mmqg_dims& d);

@@ -1,0 +1,480 @@
+// Persistent recurrent-cell kernels (bf16 mode): ONE launch runs all T timesteps of one LSTM
+// layer, forward or backward-through-time, instead of 2 launches per step.
+// Replaces the per-token aten::lstm calls of the reference (encoder.py:69,98 driven by
+// train.py:164-166) and their autograd twins; the input projection x W_ih^T + b is hoisted
+// into one tensor-core GEMM over the whole sequence (gemm_tc.cu) and arrives here as `gx`.
+//
+// Decomposition.  The hidden units are cut into slices of 16; CTA (s, m) owns slice s for the
+// 128 batch rows of m-tile m and keeps ITS weights resident in shared memory for the whole
+// sequence, so per step only activations move:
+//   forward : D[128 x 64] = h_{t-1}[128 x H] . Wslice^T     Wslice = the 4 gate rows of the 16
+//             units (64 x H bf16, 64 KB at H=512), h_{t-1} streamed by TMA (128 KB),
+//             accumulator in TMEM; the epilogue warps add gx, apply the cell update with the
+//             cell state held in registers across all T steps, and publish h_t.
+//   backward: D[128 x 16] = dG_{t+1}[128 x 4H] . W_hh[:, slice]   (W^T slice 16 x 4H, 64 KB,
+//             resident; dG_{t+1} streamed through a 6-stage TMA ring), then the pointwise cell
+//             gradient with dc in registers, publishing dG_t (bf16, the operand of the
+//             hoisted weight-gradient GEMMs).
+// Cross-CTA exchange of h_t / dG_t goes through global memory (L2) with one arrival counter
+// per (timestep, m-tile): writers st.global -> fence -> bar -> red.release.gpu, the reader's
+// TMA thread spins with ld.acquire.gpu and issues fence.proxy.async before the bulk loads.
+// All CTAs must be co-resident (grid <= #SMs, 1 CTA/SM): launched cooperatively.
+#include <cuda_bf16.h>
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace mmqg {
+
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigm_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct LstmFwdP {
+  float* gates;        // (T*B, 4H) fp32: in = x W_ih^T + b (hoisted), out = activated gates i,f,g,o
+  float* cs;           // ((T+1)*B, H) fp32; slab t+1 receives c_t (slab 0 is not read: c_{-1} = 0)
+  bf16* hs;            // ((T+1)*B, H) bf16; slab 0 = h_{-1} (zeros), slab t+1 receives h_t
+  float* mem;          // optional batch-major fp32 copy of h_t: mem[b*mem_ld + t*H + j]
+  long long mem_ld;
+  uint32_t* flags;     // ((T+1) * n_mt) arrival counters, zeroed before launch
+  int T, B, H, n_mt, n_slices, KB;
+};
+
+__global__ void __launch_bounds__(160, 1)
+lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;                       // KB x (64 rows x 128 B)
+  uint8_t* sA = smem + p.KB * 8192;         // KB x (128 rows x 128 B)
+  __shared__ uint64_t w_full, a_full[8], mma_done, tmem_free;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x, mt = blockIdx.y;
+  const int H = p.H, B = p.B, G = 4 * p.H;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&w_full, 1);
+    for (int k = 0; k < 8; ++k) mbar_init(&a_full[k], 1);
+    mbar_init(&mma_done, 1);
+    mbar_init(&tmem_free, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmH);
+  }
+  if (warp == 4) tmem_alloc(&tmem_slot, 64);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      mbar_expect_tx(&w_full, p.KB * 8192);
+      for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, &w_full, kb * 64, slice * 64);
+      for (int t = 0; t < p.T; ++t) {
+        if (t > 0) {
+          mbar_wait(&mma_done, (t - 1) & 1);                       // sA is free again
+          const uint32_t* f = p.flags + (size_t)t * p.n_mt + mt;    // h_{t-1} complete for this m-tile?
+          while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
+          }
+          fence_proxy_async();
+        }
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_expect_tx(&a_full[kb], 16384);
+          tma_load_2d(sA + kb * 16384, &tmH, &a_full[kb], kb * 64, t * B + mt * 128);
+        }
+        if (t == 0) mbar_wait(&w_full, 0);
+        else mbar_wait(&tmem_free, (t - 1) & 1);                    // epilogue has drained the accumulator
+        tc_fence_after_sync();
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(&a_full[kb], t & 1);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sW + kb * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, umma_smem_desc(a_addr + k * 32, 16, 1024), umma_smem_desc(b_addr + k * 32, 16, 1024),
+                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&mma_done);
+      }
+    }
+  } else {
+    // ---- epilogue warps: thread = batch row, 16 hidden units x 4 gates ----
+    const int row = warp * 32 + lane;
+    const int m = mt * 128 + row;
+    const bool valid = m < B;
+    const int j0 = slice * 16;
+    float c[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) c[u] = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+      // prefetch the hoisted pre-gates of this row (independent of the recurrence)
+      float4 gx[16];
+      float* grow = p.gates + ((size_t)t * B + (valid ? m : 0)) * G + j0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) gx[g * 4 + v] = *reinterpret_cast<const float4*>(grow + g * H + 4 * v);
+      mbar_wait(&mma_done, t & 1);
+      tc_fence_after_sync();
+      float acc[64];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + g * 16, acc + g * 16);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_free);
+      if (valid) {
+        const float* gxf = reinterpret_cast<const float*>(gx);
+        float hv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float ig = sigm_fast(acc[u] + gxf[u]);
+          const float fg = sigm_fast(acc[16 + u] + gxf[16 + u]);
+          const float gg = tanh_fast(acc[32 + u] + gxf[32 + u]);
+          const float og = sigm_fast(acc[48 + u] + gxf[48 + u]);
+          c[u] = fmaf(fg, c[u], ig * gg);
+          hv[u] = og * tanh_fast(c[u]);
+          acc[u] = ig; acc[16 + u] = fg; acc[32 + u] = gg; acc[48 + u] = og;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            *reinterpret_cast<float4*>(grow + g * H + 4 * v) =
+                make_float4(acc[g * 16 + 4 * v], acc[g * 16 + 4 * v + 1], acc[g * 16 + 4 * v + 2], acc[g * 16 + 4 * v + 3]);
+        float* crow = p.cs + ((size_t)(t + 1) * B + m) * H + j0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) *reinterpret_cast<float4*>(crow + 4 * v) = make_float4(c[4 * v], c[4 * v + 1], c[4 * v + 2], c[4 * v + 3]);
+        uint32_t hp[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(hv[2 * v], hv[2 * v + 1]);
+          hp[v] = *reinterpret_cast<uint32_t*>(&t2);
+        }
+        bf16* hrow = p.hs + ((size_t)(t + 1) * B + m) * H + j0;
+        *reinterpret_cast<uint4*>(hrow) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(hrow + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+        if (p.mem) {
+          float* mrow = p.mem + (size_t)m * p.mem_ld + (size_t)t * H + j0;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) *reinterpret_cast<float4*>(mrow + 4 * v) = make_float4(hv[4 * v], hv[4 * v + 1], hv[4 * v + 2], hv[4 * v + 3]);
+        }
+      }
+      __threadfence();
+      epi_bar_sync();
+      if (row == 0) red_release_gpu_add(p.flags + (size_t)(t + 1) * p.n_mt + mt, 1u);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct LstmBwdP {
+  const float* acts;   // (T*B, 4H) activated gates from the forward
+  const float* cs;     // ((T+1)*B, H) cell states (slab 0 must hold c_{-1}: zeros for the encoders)
+  bf16* dg;            // (T*B, 4H) bf16 out: d loss / d pre-activations (also streamed back through tmG)
+  const float* dh_ext; // external d loss / d h_t per step: dh_ext[t*ext_ts + b*ext_ld + j]  (nullable)
+  long long ext_ts, ext_ld;
+  const float* dh_last; // (B,H) fp32 added to d h_{T-1} (nullable)
+  const float* dc_last; // (B,H) fp32 d loss / d c_{T-1} from the consumer of the final state (nullable)
+  uint32_t* flags;      // (T * n_mt), zeroed before launch
+  int T, B, H, n_mt, n_slices, NKB;   // NKB = 4H/64
+};
+
+static constexpr int BWD_STAGES = 6;
+
+__global__ void __launch_bounds__(192, 1)
+lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, LstmBwdP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;                        // NKB x (16 rows x 128 B)
+  uint8_t* sA = smem + p.NKB * 2048;         // BWD_STAGES x (128 rows x 128 B)
+  __shared__ uint64_t w_full, full[BWD_STAGES], empty[BWD_STAGES], mma_done, tmem_free;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x, mt = blockIdx.y;
+  const int H = p.H, B = p.B, G = 4 * p.H, T = p.T;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&w_full, 1);
+    for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&mma_done, 1);
+    mbar_init(&tmem_free, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 5) tmem_alloc(&tmem_slot, 32);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_expect_tx(&w_full, p.NKB * 2048);
+      for (int kb = 0; kb < p.NKB; ++kb) tma_load_2d(sW + kb * 2048, &tmW, &w_full, kb * 64, slice * 16);
+      int i = 0;
+      for (int t = T - 2; t >= 0; --t) {           // step t consumes dG_{t+1}
+        const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
+        while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
+        }
+        fence_proxy_async();
+        for (int kb = 0; kb < p.NKB; ++kb, ++i) {
+          const int s = i % BWD_STAGES, ph = (i / BWD_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], 16384);
+          tma_load_2d(sA + s * 16384, &tmG, &full[s], kb * 64, (t + 1) * B + mt * 128);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 16, 0, 0);
+      mbar_wait(&w_full, 0);
+      int i = 0, it = 0;
+      for (int t = T - 2; t >= 0; --t, ++it) {
+        if (it > 0) mbar_wait(&tmem_free, (it - 1) & 1);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < p.NKB; ++kb, ++i) {
+          const int s = i % BWD_STAGES, ph = (i / BWD_STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + s * 16384), b_addr = smem_u32(sW + kb * 2048);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, umma_smem_desc(a_addr + k * 32, 16, 1024), umma_smem_desc(b_addr + k * 32, 16, 1024),
+                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&mma_done);
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const int m = mt * 128 + row;
+    const bool valid = m < B;
+    const int mm = valid ? m : 0;
+    const int j0 = slice * 16;
+    float dc[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) dc[u] = (p.dc_last && valid) ? p.dc_last[(size_t)m * H + j0 + u] : 0.f;
+    int it = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      // prefetch everything that does not depend on the recurrence
+      float4 a4[16], cn4[4], cp4[4], ex4[4];
+      const float* arow = p.acts + ((size_t)t * B + mm) * G + j0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) a4[g * 4 + v] = *reinterpret_cast<const float4*>(arow + g * H + 4 * v);
+      const float* cnrow = p.cs + ((size_t)(t + 1) * B + mm) * H + j0;
+      const float* cprow = p.cs + ((size_t)t * B + mm) * H + j0;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        cn4[v] = *reinterpret_cast<const float4*>(cnrow + 4 * v);
+        cp4[v] = *reinterpret_cast<const float4*>(cprow + 4 * v);
+        ex4[v] = p.dh_ext ? *reinterpret_cast<const float4*>(p.dh_ext + (size_t)t * p.ext_ts + (size_t)mm * p.ext_ld + j0 + 4 * v)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float dh[16];
+      if (t == T - 1) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) dh[u] = (p.dh_last && valid) ? p.dh_last[(size_t)m * H + j0 + u] : 0.f;
+      } else {
+        mbar_wait(&mma_done, it & 1);
+        tc_fence_after_sync();
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(32 * warp) << 16), dh);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&tmem_free);
+        ++it;
+      }
+      if (valid) {
+        const float* a = reinterpret_cast<const float*>(a4);
+        const float* cn = reinterpret_cast<const float*>(cn4);
+        const float* cp = reinterpret_cast<const float*>(cp4);
+        const float* ex = reinterpret_cast<const float*>(ex4);
+        float dgv[64];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float ig = a[u], fg = a[16 + u], gg = a[32 + u], og = a[48 + u];
+          const float d = dh[u] + ex[u];
+          const float tc_ = tanh_fast(cn[u]);
+          const float dct = dc[u] + d * og * (1.f - tc_ * tc_);
+          dgv[u] = dct * gg * ig * (1.f - ig);
+          dgv[16 + u] = dct * cp[u] * fg * (1.f - fg);
+          dgv[32 + u] = dct * ig * (1.f - gg * gg);
+          dgv[48 + u] = d * tc_ * og * (1.f - og);
+          dc[u] = dct * fg;
+        }
+        bf16* drow = p.dg + ((size_t)t * B + m) * G + j0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w8[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(dgv[g * 16 + 2 * v], dgv[g * 16 + 2 * v + 1]);
+            w8[v] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          *reinterpret_cast<uint4*>(drow + g * H) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+          *reinterpret_cast<uint4*>(drow + g * H + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+        }
+      }
+      __threadfence();
+      epi_bar_sync();
+      if (row == 0) red_release_gpu_add(p.flags + (size_t)t * p.n_mt + mt, 1u);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+// gate-slice packing of W_hh for the forward kernel: row (s*64 + g*16 + u) = W_hh[g*H + s*16 + u, :]
+__global__ void pack_whh_fwd_kernel(const float* __restrict__ w, bf16* __restrict__ out, int H) {
+  const int r = blockIdx.x;                 // packed row
+  const int s = r / 64, g = (r % 64) / 16, u = r % 16;
+  const float* src = w + (size_t)(g * H + s * 16 + u) * H;
+  bf16* dst = out + (size_t)r * H;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) dst[k] = __float2bfloat16_rn(src[k]);
+}
+// transpose for the backward kernel: out[j, r] = W_hh[r, j]   (H x 4H)
+__global__ void pack_whh_bwd_kernel(const float* __restrict__ w, bf16* __restrict__ out, int H) {
+  __shared__ float tile[32][33];
+  const int G = 4 * H;
+  const int r0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = w[(size_t)(r0 + i) * H + j0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    out[(size_t)(j0 + i) * G + r0 + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+}
+
+// y = sum of up to two split-K partial stacks (used to form dh_last for the text encoder)
+__global__ void sum_partials_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, long long stride,
+                                    float* __restrict__ y, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < na; ++k) s += a[(size_t)k * stride + i];
+  for (int k = 0; k < nb; ++k) s += b[(size_t)k * stride + i];
+  y[i] = s;
+}
+
+// ---- host -----------------------------------------------------------------------------------
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+bool lstm_persist_ok(int B, int H) {
+  if (H % 64 != 0 || H > 512 || H < 64) return false;
+  const int n_mt = ceil_div(B, 128);
+  return (H / 16) * n_mt <= num_sms();
+}
+
+int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st) {
+  MMQG_REQUIRE(w_hh && H % 32 == 0, "pack_whh: bad args");
+  if (fwd_packed) {
+    pack_whh_fwd_kernel<<<4 * H, 128, 0, st>>>(w_hh, reinterpret_cast<bf16*>(fwd_packed), H);
+    MMQG_LAUNCH_CHECK();
+  }
+  if (bwd_packed) {
+    pack_whh_bwd_kernel<<<dim3(4 * H / 32, H / 32), dim3(32, 8), 0, st>>>(w_hh, reinterpret_cast<bf16*>(bwd_packed), H);
+    MMQG_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int sum_partials(const float* a, int na, const float* b, int nb, long long stride, float* y, int n, cudaStream_t st) {
+  sum_partials_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, na, b, nb, stride, y, n);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename Kern, typename P>
+static int launch_coop(Kern kern, dim3 grid, int threads, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1, const P& p,
+                       cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMQG_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, p));
+  return 0;
+}
+
+// gates: (T*B,4H) fp32 pre-gates -> activated gates.  wp_fwd: pack_whh forward layout.  hs slab 0 must be zeros.
+int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, long long mem_ld,
+                         uint32_t* flags, int T, int B, int H, cudaStream_t st) {
+  MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
+  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64};
+  CUtensorMap tmW, tmH;
+  MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_fwd, 4 * (uint64_t)H, H, H, 64, 64));
+  MMQG_TRY(make_tmap_bf16_2d(&tmH, hs, (uint64_t)(T + 1) * B, H, H, 128, 64));
+  const size_t smem = (size_t)p.KB * (8192 + 16384) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 16384) + 1024));
+    attr = true;
+  }
+  MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(T + 1) * p.n_mt, st));
+  const double fl = 2.0 * T * B * 4.0 * H * H;
+  MMQG_PROBE(KC_LSTM_PERSIST, fl, 0);
+  MMQG_TRY(launch_coop(lstm_seq_fwd_kernel, dim3(p.n_slices, p.n_mt), 160, smem, tmW, tmH, p, st));
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
+                         long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
+                         int T, int B, int H, cudaStream_t st) {
+  MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_bwd_persist: shape B=%d H=%d not supported", B, H);
+  LstmBwdP p{acts, cs, reinterpret_cast<bf16*>(dg), dh_ext, ext_ts, ext_ld, dh_last, dc_last, flags,
+             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64};
+  CUtensorMap tmW, tmG;
+  MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_bwd, H, 4 * (uint64_t)H, 4 * (uint64_t)H, 16, 64));
+  MMQG_TRY(make_tmap_bf16_2d(&tmG, dg, (uint64_t)T * B, 4 * (uint64_t)H, 4 * (uint64_t)H, 128, 64));
+  const size_t smem = (size_t)p.NKB * 2048 + BWD_STAGES * 16384 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 2048 + BWD_STAGES * 16384 + 1024));
+    attr = true;
+  }
+  MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)T * p.n_mt, st));
+  const double fl = 2.0 * (T - 1) * B * 4.0 * H * H;
+  MMQG_PROBE(KC_LSTM_PERSIST, fl, 0);
+  MMQG_TRY(launch_coop(lstm_seq_bwd_kernel, dim3(p.n_slices, p.n_mt), 192, smem, tmW, tmG, p, st));
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmqg

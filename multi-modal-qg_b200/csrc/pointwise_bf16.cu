@@ -77,25 +77,38 @@ __global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, i
   dc[(size_t)b * lddc + j] = dct * f;
 }
 
-// out(n) = sum_m X(m,n), X bf16.  grid (ceil(N/32), nsplit); partial sums atomically added when nsplit > 1
-// (out must then be zeroed by the caller); block = 32 columns x 8 row lanes.
+// out(n) (+)= sum_m X(m,n), X bf16.  grid (ceil(N/64), row chunks); each warp row covers 64 columns
+// (128 contiguous bytes), 8 row lanes per block; chunk sums are added atomically, so the
+// caller zeroes `out` first unless it accumulates.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ X, int ldx, float* __restrict__ out,
-                                                          float* __restrict__ out2, int M, int N, float beta) {
-  __shared__ float sh[8][33];
-  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  int n = blockIdx.x * 32 + tx;
-  float s = 0.f;
-  if (n < N)
-    for (int m = ty; m < M; m += 8) s += __bfloat162float(X[(size_t)m * ldx + n]);
-  sh[ty][tx] = s;
+                                                          float* __restrict__ out2, int M, int N, int rows_per_block) {
+  __shared__ float sh[8][65];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 64 + 2 * tx;
+  const int m_begin = blockIdx.y * rows_per_block, m_end = min(M, m_begin + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (n + 1 < N && (ldx & 1) == 0) {
+    for (int m = m_begin + ty; m < m_end; m += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(X + (size_t)m * ldx + n);
+      s0 += __low2float(v); s1 += __high2float(v);
+    }
+  } else {
+    for (int m = m_begin + ty; m < m_end; m += 8) {
+      if (n < N) s0 += __bfloat162float(X[(size_t)m * ldx + n]);
+      if (n + 1 < N) s1 += __bfloat162float(X[(size_t)m * ldx + n + 1]);
+    }
+  }
+  sh[ty][2 * tx] = s0; sh[ty][2 * tx + 1] = s1;
   __syncthreads();
-  if (ty == 0 && n < N) {
-    float t = 0.f;
+  if (threadIdx.x < 64) {
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) {
+      float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sh[i][tx];
-    if (beta != 0.f) t += beta * out[n];
-    out[n] = t;
-    if (out2) out2[n] = t;
+      for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+      atomicAdd(out + c, t);
+      if (out2) atomicAdd(out2 + c, t);
+    }
   }
 }
 
@@ -190,7 +203,17 @@ int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int
 
 int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st) {
   MMQG_REQUIRE(X && out && M > 0 && N > 0, "colsum_bf16: bad args");
-  colsum_bf16_kernel<<<ceil_div(N, 32), 256, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, out, out2, M, N, beta);
+  MMQG_REQUIRE(beta == 0.f || beta == 1.f, "colsum_bf16: beta must be 0 or 1");
+  if (beta == 0.f) {
+    MMQG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
+    if (out2) MMQG_CUDA(cudaMemsetAsync(out2, 0, sizeof(float) * N, st));
+  }
+  const int col_blocks = ceil_div(N, 64);
+  int chunks = ceil_div(4 * 148, col_blocks);
+  if (chunks > ceil_div(M, 64)) chunks = ceil_div(M, 64);
+  const int rows_per_block = ceil_div(M, chunks);
+  colsum_bf16_kernel<<<dim3(col_blocks, ceil_div(M, rows_per_block)), 256, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, out,
+                                                                                     out2, M, N, rows_per_block);
   MMQG_LAUNCH_CHECK();
   return 0;
 }
