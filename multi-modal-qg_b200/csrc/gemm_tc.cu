@@ -116,13 +116,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // accum_full fires) and leaves with lanes along the columns: 128 contiguous bytes per
     // warp store, and the same for the Cin reads.
     const int q = warp & 3;
-    mbar_wait(&accum_full, 0);
-    tc_fence_after_sync();
     const bool lead = blockIdx.z == 0;
     float* Cf = reinterpret_cast<float*>(p.C) + (size_t)blockIdx.z * p.c_split_stride;
     __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
     float* stg = reinterpret_cast<float*>(smem) + q * (32 * 33);
     const int mrow0 = m0 + 32 * q;
+    const int rows = min(32, p.M - mrow0);
+    const bool use_cin = lead && p.Cin != nullptr;
+    // The addend tile is fetched while the main loop is still running: chunk 0 before the
+    // accumulator is ready, chunk c+1 before chunk c is stored (C may alias Cin, so these loads
+    // are explicitly hoisted above the stores).
+    float cin[32];
+    auto load_cin = [&](int c) {
+      const int n = n0 + c * 32 + lane;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        cin[r] = (use_cin && n < p.N && r < rows) ? p.Cin[(size_t)(mrow0 + r) * p.ldcin + n] : 0.f;
+    };
+    load_cin(0);
+    mbar_wait(&accum_full, 0);
+    tc_fence_after_sync();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
@@ -132,26 +145,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
       __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; ++r) v[r] = cin[r];
+      if (c + 1 < BN / 32) load_cin(c + 1);
       const int n = n0 + c * 32 + lane;
       if (n < p.N) {
         const float bias = (lead && p.bias) ? p.bias[n] : 0.f;
-        const int rows = min(32, p.M - mrow0);
-        const bool use_cin = lead && p.Cin != nullptr;
-        // rows in batches of 8: all Cin loads of a batch are issued before its stores (C may
-        // alias Cin, so the compiler cannot hoist the loads across stores itself)
-        for (int r0 = 0; r0 < rows; r0 += 8) {
-          float cin[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            cin[i] = (use_cin && r0 + i < rows) ? p.Cin[(size_t)(mrow0 + r0 + i) * p.ldcin + n] : 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (r0 + i < rows) {
-              const size_t m = (size_t)(mrow0 + r0 + i);
-              const float x = p.alpha * stg[(r0 + i) * 33 + lane] + bias + p.beta * cin[i];
-              if (p.c_bf16) Cb[m * p.ldc + n] = __float2bfloat16_rn(x);
-              else Cf[m * p.ldc + n] = x;
-            }
+        for (int r = 0; r < 32; ++r) {
+          if (r < rows) {
+            const size_t m = (size_t)(mrow0 + r);
+            const float x = p.alpha * stg[r * 33 + lane] + bias + p.beta * v[r];
+            if (p.c_bf16) Cb[m * p.ldc + n] = __float2bfloat16_rn(x);
+            else Cf[m * p.ldc + n] = x;
           }
         }
       }

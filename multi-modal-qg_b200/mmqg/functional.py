@@ -1,0 +1,182 @@
+"""torch.autograd glue for the step-wise drop-in modules (model/encoder.py, model/decoder.py).
+
+The reference's train.py drives its modules one token / one decoder step at a time and relies
+on autograd to stitch the steps together (train.py:164-177).  To run that loop unchanged, each
+building block is an autograd.Function whose forward and backward are libmmqg.so kernels
+(fp32 building blocks of include/mmqg.h through mmqg.ops); PyTorch only owns the tensors and
+the graph.  The sequence-level engine (mmqg.engine) is the fast path; this file is the
+compatibility path and shares its kernels.
+"""
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Embedding(Function):
+    """out(n,:) = weight(idx(n),:)   (reference encoder.py:96, decoder.py:75)."""
+
+    @staticmethod
+    def forward(ctx, weight, idx):
+        idx = idx.reshape(-1)
+        ctx.save_for_backward(idx)
+        ctx.shape = weight.shape
+        return ops.embedding_gather(_c(weight), idx)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dw = torch.zeros(ctx.shape, device=dout.device, dtype=torch.float32)     # dense, like the reference
+        ops.embedding_scatter_add(dw, idx, _c(dout))
+        return dw, None
+
+
+class Linear(Function):
+    """y = x W^T + b   (decoder.py:78,84,92,106)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = _c(x), _c(w)
+        ctx.save_for_backward(x, w)
+        return ops.gemm(x, w, False, True, bias=b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _c(dy)
+        dx = ops.gemm(dy, w, False, False)
+        dw = ops.gemm(dy, x, True, False)
+        db = ops.colsum(dy)
+        return dx, dw, db
+
+
+class Attention(Function):
+    """Three location-attention heads of one decoder step (decoder.py:78-97) given the
+    pre-softmax scores (B, TM+2AM) packed [text|audio|video]; returns the softmax weights
+    and the packed context [c_txt|c_aud|c_vid].  No length mask."""
+
+    @staticmethod
+    def forward(ctx, scores, M_txt, M_aud, M_vid, T_t, T_v):
+        attn = scores.clone()
+        M_txt, M_aud, M_vid = _c(M_txt), _c(M_aud), _c(M_vid)
+        c = ops.attn_fwd(attn, M_txt, M_aud, M_vid, T_t, T_v)
+        ctx.save_for_backward(attn, M_txt, M_aud, M_vid)
+        ctx.T = (T_t, T_v)
+        return attn, c
+
+    @staticmethod
+    def backward(ctx, dattn, dc):
+        attn, M_txt, M_aud, M_vid = ctx.saved_tensors
+        if ctx.needs_input_grad[2]:
+            raise NotImplementedError("gradient w.r.t. the audio features (VGGish) is outside the hot path")
+        T_t, T_v = ctx.T
+        ds = attn.clone()
+        dM_txt = torch.zeros_like(M_txt)
+        dM_vid = torch.zeros_like(M_vid)
+        ops.attn_bwd(ds, _c(dc), M_txt, M_aud, M_vid, dM_txt, dM_vid, T_t, T_v)
+        if dattn is not None and bool(dattn.any()):
+            # the reference only returns the weights for inspection; if a caller differentiates
+            # through them, add the softmax Jacobian of that path with plain tensor ops
+            TM, AM = M_txt.shape[1], M_aud.shape[1]
+            for lo, hi in ((0, TM), (TM, TM + AM), (TM + AM, TM + 2 * AM)):
+                a, g = attn[:, lo:hi], dattn[:, lo:hi]
+                ds[:, lo:hi] += a * (g - (a * g).sum(1, keepdim=True))
+        return ds, dM_txt, None, dM_vid, None, None
+
+
+class LSTMStack(Function):
+    """torch.nn.LSTM(input, hidden, num_layers) over a (T,B,I) sequence, gate order i,f,g,o, both
+    biases (reference encoder.py:91,54, decoder.py:69).  Weight gradients are hoisted into one
+    product per layer over the whole sequence; per step only h W_hh^T and the cell update run.
+    `masks`: optional (L-1,T,B,H) inter-layer dropout masks (already scaled by 1/(1-p))."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, masks, *weights):
+        T, B, _ = x.shape
+        L = len(weights) // 4
+        H = h0.shape[2]
+        inp = _c(x)
+        saved = []
+        hn, cn = [], []
+        for l in range(L):
+            w_ih, w_hh, b_ih, b_hh = [_c(w) for w in weights[4 * l:4 * l + 4]]
+            acts = ops.gemm(inp.reshape(T * B, -1), w_ih, False, True, bias=b_ih + b_hh).view(T, B, 4 * H)
+            hs = torch.empty(T + 1, B, H, device=x.device, dtype=torch.float32)
+            cs = torch.empty(T + 1, B, H, device=x.device, dtype=torch.float32)
+            hs[0].copy_(h0[l])
+            cs[0].copy_(c0[l])
+            for t in range(T):
+                ops.gemm(hs[t], w_hh, False, True, out=acts[t], Cin=acts[t])
+                h, c = ops.lstm_pointwise_fwd(acts[t], cs[t])
+                hs[t + 1].copy_(h)
+                cs[t + 1].copy_(c)
+            saved += [inp, acts, hs, cs]
+            hn.append(hs[T])
+            cn.append(cs[T])
+            inp = hs[1:]
+            if masks is not None and l < L - 1:
+                inp = inp * masks[l]
+        ctx.save_for_backward(*saved, *weights, *([masks] if masks is not None else []))
+        ctx.dims = (T, B, H, L, masks is not None)
+        return inp.clone(), torch.stack(hn), torch.stack(cn)
+
+    @staticmethod
+    def backward(ctx, dy, dhn, dcn):
+        T, B, H, L, has_mask = ctx.dims
+        sv = ctx.saved_tensors
+        saved, weights = sv[:4 * L], sv[4 * L:8 * L]
+        masks = sv[8 * L] if has_mask else None
+        dev = dy.device
+        dext = _c(dy).clone() if dy is not None else torch.zeros(T, B, H, device=dev)
+        dh0, dc0 = [None] * L, [None] * L
+        grads = [None] * (4 * L)
+        dx = None
+        for l in range(L - 1, -1, -1):
+            inp, acts, hs, cs = saved[4 * l:4 * l + 4]
+            w_ih, w_hh = _c(weights[4 * l]), _c(weights[4 * l + 1])
+            dg_all = acts.clone()
+            dc = dcn[l].clone() if dcn is not None else torch.zeros(B, H, device=dev)
+            dh_rec = _c(dhn[l]).clone() if dhn is not None else torch.zeros(B, H, device=dev)
+            for t in range(T - 1, -1, -1):
+                ops.lstm_pointwise_bwd(dg_all[t], cs[t], cs[t + 1], None, dh_rec, dext[t], dc)
+                dh_rec = ops.gemm(dg_all[t], w_hh, False, False)
+            dh0[l], dc0[l] = dh_rec, dc
+            flat = dg_all.view(T * B, 4 * H)
+            grads[4 * l] = ops.gemm(flat, inp.reshape(T * B, -1), True, False)
+            grads[4 * l + 1] = ops.gemm(flat, hs[:T].reshape(T * B, H), True, False)
+            db = ops.colsum(flat)
+            grads[4 * l + 2], grads[4 * l + 3] = db, db.clone()
+            dx = ops.gemm(flat, w_ih, False, False).view(T, B, -1)
+            if l > 0:
+                dext = dx * masks[l - 1] if masks is not None else dx
+        return (dx, torch.stack(dh0), torch.stack(dc0), None, *grads)
+
+
+def lstm_stack(x, hidden, lstm_module, training):
+    """Run `lstm_module`'s parameters (a torch.nn.LSTM used purely as the parameter container
+    that keeps the reference's state_dict keys) through the CUDA kernels."""
+    h0, c0 = hidden
+    L = lstm_module.num_layers
+    weights = []
+    for l in range(L):
+        weights += [getattr(lstm_module, f"weight_ih_l{l}"), getattr(lstm_module, f"weight_hh_l{l}"),
+                    getattr(lstm_module, f"bias_ih_l{l}"), getattr(lstm_module, f"bias_hh_l{l}")]
+    masks = None
+    p = float(lstm_module.dropout)
+    if training and p > 0 and L > 1:
+        T, B, _ = x.shape
+        keep = torch.rand(L - 1, T, B, lstm_module.hidden_size, device=x.device) >= p
+        masks = keep.to(torch.float32) / (1.0 - p)
+    y, hn, cn = LSTMStack.apply(x, _c(h0), _c(c0), masks, *weights)
+    return y, (hn, cn)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and not t.is_cuda:
+            raise RuntimeError("mmqg modules run on CUDA only (B200, sm_100a): move the module and its inputs to a CUDA "
+                               "device; there is no CPU fallback")
