@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--cpu-samples", type=int, default=6, help="samples the CPU baseline leg times")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--probe", type=int, default=1, help="kernel class the roofline probe times (see mmqg.h)")
+    ap.add_argument("--probe", type=int, default=None, help="kernel class the roofline probe times (see mmqg.h)")
     return ap.parse_args()
 
 
@@ -156,6 +156,8 @@ def workload_config(d, args, world):
 
 def main():
     args = parse()
+    if args.probe is None:
+        args.probe = 7 if args.mode == "bf16" else 1       # dominant kernel class of each mode
     from mmqg.dims import config as cfg
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -279,9 +281,11 @@ def main():
         _cabi.check(L.mmqg_probe_stop(C.byref(tms), C.byref(n), C.byref(fl), C.byref(by)))
         pk = peaks()
         names = {1: "per-timestep recurrent GEMM (gemm_f32_kernel, B x 4H x H class)", 2: "hoisted whole-sequence GEMM",
-                 3: "lstm_pointwise", 4: "attention step", 5: "nll_rows", 6: "embedding"}
+                 3: "lstm_pointwise", 4: "attention step", 5: "nll_rows", 6: "embedding",
+                 7: "persistent recurrent-cell kernels lstm_seq_fwd/bwd_kernel (tcgen05, one launch per layer and "
+                    "direction; FLOPs = 2*T*B*4H*H per launch)"}
         if n.value and tms.value > 0:
-            if args.probe in (1, 2):
+            if args.probe in (1, 2, 7):
                 ach = fl.value / (tms.value * 1e-3) / 1e12
                 roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
                         "frac": ach / pk["tflops"], "traffic": None}

@@ -126,38 +126,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The addend tile is fetched while the main loop is still running: chunk 0 before the
     // accumulator is ready, chunk c+1 before chunk c is stored (C may alias Cin, so these loads
     // are explicitly hoisted above the stores).
-    float cin[32];
-    auto load_cin = [&](int c) {
-      const int n = n0 + c * 32 + lane;
+    constexpr int HR = 16;                       // rows per addend batch
+    float cin[HR];
+    auto load_cin = [&](int idx) {               // idx = 2*chunk + half
+      const int n = n0 + (idx >> 1) * 32 + lane;
+      const int r0 = (idx & 1) * HR;
 #pragma unroll
-      for (int r = 0; r < 32; ++r)
-        cin[r] = (use_cin && n < p.N && r < rows) ? p.Cin[(size_t)(mrow0 + r) * p.ldcin + n] : 0.f;
+      for (int r = 0; r < HR; ++r)
+        cin[r] = (n < p.N && r0 + r < rows) ? p.Cin[(size_t)(mrow0 + r0 + r) * p.ldcin + n] : 0.f;
     };
-    load_cin(0);
+    if (use_cin) load_cin(0);
     mbar_wait(&accum_full, 0);
     tc_fence_after_sync();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c * 32, v);
-      tmem_ld_wait();
-      __syncwarp();
+      {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c * 32, v);
+        tmem_ld_wait();
+        __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < 32; ++r) v[r] = cin[r];
-      if (c + 1 < BN / 32) load_cin(c + 1);
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+        __syncwarp();
+      }
       const int n = n0 + c * 32 + lane;
-      if (n < p.N) {
-        const float bias = (lead && p.bias) ? p.bias[n] : 0.f;
+      const float bias = (lead && p.bias && n < p.N) ? p.bias[n] : 0.f;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float cur[HR];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          if (r < rows) {
-            const size_t m = (size_t)(mrow0 + r);
-            const float x = p.alpha * stg[r * 33 + lane] + bias + p.beta * v[r];
-            if (p.c_bf16) Cb[m * p.ldc + n] = __float2bfloat16_rn(x);
-            else Cf[m * p.ldc + n] = x;
+        for (int r = 0; r < HR; ++r) cur[r] = use_cin ? cin[r] : 0.f;
+        const int idx = 2 * c + half;
+        if (use_cin && idx + 1 < 2 * (BN / 32)) load_cin(idx + 1);
+        if (n < p.N) {
+#pragma unroll
+          for (int r = 0; r < HR; ++r) {
+            const int rr = half * HR + r;
+            if (rr < rows) {
+              const size_t m = (size_t)(mrow0 + rr);
+              const float x = p.alpha * stg[rr * 33 + lane] + bias + p.beta * cur[r];
+              if (p.c_bf16) Cb[m * p.ldc + n] = __float2bfloat16_rn(x);
+              else Cf[m * p.ldc + n] = x;
+            }
           }
         }
       }
