@@ -238,7 +238,11 @@ int gemm_bf16(const mmqg_gemm_bf16_args& g, cudaStream_t st) {
   MMQG_REQUIRE(g.A && g.B && g.C && g.M > 0 && g.N > 0 && g.K > 0, "gemm_bf16: bad args");
   MMQG_REQUIRE(g.K2 == 0 || (g.A2 && g.B2), "gemm_bf16: K2>0 needs A2,B2");
   const bool amn = g.a_mn_major != 0, bmn = g.b_mn_major != 0;
-  constexpr int BN = 128;
+  // Tile width: skinny problems (the per-timestep products, M = B) take 64-wide tiles so that
+  // twice as many SMs pull operands; everything else 128.
+  const int want_split = g.split_k > 1 ? g.split_k : 1;
+  const bool narrow = (long long)ceil_div(g.M, TBM) * ceil_div(g.N, 128) * want_split < 96 && g.N > 64;
+  const int BN = narrow ? 64 : 128;
   CUtensorMap ta, tb, ta2, tb2;
   auto mk_a = [&](CUtensorMap* t, const void* A, int lda, int K) {
     return amn ? make_tmap_bf16_2d(t, A, K, g.M, lda, 64, 64) : make_tmap_bf16_2d(t, A, g.M, K, lda, TBM, 64);
@@ -270,10 +274,16 @@ int gemm_bf16(const mmqg_gemm_bf16_args& g, cudaStream_t st) {
   }
   MMQG_PROBE(tl_gemm_class, 2.0 * g.M * g.N * ((double)g.K + g.K2),
              2.0 * ((double)g.M + g.N) * ((double)g.K + g.K2) + (g.c_bf16 ? 2.0 : 4.0) * g.M * g.N);
-  if (!amn && !bmn) return launch_tc<BN, false, false>(ta, tb, ta2, tb2, p, st);
-  if (!amn && bmn) return launch_tc<BN, false, true>(ta, tb, ta2, tb2, p, st);
-  if (amn && bmn) return launch_tc<BN, true, true>(ta, tb, ta2, tb2, p, st);
-  return launch_tc<BN, true, false>(ta, tb, ta2, tb2, p, st);
+  if (narrow) {
+    if (!amn && !bmn) return launch_tc<64, false, false>(ta, tb, ta2, tb2, p, st);
+    if (!amn && bmn) return launch_tc<64, false, true>(ta, tb, ta2, tb2, p, st);
+    if (amn && bmn) return launch_tc<64, true, true>(ta, tb, ta2, tb2, p, st);
+    return launch_tc<64, true, false>(ta, tb, ta2, tb2, p, st);
+  }
+  if (!amn && !bmn) return launch_tc<128, false, false>(ta, tb, ta2, tb2, p, st);
+  if (!amn && bmn) return launch_tc<128, false, true>(ta, tb, ta2, tb2, p, st);
+  if (amn && bmn) return launch_tc<128, true, true>(ta, tb, ta2, tb2, p, st);
+  return launch_tc<128, true, false>(ta, tb, ta2, tb2, p, st);
 }
 
 }  // namespace mmqg

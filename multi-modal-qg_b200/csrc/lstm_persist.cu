@@ -35,7 +35,76 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigm_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+
+// ---- warp-cooperative tile movers ---------------------------------------------------------
+// A warp owns 32 consecutive batch rows and per row only touches short segments (16 fp32 = 64 B
+// of a row that is 2-8 KB long).  Thread-per-row global accesses would touch 32 different lines
+// per instruction and flood the LSU (measured: ~5.6k L1 wavefronts per step, which also delayed
+// the flag polls by ~3 us).  Instead 4 lanes share one row segment (8 rows per instruction) and
+// a padded per-warp smem tile transposes between that layout and the thread-per-row layout the
+// TMEM accumulator arrives in.
+static constexpr int STG_LD = 20;            // floats per staged row (16 + 4 pad, keeps 16 B alignment)
+static constexpr int STG_WARP = 32 * STG_LD; // floats per warp
+
+__device__ __forceinline__ void coop_ldg(const float* base, size_t row_stride, int rows_valid, int lane, float4 (&v)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    v[i] = r < rows_valid ? *reinterpret_cast<const float4*>(base + (size_t)r * row_stride + 4 * (lane & 3))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void coop_stg(float* base, size_t row_stride, int rows_valid, int lane, const float4 (&v)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    if (r < rows_valid) *reinterpret_cast<float4*>(base + (size_t)r * row_stride + 4 * (lane & 3)) = v[i];
+  }
+}
+// cooperative registers -> staging -> this thread's row (16 floats)
+__device__ __forceinline__ void coop_to_row(float* stg, int lane, const float4 (&v)[4], float* mine) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (8 * i + (lane >> 2)) * STG_LD + 4 * (lane & 3)) = v[i];
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 x = *reinterpret_cast<const float4*>(stg + lane * STG_LD + 4 * q);
+    mine[4 * q] = x.x; mine[4 * q + 1] = x.y; mine[4 * q + 2] = x.z; mine[4 * q + 3] = x.w;
+  }
+}
+// this thread's row (16 floats) -> staging -> cooperative registers
+__device__ __forceinline__ void row_to_coop(float* stg, int lane, const float* mine, float4 (&v)[4]) {
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * q) = make_float4(mine[4 * q], mine[4 * q + 1], mine[4 * q + 2], mine[4 * q + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(stg + (8 * i + (lane >> 2)) * STG_LD + 4 * (lane & 3));
+}
+// 16 bf16 per row (packed as 8 words): 2 lanes share a row segment, 16 rows per instruction
+__device__ __forceinline__ void row_bf16_to_global(uint32_t* stg, int lane, const uint32_t (&w8)[8], bf16* base, size_t row_stride,
+                                                   int rows_valid) {
+  __syncwarp();
+  *reinterpret_cast<uint4*>(stg + lane * 12) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+  *reinterpret_cast<uint4*>(stg + lane * 12 + 4) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = 16 * i + (lane >> 1), hsel = lane & 1;
+    const uint4 x = *reinterpret_cast<const uint4*>(stg + r * 12 + 4 * hsel);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(base + (size_t)r * row_stride + 8 * hsel) = x;
+  }
+}
 
 struct LstmFwdP {
   float* gates;        // (T*B, 4H) fp32: in = x W_ih^T + b (hoisted), out = activated gates i,f,g,o
@@ -45,6 +114,7 @@ struct LstmFwdP {
   long long mem_ld;
   uint32_t* flags;     // ((T+1) * n_mt) arrival counters, zeroed before launch
   int T, B, H, n_mt, n_slices, KB;
+  long long* trace;    // debug: per-step clock64 stamps of CTA (0,0), 8 per step (nullable)
 };
 
 __global__ void __launch_bounds__(160, 1)
@@ -78,16 +148,19 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   if (warp == 4) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      long long* tr = p.trace;
       mbar_expect_tx(&w_full, p.KB * 8192);
       for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, &w_full, kb * 64, slice * 64);
       for (int t = 0; t < p.T; ++t) {
         if (t > 0) {
           mbar_wait(&mma_done, (t - 1) & 1);                       // sA is free again
           const uint32_t* f = p.flags + (size_t)t * p.n_mt + mt;    // h_{t-1} complete for this m-tile?
-          while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
+          while (ld_relaxed_gpu(f) < (uint32_t)p.n_slices) {
           }
-          fence_proxy_async();
+          fence_acq_rel_gpu();      // acquire: orders the counter observation before the loads below
+          fence_proxy_async();      // ... and hands that ordering to the async proxy (TMA)
         }
+        if (tr) { const long long g = gtime(); atomicMin((unsigned long long*)&tr[t * 8 + 0], (unsigned long long)g); atomicMax((unsigned long long*)&tr[t * 8 + 1], (unsigned long long)g); }
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_expect_tx(&a_full[kb], 16384);
           tma_load_2d(sA + kb * 16384, &tmH, &a_full[kb], kb * 64, t * B + mt * 128);
@@ -104,27 +177,31 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             umma_bf16(tmem_base, umma_smem_desc(a_addr + k * 32, 16, 1024), umma_smem_desc(b_addr + k * 32, 16, 1024),
                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
+        if (tr) atomicMax((unsigned long long*)&tr[t * 8 + 7], (unsigned long long)gtime());
         umma_commit(&mma_done);
       }
     }
   } else {
     // ---- epilogue warps: thread = batch row, 16 hidden units x 4 gates ----
     const int row = warp * 32 + lane;
-    const int m = mt * 128 + row;
+    const int m0w = mt * 128 + warp * 32;                 // first batch row of this warp
+    const int m = m0w + lane;
     const bool valid = m < B;
+    const int rows_valid = max(0, min(32, B - m0w));
     const int j0 = slice * 16;
+    float* stg = reinterpret_cast<float*>(sA + p.KB * 16384) + warp * STG_WARP;
     float c[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) c[u] = 0.f;
     for (int t = 0; t < p.T; ++t) {
-      // prefetch the hoisted pre-gates of this row (independent of the recurrence)
-      float4 gx[16];
-      float* grow = p.gates + ((size_t)t * B + (valid ? m : 0)) * G + j0;
+      // prefetch the hoisted pre-gates of this warp's 32 rows (independent of the recurrence)
+      float* gbase = p.gates + ((size_t)t * B + m0w) * G + j0;
+      float4 gxc[4][4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) gx[g * 4 + v] = *reinterpret_cast<const float4*>(grow + g * H + 4 * v);
+      for (int g = 0; g < 4; ++g) coop_ldg(gbase + g * H, G, rows_valid, lane, gxc[g]);
       mbar_wait(&mma_done, t & 1);
+      long long* tre = (p.trace && row == 0) ? p.trace : nullptr;
+      if (tre) { const long long g = gtime(); atomicMin((unsigned long long*)&tre[t * 8 + 2], (unsigned long long)g); atomicMax((unsigned long long*)&tre[t * 8 + 3], (unsigned long long)g); }
       tc_fence_after_sync();
       float acc[64];
 #pragma unroll
@@ -132,46 +209,60 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(&tmem_free);
-      if (valid) {
-        const float* gxf = reinterpret_cast<const float*>(gx);
-        float hv[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const float ig = sigm_fast(acc[u] + gxf[u]);
-          const float fg = sigm_fast(acc[16 + u] + gxf[16 + u]);
-          const float gg = tanh_fast(acc[32 + u] + gxf[32 + u]);
-          const float og = sigm_fast(acc[48 + u] + gxf[48 + u]);
-          c[u] = fmaf(fg, c[u], ig * gg);
-          hv[u] = og * tanh_fast(c[u]);
-          acc[u] = ig; acc[16 + u] = fg; acc[32 + u] = gg; acc[48 + u] = og;
-        }
+      for (int g = 0; g < 4; ++g) {
+        float gxr[16];
+        coop_to_row(stg, lane, gxc[g], gxr);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+        for (int u = 0; u < 16; ++u) acc[g * 16 + u] += gxr[u];
+      }
+      float hv[16];
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
-            *reinterpret_cast<float4*>(grow + g * H + 4 * v) =
-                make_float4(acc[g * 16 + 4 * v], acc[g * 16 + 4 * v + 1], acc[g * 16 + 4 * v + 2], acc[g * 16 + 4 * v + 3]);
-        float* crow = p.cs + ((size_t)(t + 1) * B + m) * H + j0;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) *reinterpret_cast<float4*>(crow + 4 * v) = make_float4(c[4 * v], c[4 * v + 1], c[4 * v + 2], c[4 * v + 3]);
+      for (int u = 0; u < 16; ++u) {
+        const float ig = sigm_fast(acc[u]);
+        const float fg = sigm_fast(acc[16 + u]);
+        const float gg = tanh_fast(acc[32 + u]);
+        const float og = sigm_fast(acc[48 + u]);
+        c[u] = fmaf(fg, c[u], ig * gg);
+        hv[u] = og * tanh_fast(c[u]);
+        acc[u] = ig; acc[16 + u] = fg; acc[32 + u] = gg; acc[48 + u] = og;
+      }
+      // h_t first: it is the only thing the other CTAs are waiting for
+      {
         uint32_t hp[8];
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
           __nv_bfloat162 t2 = __floats2bfloat162_rn(hv[2 * v], hv[2 * v + 1]);
           hp[v] = *reinterpret_cast<uint32_t*>(&t2);
         }
-        bf16* hrow = p.hs + ((size_t)(t + 1) * B + m) * H + j0;
-        *reinterpret_cast<uint4*>(hrow) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        *reinterpret_cast<uint4*>(hrow + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-        if (p.mem) {
-          float* mrow = p.mem + (size_t)m * p.mem_ld + (size_t)t * H + j0;
+        row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.hs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid);
+      }
+      if (tre) atomicMax((unsigned long long*)&tre[t * 8 + 6], (unsigned long long)gtime());
+      // publish: CTA barrier, then ONE thread fences (cumulativity covers the CTA's h stores)
+      // and bumps the arrival counter
+      epi_bar_sync();
+      if (row == 0) {
+        __threadfence();
+        red_relaxed_gpu_add(p.flags + (size_t)(t + 1) * p.n_mt + mt, 1u);   // the fence above is the release
+        if (tre) { const long long g = gtime(); atomicMin((unsigned long long*)&tre[t * 8 + 4], (unsigned long long)g); atomicMax((unsigned long long*)&tre[t * 8 + 5], (unsigned long long)g); }
+      }
+      // everything else (saved activations for the backward pass, c_t, the attention-memory
+      // copy) is off the critical path and overlaps the wait for the next step
+      {
+        float4 tmp[4];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) *reinterpret_cast<float4*>(mrow + 4 * v) = make_float4(hv[4 * v], hv[4 * v + 1], hv[4 * v + 2], hv[4 * v + 3]);
+        for (int g = 0; g < 4; ++g) {
+          row_to_coop(stg, lane, acc + g * 16, tmp);
+          coop_stg(gbase + g * H, G, rows_valid, lane, tmp);
+        }
+        row_to_coop(stg, lane, c, tmp);
+        coop_stg(p.cs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid, lane, tmp);
+        if (p.mem) {
+          row_to_coop(stg, lane, hv, tmp);
+          coop_stg(p.mem + (size_t)m0w * p.mem_ld + (size_t)t * H + j0, (size_t)p.mem_ld, rows_valid, lane, tmp);
         }
       }
-      __threadfence();
-      epi_bar_sync();
-      if (row == 0) red_release_gpu_add(p.flags + (size_t)(t + 1) * p.n_mt + mt, 1u);
+      (void)valid;
     }
   }
   tc_fence_before_sync();
@@ -232,8 +323,9 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       int i = 0;
       for (int t = T - 2; t >= 0; --t) {           // step t consumes dG_{t+1}
         const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
-        while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
+        while (ld_relaxed_gpu(f) < (uint32_t)p.n_slices) {
         }
+        fence_acq_rel_gpu();
         fence_proxy_async();
         for (int kb = 0; kb < p.NKB; ++kb, ++i) {
           const int s = i % BWD_STAGES, ph = (i / BWD_STAGES) & 1;
@@ -336,9 +428,11 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           *reinterpret_cast<uint4*>(drow + g * H + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
         }
       }
-      __threadfence();
       epi_bar_sync();
-      if (row == 0) red_release_gpu_add(p.flags + (size_t)t * p.n_mt + mt, 1u);
+      if (row == 0) {
+        __threadfence();
+        red_relaxed_gpu_add(p.flags + (size_t)t * p.n_mt + mt, 1u);
+      }
     }
   }
   tc_fence_before_sync();
@@ -380,6 +474,8 @@ __global__ void sum_partials_kernel(const float* __restrict__ a, int na, const f
 }
 
 // ---- host -----------------------------------------------------------------------------------
+static long long* g_lstm_trace = nullptr;   // debug hook, see mmqg_debug_lstm_trace()
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -436,14 +532,14 @@ static int launch_coop(Kern kern, dim3 grid, int threads, size_t smem, const CUt
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, long long mem_ld,
                          uint32_t* flags, int T, int B, int H, cudaStream_t st) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
-  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64};
+  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, g_lstm_trace};
   CUtensorMap tmW, tmH;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_fwd, 4 * (uint64_t)H, H, H, 64, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmH, hs, (uint64_t)(T + 1) * B, H, H, 128, 64));
-  const size_t smem = (size_t)p.KB * (8192 + 16384) + 1024;
+  const size_t smem = (size_t)p.KB * (8192 + 16384) + 4 * STG_WARP * sizeof(float) + 1024;
   static bool attr = false;
   if (!attr) {
-    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 16384) + 1024));
+    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 16384) + 4 * STG_WARP * sizeof(float) + 1024));
     attr = true;
   }
   MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(T + 1) * p.n_mt, st));
@@ -478,3 +574,7 @@ int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const voi
 }
 
 }  // namespace mmqg
+
+// Debug hook (not part of the product path): device buffer of 8*T int64 that the next forward
+// persistent launches fill with clock64() stamps of CTA (0,0); pass NULL to switch off.
+extern "C" void mmqg_debug_lstm_trace(void* dev_buf) { mmqg::g_lstm_trace = reinterpret_cast<long long*>(dev_buf); }
