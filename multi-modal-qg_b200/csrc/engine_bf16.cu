@@ -156,8 +156,43 @@ static bool persist_enabled() {
   }
   return v != 0;
 }
-static bool persist_text(const mmqg_dims& d) { return persist_enabled() && lstm_persist_ok(d.B, d.H); }
-static bool persist_video(const mmqg_dims& d) { return persist_enabled() && lstm_persist_ok(d.B, d.H_v); }
+static bool cluster_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // Off by default: measured on B200 at B=256, H=512 the cluster variant (16-CTA clusters, TMA
+    // multicast, 4-slot ring recycled cluster-wide) runs 7.7 / 16 us per step forward / backward
+    // against 6.0 / 9.7 us for the global-flag kernels -- the cluster-wide slot round trip caps
+    // the streaming rate at ring_bytes / latency.  MMQG_CLUSTER=1 selects it.
+    const char* e = getenv("MMQG_CLUSTER");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+// 2 = cluster kernels (barrier.cluster + TMA multicast), 1 = global-flag persistent kernels, 0 = per-step launches
+static int persist_kind(int B, int H) {
+  if (!persist_enabled()) return 0;
+  if (cluster_enabled() && lstm_cluster_ok(B, H)) return 2;
+  return lstm_persist_ok(B, H) ? 1 : 0;
+}
+static bool persist_text(const mmqg_dims& d) { return persist_kind(d.B, d.H) != 0; }
+static bool persist_video(const mmqg_dims& d) { return persist_kind(d.B, d.H_v) != 0; }
+static int pack_rec(const float* w_hh, void* fwd, void* bwd, int B, int H, cudaStream_t st) {
+  if (persist_kind(B, H) == 2) {
+    MMQG_TRY(pack_whh_cluster(w_hh, fwd, H, st));
+    return pack_whh(w_hh, nullptr, bwd, H, st);
+  }
+  return pack_whh(w_hh, fwd, bwd, H, st);
+}
+static int rec_fwd(float* gates, float* cs, void* hs, const void* wp, float* mem, long long mem_ld, uint32_t* flags, int T, int B,
+                   int H, cudaStream_t st) {
+  if (persist_kind(B, H) == 2) return lstm_seq_fwd_cluster(gates, cs, hs, wp, mem, mem_ld, T, B, H, st);
+  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, mem_ld, flags, T, B, H, st);
+}
+static int rec_bwd(const float* acts, const float* cs, void* dg, const void* wp, const float* ext, long long ts, long long ld,
+                   const float* dh_last, const float* dc_last, uint32_t* flags, int T, int B, int H, cudaStream_t st) {
+  if (persist_kind(B, H) == 2) return lstm_seq_bwd_cluster(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, T, B, H, st);
+  return lstm_seq_bwd_persist(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, flags, T, B, H, st);
+}
 
 // fp32 parameters -> packed bf16 caches + summed biases + concatenated attention bias
 static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cudaStream_t st) {
@@ -188,8 +223,8 @@ static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cuda
   }
   MMQG_TRY(cvt_f32_bf16_2d(P.out_w, H, w.wo, H, d.V, H, H, st));
   if (persist_text(d))
-    for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_whh(P.text_w_hh[l], w.wtp_f[l], w.wtp_b[l], H, st));
-  if (persist_video(d)) MMQG_TRY(pack_whh(P.vid_w_hh, w.wvp_f, w.wvp_b, Hv, st));
+    for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_rec(P.text_w_hh[l], w.wtp_f[l], w.wtp_b[l], d.B, H, st));
+  if (persist_video(d)) MMQG_TRY(pack_rec(P.vid_w_hh, w.wvp_f, w.wvp_b, d.B, Hv, st));
   return 0;
 }
 
@@ -208,7 +243,7 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
                   w.acts_v + (size_t)t * B * Gv, Gv).bias(w.bsum_vid).run(st));
     MMQG_CUDA(cudaMemsetAsync(w.hs_v, 0, sizeof(b16) * (size_t)B * Hv, st));
     MMQG_CUDA(cudaMemsetAsync(w.cs_v, 0, sizeof(float) * (size_t)B * Hv, st));
-    MMQG_TRY(lstm_seq_fwd_persist(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags, d.T_v, B, Hv, st));
+    MMQG_TRY(rec_fwd(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags, d.T_v, B, Hv, st));
   } else
   for (int t = 0; t < d.T_v; ++t) {
     StepGemmScope step_scope;
@@ -230,8 +265,8 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
     if (persist_text(d)) {
       MMQG_CUDA(cudaMemsetAsync(w.hs_text[l], 0, sizeof(b16) * (size_t)B * H, st));
       MMQG_CUDA(cudaMemsetAsync(w.cs_text[l], 0, sizeof(float) * (size_t)B * H, st));
-      MMQG_TRY(lstm_seq_fwd_persist(w.acts_text[l], w.cs_text[l], w.hs_text[l], w.wtp_f[l], l == d.L - 1 ? w.m_txt : nullptr,
-                                    (long long)d.TM * H, w.flags, d.T_t, B, H, st));
+      MMQG_TRY(rec_fwd(w.acts_text[l], w.cs_text[l], w.hs_text[l], w.wtp_f[l], l == d.L - 1 ? w.m_txt : nullptr,
+                       (long long)d.TM * H, w.flags, d.T_t, B, H, st));
       continue;
     }
     for (int t = 0; t < d.T_t; ++t) {
@@ -384,8 +419,8 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
     const int Hv = d.H_v, Gv = 4 * d.H_v;
     const long long pv = (long long)B * Hv;
     if (persist_video(d)) {
-      MMQG_TRY(lstm_seq_bwd_persist(w.acts_v, w.cs_v, w.dg_v, w.wvp_b, w.dm_vid, Hv, (long long)d.AM * Hv, nullptr, nullptr,
-                                    w.flags, d.T_v, B, Hv, st));
+      MMQG_TRY(rec_bwd(w.acts_v, w.cs_v, w.dg_v, w.wvp_b, w.dm_vid, Hv, (long long)d.AM * Hv, nullptr, nullptr,
+                       w.flags, d.T_v, B, Hv, st));
     } else
     for (int t = d.T_v - 1; t >= 0; --t) {
       StepGemmScope step_scope;
@@ -416,8 +451,8 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
       MMQG_TRY(sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, w.dh_last, B * H, st));
       const float* ext = l == L - 1 ? w.dm_txt : w.dx_text;
       const long long ts = l == L - 1 ? H : (long long)B * H, ld = l == L - 1 ? (long long)d.TM * H : H;
-      MMQG_TRY(lstm_seq_bwd_persist(w.acts_text[l], w.cs_text[l], w.dg_text[l], w.wtp_b[l], ext, ts, ld, w.dh_last, w.dc[l],
-                                    w.flags, d.T_t, B, H, st));
+      MMQG_TRY(rec_bwd(w.acts_text[l], w.cs_text[l], w.dg_text[l], w.wtp_b[l], ext, ts, ld, w.dh_last, w.dc[l],
+                       w.flags, d.T_t, B, H, st));
     } else
     for (int t = d.T_t - 1; t >= 0; --t) {
       StepGemmScope step_scope;

@@ -54,6 +54,13 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
 int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
                          int T, int B, int H, cudaStream_t st);
+// cluster variant (lstm_cluster.cu): cluster barrier + TMA multicast instead of global flags
+bool lstm_cluster_ok(int B, int H);
+int pack_whh_cluster(const float* w_hh, void* fwd_packed, int H, cudaStream_t st);
+int lstm_seq_fwd_cluster(float* gates, float* cs, void* hs, const void* wp_fwd32, float* mem, long long mem_ld, int T, int B,
+                         int H, cudaStream_t st);
+int lstm_seq_bwd_cluster(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext, long long ext_ts,
+                         long long ext_ld, const float* dh_last, const float* dc_last, int T, int B, int H, cudaStream_t st);
 // bf16-mode orchestration (engine_bf16.cu)
 size_t train_workspace_bytes_bf16(const mmqg_dims& d, int T_q);
 int check_dims_bf16(const mmqg_dims& d);
