@@ -10,11 +10,12 @@
 // dG^T X (both MN-major).  Replaces the addmm/mm calls of the reference (SURVEY.md section
 // 2.3) in bf16 mode; the fp32 SIMT twin is gemm_f32.cu.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2-5 epilogue
-// (TMEM lane quarter = warp % 4).  Tile 128 x BN x 64, 6-stage (BN=128) ring, one tile per CTA;
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2-9 epilogue
+// (TMEM lane quarter = warp % 4, two warps per quarter split the columns).  Tile 128 x BN x 64, 6-stage (BN=128) ring, one tile per CTA;
 // split_k > 1 writes fp32 partial tiles that the caller reduces.
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace mmqg {
 
@@ -22,16 +23,9 @@ using namespace tc;
 
 static constexpr int TBM = 128, TBK = 64;
 
-struct TcGemmP {
-  int M, N, nk1, nk2;          // nk*: number of 64-wide k-blocks of each operand pair
-  void* C; int ldc; int c_bf16;
-  const float* Cin; int ldcin; float beta, alpha;
-  const float* bias;
-  int split_k; long long c_split_stride;
-};
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, TcGemmP p) {
   constexpr int A_BYTES = TBM * TBK * 2, B_BYTES = BN * TBK * 2;
@@ -109,69 +103,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(&accum_full);      // accumulator complete
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> smem transpose -> coalesced global ----
-    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  Writing
-    // rows straight to global would touch 32 different lines per instruction, so every
-    // 32x32 block goes through a padded per-warp staging tile (the operand ring is free once
-    // accum_full fires) and leaves with lanes along the columns: 128 contiguous bytes per
-    // warp store, and the same for the Cin reads.
-    const int q = warp & 3;
-    const bool lead = blockIdx.z == 0;
-    float* Cf = reinterpret_cast<float*>(p.C) + (size_t)blockIdx.z * p.c_split_stride;
-    __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
-    float* stg = reinterpret_cast<float*>(smem) + q * (32 * 33);
-    const int mrow0 = m0 + 32 * q;
-    const int rows = min(32, p.M - mrow0);
-    const bool use_cin = lead && p.Cin != nullptr;
-    // The addend tile is fetched while the main loop is still running: chunk 0 before the
-    // accumulator is ready, chunk c+1 before chunk c is stored (C may alias Cin, so these loads
-    // are explicitly hoisted above the stores).
-    constexpr int HR = 16;                       // rows per addend batch
-    float cin[HR];
-    auto load_cin = [&](int idx) {               // idx = 2*chunk + half
-      const int n = n0 + (idx >> 1) * 32 + lane;
-      const int r0 = (idx & 1) * HR;
-#pragma unroll
-      for (int r = 0; r < HR; ++r)
-        cin[r] = (n < p.N && r0 + r < rows) ? p.Cin[(size_t)(mrow0 + r0 + r) * p.ldcin + n] : 0.f;
-    };
-    if (use_cin) load_cin(0);
+    // ---- epilogue (8 warps: 2 per TMEM lane quarter, each half of the tile's columns) ----
+    // The operand ring is idle once accum_full fires, so it doubles as the staging buffer.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const EpiOut out = make_epi_out(p, blockIdx.z, blockIdx.z == 0);
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * EPI_STG_FLOATS;
     mbar_wait(&accum_full, 0);
     tc_fence_after_sync();
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      {
-        float v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c * 32, v);
-        tmem_ld_wait();
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-        __syncwarp();
-      }
-      const int n = n0 + c * 32 + lane;
-      const float bias = (lead && p.bias && n < p.N) ? p.bias[n] : 0.f;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float cur[HR];
-#pragma unroll
-        for (int r = 0; r < HR; ++r) cur[r] = use_cin ? cin[r] : 0.f;
-        const int idx = 2 * c + half;
-        if (use_cin && idx + 1 < 2 * (BN / 32)) load_cin(idx + 1);
-        if (n < p.N) {
-#pragma unroll
-          for (int r = 0; r < HR; ++r) {
-            const int rr = half * HR + r;
-            if (rr < rows) {
-              const size_t m = (size_t)(mrow0 + rr);
-              const float x = p.alpha * stg[rr * 33 + lane] + bias + p.beta * cur[r];
-              if (p.c_bf16) Cb[m * p.ldc + n] = __float2bfloat16_rn(x);
-              else Cf[m * p.ldc + n] = x;
-            }
-          }
-        }
-      }
-    }
+    constexpr int NCH = BN / 64;
+    epilogue_block<NCH>(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + half * (BN / 2), stg, out, m0 + 32 * q,
+                        n0 + half * (BN / 2), lane, nullptr);
     tc_fence_before_sync();
   }
   __syncthreads();
@@ -229,7 +170,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& b, const CUtensorM
     attr = true;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM), p.split_k);
-  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, 192, SMEM, st>>>(a, b, a2, b2, p);
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, 320, SMEM, st>>>(a, b, a2, b2, p);
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -242,7 +183,10 @@ int gemm_bf16(const mmqg_gemm_bf16_args& g, cudaStream_t st) {
   // twice as many SMs pull operands; everything else 128.
   const int want_split = g.split_k > 1 ? g.split_k : 1;
   const bool narrow = (long long)ceil_div(g.M, TBM) * ceil_div(g.N, 128) * want_split < 96 && g.N > 64;
-  const int BN = narrow ? 64 : 128;
+  // Large problems go to the persistent 128x256-tile kernel (double-buffered accumulators).
+  static const bool persist_on = []() { const char* e = getenv("MMQG_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
+  const bool persist = persist_on && want_split == 1 && (long long)ceil_div(g.M, TBM) * ceil_div(g.N, 256) >= 120;
+  const int BN = persist ? 256 : (narrow ? 64 : 128);
   CUtensorMap ta, tb, ta2, tb2;
   auto mk_a = [&](CUtensorMap* t, const void* A, int lda, int K) {
     return amn ? make_tmap_bf16_2d(t, A, K, g.M, lda, 64, 64) : make_tmap_bf16_2d(t, A, g.M, K, lda, TBM, 64);
@@ -274,6 +218,7 @@ int gemm_bf16(const mmqg_gemm_bf16_args& g, cudaStream_t st) {
   }
   MMQG_PROBE(tl_gemm_class, 2.0 * g.M * g.N * ((double)g.K + g.K2),
              2.0 * ((double)g.M + g.N) * ((double)g.K + g.K2) + (g.c_bf16 ? 2.0 : 4.0) * g.M * g.N);
+  if (persist) return gemm_tc_persist_launch(ta, tb, ta2, tb2, p, amn, bmn, st);
   if (narrow) {
     if (!amn && !bmn) return launch_tc<64, false, false>(ta, tb, ta2, tb2, p, st);
     if (!amn && bmn) return launch_tc<64, false, true>(ta, tb, ta2, tb2, p, st);

@@ -168,6 +168,18 @@ __device__ __forceinline__ bool elect_one() {
 
 }  // namespace tc
 
+// Parameters shared by the tcgen05 GEMM kernels (gemm_tc.cu, gemm_tc_persist.cu).
+struct TcGemmP {
+  int M, N, nk1, nk2;          // nk*: number of 64-wide k-blocks of each operand pair
+  void* C; int ldc; int c_bf16;
+  const float* Cin; int ldcin; float beta, alpha;
+  const float* bias;
+  int split_k; long long c_split_stride;
+};
+// Persistent 128x256-tile variant for large problems (gemm_tc_persist.cu).
+int gemm_tc_persist_launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2,
+                           const TcGemmP& p, bool a_mn, bool b_mn, cudaStream_t st);
+
 // ---- host side: tensor maps ---------------------------------------------------------------
 // 2-D bf16 row-major tensor (rows x cols, leading dimension ld elements), box = box_cols x box_rows,
 // SWIZZLE_128B (box_cols * 2 bytes must be 128).  Returns 0 or an mmqg status.
