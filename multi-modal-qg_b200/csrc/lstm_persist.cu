@@ -196,9 +196,15 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     for (int t = 0; t < p.T; ++t) {
       // prefetch the hoisted pre-gates of this warp's 32 rows (independent of the recurrence)
       float* gbase = p.gates + ((size_t)t * B + m0w) * G + j0;
-      float4 gxc[4][4];
+      float gxr[64];
+      {
+        float4 gxc[4][4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) coop_ldg(gbase + g * H, G, rows_valid, lane, gxc[g]);
+        for (int g = 0; g < 4; ++g) coop_ldg(gbase + g * H, G, rows_valid, lane, gxc[g]);
+        // transpose to thread-per-row while the tensor core is still busy with this step
+#pragma unroll
+        for (int g = 0; g < 4; ++g) coop_to_row(stg, lane, gxc[g], gxr + g * 16);
+      }
       mbar_wait(&mma_done, t & 1);
       long long* tre = (p.trace && row == 0) ? p.trace : nullptr;
       if (tre) { const long long g = gtime(); atomicMin((unsigned long long*)&tre[t * 8 + 2], (unsigned long long)g); atomicMax((unsigned long long*)&tre[t * 8 + 3], (unsigned long long)g); }
@@ -210,12 +216,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       tc_fence_before_sync();
       mbar_arrive(&tmem_free);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float gxr[16];
-        coop_to_row(stg, lane, gxc[g], gxr);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) acc[g * 16 + u] += gxr[u];
-      }
+      for (int u = 0; u < 64; ++u) acc[u] += gxr[u];
       float hv[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
@@ -286,7 +287,7 @@ struct LstmBwdP {
   int T, B, H, n_mt, n_slices, NKB;   // NKB = 4H/64
 };
 
-static constexpr int BWD_STAGES = 6;
+static constexpr int BWD_STAGES = 6;     // 144 KB in flight: the streaming rate is ring bytes / TMA round trip
 
 __global__ void __launch_bounds__(192, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, LstmBwdP p) {
@@ -359,31 +360,36 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     }
   } else {
     const int row = warp * 32 + lane;
-    const int m = mt * 128 + row;
+    const int m0w = mt * 128 + warp * 32;
+    const int m = m0w + lane;
     const bool valid = m < B;
-    const int mm = valid ? m : 0;
+    const int rows_valid = max(0, min(32, B - m0w));
     const int j0 = slice * 16;
+    float* stg = reinterpret_cast<float*>(sA + BWD_STAGES * 16384) + warp * STG_WARP;
     float dc[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) dc[u] = (p.dc_last && valid) ? p.dc_last[(size_t)m * H + j0 + u] : 0.f;
     int it = 0;
     for (int t = T - 1; t >= 0; --t) {
-      // prefetch everything that does not depend on the recurrence
-      float4 a4[16], cn4[4], cp4[4], ex4[4];
-      const float* arow = p.acts + ((size_t)t * B + mm) * G + j0;
+      // cooperative prefetch (4 lanes per 64-byte row segment) of everything that does not
+      // depend on the recurrence
+      float4 a4[4][4], cn4[4], cp4[4], ex4[4];
+      const float* abase = p.acts + ((size_t)t * B + m0w) * G + j0;
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < 4; ++g) coop_ldg(abase + g * H, G, rows_valid, lane, a4[g]);
+      coop_ldg(p.cs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid, lane, cn4);
+      coop_ldg(p.cs + ((size_t)t * B + m0w) * H + j0, H, rows_valid, lane, cp4);
+      if (p.dh_ext) coop_ldg(p.dh_ext + (size_t)t * p.ext_ts + (size_t)m0w * p.ext_ld + j0, (size_t)p.ext_ld, rows_valid, lane, ex4);
+      else {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) a4[g * 4 + v] = *reinterpret_cast<const float4*>(arow + g * H + 4 * v);
-      const float* cnrow = p.cs + ((size_t)(t + 1) * B + mm) * H + j0;
-      const float* cprow = p.cs + ((size_t)t * B + mm) * H + j0;
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        cn4[v] = *reinterpret_cast<const float4*>(cnrow + 4 * v);
-        cp4[v] = *reinterpret_cast<const float4*>(cprow + 4 * v);
-        ex4[v] = p.dh_ext ? *reinterpret_cast<const float4*>(p.dh_ext + (size_t)t * p.ext_ts + (size_t)mm * p.ext_ld + j0 + 4 * v)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i2 = 0; i2 < 4; ++i2) ex4[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      float a[64], cn[16], cp[16], ex[16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) coop_to_row(stg, lane, a4[g], a + g * 16);
+      coop_to_row(stg, lane, cn4, cn);
+      coop_to_row(stg, lane, cp4, cp);
+      coop_to_row(stg, lane, ex4, ex);
       float dh[16];
       if (t == T - 1) {
 #pragma unroll
@@ -397,11 +403,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         mbar_arrive(&tmem_free);
         ++it;
       }
-      if (valid) {
-        const float* a = reinterpret_cast<const float*>(a4);
-        const float* cn = reinterpret_cast<const float*>(cn4);
-        const float* cp = reinterpret_cast<const float*>(cp4);
-        const float* ex = reinterpret_cast<const float*>(ex4);
+      {
         float dgv[64];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
@@ -415,7 +417,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           dgv[48 + u] = d * tc_ * og * (1.f - og);
           dc[u] = dct * fg;
         }
-        bf16* drow = p.dg + ((size_t)t * B + m) * G + j0;
+        bf16* dbase = p.dg + ((size_t)t * B + m0w) * G + j0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t w8[8];
@@ -424,8 +426,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             __nv_bfloat162 t2 = __floats2bfloat162_rn(dgv[g * 16 + 2 * v], dgv[g * 16 + 2 * v + 1]);
             w8[v] = *reinterpret_cast<uint32_t*>(&t2);
           }
-          *reinterpret_cast<uint4*>(drow + g * H) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-          *reinterpret_cast<uint4*>(drow + g * H + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+          row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, w8, dbase + g * H, G, rows_valid);
         }
       }
       epi_bar_sync();
@@ -559,10 +560,10 @@ int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const voi
   CUtensorMap tmW, tmG;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_bwd, H, 4 * (uint64_t)H, 4 * (uint64_t)H, 16, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmG, dg, (uint64_t)T * B, 4 * (uint64_t)H, 4 * (uint64_t)H, 128, 64));
-  const size_t smem = (size_t)p.NKB * 2048 + BWD_STAGES * 16384 + 1024;
+  const size_t smem = (size_t)p.NKB * 2048 + BWD_STAGES * 16384 + 4 * STG_WARP * sizeof(float) + 1024;
   static bool attr = false;
   if (!attr) {
-    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 2048 + BWD_STAGES * 16384 + 1024));
+    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 2048 + BWD_STAGES * 16384 + 4 * STG_WARP * (int)sizeof(float) + 1024));
     attr = true;
   }
   MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)T * p.n_mt, st));
