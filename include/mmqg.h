@@ -120,6 +120,9 @@ int mmqg_train_forward(const mmqg_dims* d, const mmqg_tensors* params, const mmq
  *   1 decoder (attention Linears, decoder LSTM; also d/d memories, d/d encoder state)
  *   2 video LSTM      3 text LSTM + shared embedding
  * Phases must be called in order 1,2,3 (2 and 3 are independent of each other).
+ * phase 0 runs the whole backward in one call; in bf16 mode the hoisted weight-gradient
+ * products then run on an internal auxiliary stream beside the persistent BPTT kernels and
+ * are joined back onto `stream` before the call returns (CUDA-graph capturable).
  * Every gradient tensor is overwritten, not accumulated (the reference zeroes grads
  * every iteration, train.py:149-151). */
 int mmqg_train_backward(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,

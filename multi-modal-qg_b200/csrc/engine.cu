@@ -327,7 +327,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   MMQG_REQUIRE(workspace, "null workspace");
   MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
   MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: not implemented yet", dropout_p);
-  MMQG_REQUIRE(phase >= 1 && phase <= 3, "phase %d not in 1..3", phase);
+  MMQG_REQUIRE(phase >= 0 && phase <= 3, "phase %d not in 0..3", phase);
   (void)seed;
   if (mode == MMQG_MODE_BF16)
     return train_backward_bf16(d, *params, *batch, workspace, workspace_bytes, *grads, phase, as_stream(stream));
@@ -342,6 +342,11 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   const long long ps = (long long)B * H;       // split-K partial stride for (B,H) products
   const AttnShape as = attn_shape(d);
 
+  if (phase == 0) {      // whole backward; the fp32 mode simply runs the phases in order
+    for (int ph = 1; ph <= 3; ++ph)
+      MMQG_TRY(mmqg_train_backward(dp, params, batch, workspace, workspace_bytes, grads, ph, dropout_p, seed, mode, stream));
+    return 0;
+  }
   if (phase == 1) {
     // ---- decoder BPTT (reverse of decoder.py:74-107 for t = T_q-1 .. 0) ----
     // pad columns of dS (slots S..S_pad) take part in the K-loops below against zero weight

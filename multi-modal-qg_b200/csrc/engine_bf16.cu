@@ -40,7 +40,7 @@ struct Ws16 {
   // persistent recurrent kernels: gate-slice packed W_hh (forward) and W_hh^T (backward),
   // arrival counters, and the summed d loss / d h_final handed to the text encoder
   b16 *wtp_f[MMQG_MAX_LAYERS], *wtp_b[MMQG_MAX_LAYERS], *wvp_f, *wvp_b;
-  uint32_t* flags;
+  uint32_t *flags, *flags_v;
   float* dh_last;
   int Sp, Ep, Vp, Rc;
   size_t bytes;
@@ -112,6 +112,7 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   for (int l = 0; l < d.L; ++l) { w.wtp_f[l] = c.take<b16>(G * H); w.wtp_b[l] = c.take<b16>(G * H); }
   w.wvp_f = c.take<b16>(Gv * Hv); w.wvp_b = c.take<b16>(Gv * Hv);
   w.flags = c.take<uint32_t>((size_t)((d.T_t > d.T_v ? d.T_t : d.T_v) + 1) * ((B + 127) / 128));
+  w.flags_v = c.take<uint32_t>((size_t)(d.T_v + 1) * ((B + 127) / 128));
   w.dh_last = c.take<float>(B * H);
   w.bytes = align_up(c.off, 256);
   return w;
@@ -344,18 +345,36 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
   return 0;
 }
 
-int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
-                        size_t workspace_bytes, mmqg_tensors& Gd, int phase, cudaStream_t st) {
-  MMQG_TRY(check_dims_bf16(d));
-  Ws16 w = carve16(d, d.T_q, workspace);
-  if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
-  const int B = d.B, H = d.H, G = 4 * d.H, E = d.E, Ep = w.Ep, Q = d.E + d.H, C = d.H + d.H_a + d.H_v, X0 = E + C;
-  const int R = d.T_q * B, Sp = w.Sp, L = d.L;
-  const long long ps = (long long)B * H;
-  AttnShape as = attn_shape16(d);
-  as.ldds16 = Sp;
+// ---- backward -----------------------------------------------------------------------------
+// One auxiliary stream (created lazily, joined back before returning) lets the hoisted
+// weight-gradient products run beside the latency-bound persistent BPTT kernels, which occupy
+// only 64 of the 148 SMs (phase 0 = whole backward, overlapped).
+struct AuxStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[8] = {};
+  int init() {
+    if (s) return 0;
+    MMQG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : ev) MMQG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+  }
+};
+static AuxStream g_aux;
 
-  if (phase == 1) {
+struct Bwd16 {
+  const mmqg_dims& d; const mmqg_tensors& P; const mmqg_batch& bt; Ws16& w; mmqg_tensors& Gd;
+  int B, H, G, E, Ep, Q, C, X0, R, Sp, L;
+  long long ps;
+  Bwd16(const mmqg_dims& d_, const mmqg_tensors& P_, const mmqg_batch& bt_, Ws16& w_, mmqg_tensors& Gd_)
+      : d(d_), P(P_), bt(bt_), w(w_), Gd(Gd_) {
+    B = d.B; H = d.H; G = 4 * d.H; E = d.E; Ep = w.Ep; Q = d.E + d.H; C = d.H + d.H_a + d.H_v; X0 = E + C;
+    R = d.T_q * B; Sp = w.Sp; L = d.L; ps = (long long)B * H;
+  }
+
+  // decoder BPTT, reverse of decoder.py:74-107 for t = T_q-1 .. 0
+  int dec_loop(cudaStream_t st) {
+    AttnShape as = attn_shape16(d);
+    as.ldds16 = Sp;
     MMQG_CUDA(cudaMemsetAsync(w.ds_all, 0, sizeof(float) * (size_t)R * Sp, st));
     MMQG_CUDA(cudaMemsetAsync(w.ds16, 0, sizeof(b16) * (size_t)R * Sp, st));
     for (int t = d.T_q - 1; t >= 0; --t) {
@@ -388,6 +407,12 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
                         nullptr, nullptr, as, st));
       MMQG_TRY(Tc(as.ds16, Sp, false, w.wa_h, H, true, B, H, Sp, w.dq_h, H).split(kSplitB, ps).run(st));
     }
+    // memory gradients feed the encoders' BPTT
+    return attn_dmem(w.attn_all, Sp, w.dctx_all, C, w.dm_txt, w.dm_vid, d.T_q, as, st);
+  }
+
+  // hoisted decoder gradients: LSTM weights/biases, attention Linears, decoder-side embedding rows
+  int dec_hoisted(cudaStream_t st) {
     for (int l = 0; l < L; ++l) {
       const b16* dG = w.dg_dec[l];
       MMQG_TRY(Tc(dG, G, true, w.hs_dec[l], H, true, G, H, R, Gd.dec_w_hh[l], H).run(st));
@@ -399,7 +424,6 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
       }
       MMQG_TRY(colsum_bf16(dG, G, Gd.dec_b_ih[l], Gd.dec_b_hh[l], R, G, 0.f, st));
     }
-    MMQG_TRY(attn_dmem(w.attn_all, Sp, w.dctx_all, C, w.dm_txt, w.dm_vid, d.T_q, as, st));
     MMQG_TRY(Tc(w.ds16, Sp, true, w.e_dec, Ep, true, Sp, E, R, w.attn_dw_cat, Q).run(st));
     MMQG_TRY(Tc(w.ds16, Sp, true, w.hs_dec[L - 1], H, true, Sp, H, R, w.attn_dw_cat + E, Q).run(st));
     MMQG_TRY(colsum(w.ds_all, Sp, w.attn_db_cat, nullptr, R, Sp, 0.f, st));
@@ -411,26 +435,27 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
     }
     MMQG_TRY(Tc(w.dg_dec[0], G, false, w.wd_e, Ep, true, R, E, G, w.de_dec, E).second(w.ds16, Sp, w.wa_e, Ep, Sp).run(st));
     MMQG_CUDA(cudaMemsetAsync(Gd.emb, 0, sizeof(float) * (size_t)d.V * E, st));
-    MMQG_TRY(embedding_scatter_add(Gd.emb, w.idx_dec, w.de_dec, R, E, d.V, st));
-    return 0;
+    return embedding_scatter_add(Gd.emb, w.idx_dec, w.de_dec, R, E, d.V, st);
   }
 
-  if (phase == 2) {
+  // video LSTM BPTT (encoder.py:69), dh_ext(t) = dM_vid(:,t,:), and its weight gradients
+  int video(cudaStream_t st) {
     const int Hv = d.H_v, Gv = 4 * d.H_v;
     const long long pv = (long long)B * Hv;
     if (persist_video(d)) {
-      MMQG_TRY(rec_bwd(w.acts_v, w.cs_v, w.dg_v, w.wvp_b, w.dm_vid, Hv, (long long)d.AM * Hv, nullptr, nullptr,
-                       w.flags, d.T_v, B, Hv, st));
-    } else
-    for (int t = d.T_v - 1; t >= 0; --t) {
-      StepGemmScope step_scope;
-      const bool last = t == d.T_v - 1;
-      b16* dg = w.dg_v + (size_t)t * B * Gv;
-      MMQG_TRY(lstm_pointwise_bwd_bf16(w.acts_v + (size_t)t * B * Gv, Gv, t > 0 ? w.cs_v + (size_t)t * B * Hv : nullptr, Hv,
-                                       w.cs_v + (size_t)(t + 1) * B * Hv, Hv, last ? nullptr : w.dh_rec_vid, Hv, kSplitB, pv,
-                                       nullptr, 0, 0, 0, w.dm_vid + (size_t)t * Hv, d.AM * Hv, w.dc_v, Hv, last ? 1 : 0, dg,
-                                       Gv, B, Hv, st));
-      if (t > 0) MMQG_TRY(Tc(dg, Gv, false, w.wv_hh, Hv, true, B, Hv, Gv, w.dh_rec_vid, Hv).split(kSplitB, pv).run(st));
+      MMQG_TRY(rec_bwd(w.acts_v, w.cs_v, w.dg_v, w.wvp_b, w.dm_vid, Hv, (long long)d.AM * Hv, nullptr, nullptr, w.flags_v,
+                       d.T_v, B, Hv, st));
+    } else {
+      for (int t = d.T_v - 1; t >= 0; --t) {
+        StepGemmScope step_scope;
+        const bool last = t == d.T_v - 1;
+        b16* dg = w.dg_v + (size_t)t * B * Gv;
+        MMQG_TRY(lstm_pointwise_bwd_bf16(w.acts_v + (size_t)t * B * Gv, Gv, t > 0 ? w.cs_v + (size_t)t * B * Hv : nullptr, Hv,
+                                         w.cs_v + (size_t)(t + 1) * B * Hv, Hv, last ? nullptr : w.dh_rec_vid, Hv, kSplitB, pv,
+                                         nullptr, 0, 0, 0, w.dm_vid + (size_t)t * Hv, d.AM * Hv, w.dc_v, Hv, last ? 1 : 0, dg,
+                                         Gv, B, Hv, st));
+        if (t > 0) MMQG_TRY(Tc(dg, Gv, false, w.wv_hh, Hv, true, B, Hv, Gv, w.dh_rec_vid, Hv).split(kSplitB, pv).run(st));
+      }
     }
     if (d.T_v > 1)
       MMQG_TRY(Tc(w.dg_v + (size_t)B * Gv, Gv, true, w.hs_v + (size_t)B * Hv, Hv, true, Gv, Hv, (d.T_v - 1) * B, Gd.vid_w_hh, Hv).run(st));
@@ -439,11 +464,11 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
     for (int t = 0; t < d.T_v; ++t)
       MMQG_TRY(Tc(w.dg_v + (size_t)t * B * Gv, Gv, true, w.frames16 + (size_t)t * d.F_v, d.T_v * d.F_v, true, Gv, d.F_v, B,
                   Gd.vid_w_ih, d.F_v).accumulate(t > 0).run(st));
-    MMQG_TRY(colsum_bf16(w.dg_v, Gv, Gd.vid_b_ih, Gd.vid_b_hh, d.T_v * B, Gv, 0.f, st));
-    return 0;
+    return colsum_bf16(w.dg_v, Gv, Gd.vid_b_ih, Gd.vid_b_hh, d.T_v * B, Gv, 0.f, st);
   }
 
-  for (int l = L - 1; l >= 0; --l) {
+  // BPTT of text layer l (encoder.py:95-100) and the input gradient the layer below needs
+  int text_bptt(int l, cudaStream_t st) {
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
     if (persist_text(d)) {
       // d loss / d h_final = the decoder's gradient w.r.t. its initial state (train.py:169) plus,
@@ -451,22 +476,28 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
       MMQG_TRY(sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, w.dh_last, B * H, st));
       const float* ext = l == L - 1 ? w.dm_txt : w.dx_text;
       const long long ts = l == L - 1 ? H : (long long)B * H, ld = l == L - 1 ? (long long)d.TM * H : H;
-      MMQG_TRY(rec_bwd(w.acts_text[l], w.cs_text[l], w.dg_text[l], w.wtp_b[l], ext, ts, ld, w.dh_last, w.dc[l],
-                       w.flags, d.T_t, B, H, st));
-    } else
-    for (int t = d.T_t - 1; t >= 0; --t) {
-      StepGemmScope step_scope;
-      const bool last = t == d.T_t - 1;
-      b16* dg = w.dg_text[l] + (size_t)t * B * G;
-      const float* dh0 = last ? w.dh_rec[l] : w.dh_rec_enc;
-      const float* dh1 = (last && l == L - 1) ? w.dq_h : nullptr;
-      const float* dh2 = l == L - 1 ? w.dm_txt + (size_t)t * H : w.dx_text + (size_t)t * B * H;
-      const int ldh2 = l == L - 1 ? d.TM * H : H;
-      MMQG_TRY(lstm_pointwise_bwd_bf16(w.acts_text[l] + (size_t)t * B * G, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr,
-                                       H, w.cs_text[l] + (size_t)(t + 1) * B * H, H, dh0, H, kSplitB, ps, dh1, H, kSplitB, ps,
-                                       dh2, ldh2, w.dc[l], H, 0, dg, G, B, H, st));
-      if (t > 0) MMQG_TRY(Tc(dg, G, false, w.wt_hh[l], H, true, B, H, G, w.dh_rec_enc, H).split(kSplitB, ps).run(st));
+      MMQG_TRY(rec_bwd(w.acts_text[l], w.cs_text[l], w.dg_text[l], w.wtp_b[l], ext, ts, ld, w.dh_last, w.dc[l], w.flags,
+                       d.T_t, B, H, st));
+    } else {
+      for (int t = d.T_t - 1; t >= 0; --t) {
+        StepGemmScope step_scope;
+        const bool last = t == d.T_t - 1;
+        b16* dg = w.dg_text[l] + (size_t)t * B * G;
+        const float* dh0 = last ? w.dh_rec[l] : w.dh_rec_enc;
+        const float* dh1 = (last && l == L - 1) ? w.dq_h : nullptr;
+        const float* dh2 = l == L - 1 ? w.dm_txt + (size_t)t * H : w.dx_text + (size_t)t * B * H;
+        const int ldh2 = l == L - 1 ? d.TM * H : H;
+        MMQG_TRY(lstm_pointwise_bwd_bf16(w.acts_text[l] + (size_t)t * B * G, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr,
+                                         H, w.cs_text[l] + (size_t)(t + 1) * B * H, H, dh0, H, kSplitB, ps, dh1, H, kSplitB, ps,
+                                         dh2, ldh2, w.dc[l], H, 0, dg, G, B, H, st));
+        if (t > 0) MMQG_TRY(Tc(dg, G, false, w.wt_hh[l], H, true, B, H, G, w.dh_rec_enc, H).split(kSplitB, ps).run(st));
+      }
     }
+    return Tc(w.dg_text[l], G, false, w.wt_ih[l], Ip, true, d.T_t * B, I, G, w.dx_text, I).run(st);
+  }
+
+  int text_hoisted(int l, cudaStream_t st) {
+    const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
     const b16* dG = w.dg_text[l];
     const b16* X = l == 0 ? w.x0 : w.hs_text[l - 1] + (size_t)B * H;
     MMQG_TRY(Tc(dG, G, true, X, Ip, true, G, I, d.T_t * B, Gd.text_w_ih[l], I).run(st));
@@ -474,11 +505,47 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
       MMQG_TRY(Tc(dG + (size_t)B * G, G, true, w.hs_text[l] + (size_t)B * H, H, true, G, H, (d.T_t - 1) * B, Gd.text_w_hh[l], H).run(st));
     else
       MMQG_CUDA(cudaMemsetAsync(Gd.text_w_hh[l], 0, sizeof(float) * (size_t)G * H, st));
-    MMQG_TRY(colsum_bf16(dG, G, Gd.text_b_ih[l], Gd.text_b_hh[l], d.T_t * B, G, 0.f, st));
-    MMQG_TRY(Tc(dG, G, false, w.wt_ih[l], Ip, true, d.T_t * B, I, G, w.dx_text, I).run(st));
+    return colsum_bf16(dG, G, Gd.text_b_ih[l], Gd.text_b_hh[l], d.T_t * B, G, 0.f, st);
   }
-  MMQG_TRY(embedding_scatter_add(Gd.emb, w.idx_ctx, w.dx_text, d.T_t * B, E, d.V, st));
-  return 0;
+
+  int emb_enc(cudaStream_t st) { return embedding_scatter_add(Gd.emb, w.idx_ctx, w.dx_text, d.T_t * B, E, d.V, st); }
+};
+
+int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                        size_t workspace_bytes, mmqg_tensors& Gd, int phase, cudaStream_t st) {
+  MMQG_TRY(check_dims_bf16(d));
+  Ws16 w = carve16(d, d.T_q, workspace);
+  if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
+  Bwd16 b(d, P, bt, w, Gd);
+  if (phase == 1) {
+    MMQG_TRY(b.dec_loop(st));
+    return b.dec_hoisted(st);
+  }
+  if (phase == 2) return b.video(st);
+  if (phase == 3) {
+    for (int l = d.L - 1; l >= 0; --l) {
+      MMQG_TRY(b.text_bptt(l, st));
+      MMQG_TRY(b.text_hoisted(l, st));
+    }
+    return b.emb_enc(st);
+  }
+  // phase 0: the whole backward with the hoisted products overlapped on the auxiliary stream
+  MMQG_TRY(g_aux.init());
+  cudaStream_t ax = g_aux.s;
+  MMQG_TRY(b.dec_loop(st));
+  MMQG_CUDA(cudaEventRecord(g_aux.ev[0], st));
+  MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[0], 0));
+  MMQG_TRY(b.dec_hoisted(ax));
+  MMQG_TRY(b.video(ax));
+  for (int l = d.L - 1; l >= 0; --l) {
+    MMQG_TRY(b.text_bptt(l, st));
+    MMQG_CUDA(cudaEventRecord(g_aux.ev[1 + l], st));
+    MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[1 + l], 0));
+    MMQG_TRY(b.text_hoisted(l, ax));
+  }
+  MMQG_CUDA(cudaEventRecord(g_aux.ev[7], ax));
+  MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[7], 0));       // join: everything is ordered on `st` again
+  return b.emb_enc(st);
 }
 
 }  // namespace mmqg

@@ -100,12 +100,13 @@ class TrainEngine:
         is called after the gradient group i (0 loss head, 1 decoder, 2 video, 3 text+emb)
         has been enqueued -- the hook the data-parallel all-reduce uses."""
         loss = self.forward(batch, True, grad_scale)
-        if on_phase:
-            on_phase(0)
+        if on_phase is None:
+            self.backward(batch, 0)          # whole backward, hoisted products overlapped internally
+            return loss
+        on_phase(0)
         for ph in (1, 2, 3):
             self.backward(batch, ph)
-            if on_phase:
-                on_phase(ph)
+            on_phase(ph)
         return loss
 
     # -- greedy decode ---------------------------------------------------------------------
