@@ -40,8 +40,8 @@ struct Ws16 {
   // persistent recurrent kernels: gate-slice packed W_hh (forward) and W_hh^T (backward),
   // arrival counters, and the summed d loss / d h_final handed to the text encoder
   b16 *wtp_f[MMQG_MAX_LAYERS], *wtp_b[MMQG_MAX_LAYERS], *wvp_f, *wvp_b;
-  uint32_t *flags, *flags_v;
-  float* dh_last;
+  uint32_t *flags, *flags_v, *flags_t[MMQG_MAX_LAYERS];
+  float *dh_last, *dh_last_l[MMQG_MAX_LAYERS], *dx_emb;
   int Sp, Ep, Vp, Rc;
   size_t bytes;
 };
@@ -114,6 +114,11 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.flags = c.take<uint32_t>((size_t)((d.T_t > d.T_v ? d.T_t : d.T_v) + 1) * ((B + 127) / 128));
   w.flags_v = c.take<uint32_t>((size_t)(d.T_v + 1) * ((B + 127) / 128));
   w.dh_last = c.take<float>(B * H);
+  for (int l = 0; l < d.L; ++l) {
+    w.flags_t[l] = c.take<uint32_t>((size_t)(d.T_t + 1) * ((B + 127) / 128));
+    w.dh_last_l[l] = c.take<float>(B * H);
+  }
+  w.dx_emb = c.take<float>(Rt * d.E);
   w.bytes = align_up(c.off, 256);
   return w;
 }
@@ -187,12 +192,12 @@ static int pack_rec(const float* w_hh, void* fwd, void* bwd, int B, int H, cudaS
 static int rec_fwd(float* gates, float* cs, void* hs, const void* wp, float* mem, long long mem_ld, uint32_t* flags, int T, int B,
                    int H, cudaStream_t st) {
   if (persist_kind(B, H) == 2) return lstm_seq_fwd_cluster(gates, cs, hs, wp, mem, mem_ld, T, B, H, st);
-  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, mem_ld, flags, T, B, H, st);
+  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, mem_ld, flags, T, B, H, 0, st);
 }
 static int rec_bwd(const float* acts, const float* cs, void* dg, const void* wp, const float* ext, long long ts, long long ld,
                    const float* dh_last, const float* dc_last, uint32_t* flags, int T, int B, int H, cudaStream_t st) {
   if (persist_kind(B, H) == 2) return lstm_seq_bwd_cluster(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, T, B, H, st);
-  return lstm_seq_bwd_persist(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, flags, T, B, H, st);
+  return lstm_seq_bwd_persist(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, flags, T, B, H, 0, nullptr, st);
 }
 
 // fp32 parameters -> packed bf16 caches + summed biases + concatenated attention bias
@@ -229,6 +234,46 @@ static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cuda
   return 0;
 }
 
+// Internal auxiliary streams (created lazily; every use forks from and joins back onto the
+// caller's stream, so the calls stay CUDA-graph capturable).  They let (a) the hoisted
+// weight-gradient products run beside the latency-bound persistent BPTT kernels, which occupy
+// only 64 of the 148 SMs, and (b) consecutive LSTM layers overlap chunk by chunk in time.
+struct AuxStream {
+  static constexpr int NS = 4, NE = 96;
+  cudaStream_t s[NS] = {};
+  cudaEvent_t ev[NE] = {};
+  bool ready = false;
+  int init() {
+    if (ready) return 0;
+    for (auto& x : s) MMQG_CUDA(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+    for (auto& e : ev) MMQG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ready = true;
+    return 0;
+  }
+};
+static AuxStream g_aux;
+static constexpr int kMaxChunks = 8;
+// event slots: [0,8) misc, [16,48) forward done(l,c), [48,80) backward done(l,c)
+static cudaEvent_t ev_fwd(int l, int c) { return g_aux.ev[16 + l * kMaxChunks + c]; }
+static cudaEvent_t ev_bwd(int l, int c) { return g_aux.ev[48 + l * kMaxChunks + c]; }
+
+// Number of time chunks the text-encoder layers are pipelined over (1 = layer after layer).
+// Layer l can run chunk c as soon as layer l-1 has finished chunk c, so with the layers on
+// separate streams the serial chain shrinks from L*T_t to about (NC+L-1)/NC * T_t steps.
+static int text_chunks(const mmqg_dims& d) {
+  static int want = -1;
+  if (want < 0) {
+    const char* e = getenv("MMQG_CHUNKS");
+    want = e ? atoi(e) : 4;
+    if (want < 1) want = 1;
+    if (want > kMaxChunks) want = kMaxChunks;
+  }
+  if (persist_kind(d.B, d.H) != 1 || d.L < 2 || d.L > AuxStream::NS) return 1;
+  int nc = want;
+  while (nc > 1 && d.T_t / nc < 8) --nc;
+  return nc;
+}
+
 static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, Ws16& w, cudaStream_t st) {
   const int B = d.B, H = d.H, G = 4 * d.H, Hv = d.H_v, Gv = 4 * d.H_v;
   MMQG_CUDA(cudaMemcpy2DAsync(w.m_aud, sizeof(float) * (size_t)d.AM * d.H_a, bt.audio,
@@ -259,6 +304,36 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
   }
   // text LSTM stack (encoder.py:95-100): hoisted input projection per layer, recurrent part per step
   MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_ctx, w.x0, w.Ep, d.T_t * B, d.E, w.Ep, d.V, st));
+  const int NC = text_chunks(d);
+  if (NC > 1) {
+    // layers pipelined over NC time chunks, one stream per layer
+    MMQG_TRY(g_aux.init());
+    const int CL = (d.T_t + NC - 1) / NC;
+    MMQG_TRY(Tc(w.x0, w.Ep, false, w.wt_ih[0], w.Ep, false, d.T_t * B, G, w.Ep, w.acts_text[0], G).bias(w.bsum_text[0]).run(st));
+    for (int l = 0; l < d.L; ++l) {
+      MMQG_CUDA(cudaMemsetAsync(w.hs_text[l], 0, sizeof(b16) * (size_t)B * H, st));
+      MMQG_CUDA(cudaMemsetAsync(w.cs_text[l], 0, sizeof(float) * (size_t)B * H, st));
+    }
+    MMQG_CUDA(cudaEventRecord(g_aux.ev[0], st));
+    for (int l = 1; l < d.L; ++l) MMQG_CUDA(cudaStreamWaitEvent(g_aux.s[l - 1], g_aux.ev[0], 0));
+    for (int c = 0; c < NC; ++c) {
+      const int t0 = c * CL, nT = (d.T_t - t0 < CL) ? d.T_t - t0 : CL;
+      for (int l = 0; l < d.L; ++l) {
+        cudaStream_t s = l == 0 ? st : g_aux.s[l - 1];
+        if (l > 0) {
+          MMQG_CUDA(cudaStreamWaitEvent(s, ev_fwd(l - 1, c), 0));
+          MMQG_TRY(Tc(w.hs_text[l - 1] + (size_t)(t0 + 1) * B * H, H, false, w.wt_ih[l], H, false, nT * B, G, H,
+                      w.acts_text[l] + (size_t)t0 * B * G, G).bias(w.bsum_text[l]).run(s));
+        }
+        MMQG_TRY(lstm_seq_fwd_persist(w.acts_text[l] + (size_t)t0 * B * G, w.cs_text[l] + (size_t)t0 * B * H,
+                                      w.hs_text[l] + (size_t)t0 * B * H, w.wtp_f[l],
+                                      l == d.L - 1 ? w.m_txt + (size_t)t0 * H : nullptr, (long long)d.TM * H, w.flags_t[l], nT, B,
+                                      H, c > 0 ? 1 : 0, s));
+        MMQG_CUDA(cudaEventRecord(ev_fwd(l, c), s));
+      }
+    }
+    for (int l = 1; l < d.L; ++l) MMQG_CUDA(cudaStreamWaitEvent(st, ev_fwd(l, NC - 1), 0));   // join
+  } else
   for (int l = 0; l < d.L; ++l) {
     const b16* X = l == 0 ? w.x0 : w.hs_text[l - 1] + (size_t)B * H;
     const int Ip = l == 0 ? w.Ep : H;
@@ -346,21 +421,6 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
 }
 
 // ---- backward -----------------------------------------------------------------------------
-// One auxiliary stream (created lazily, joined back before returning) lets the hoisted
-// weight-gradient products run beside the latency-bound persistent BPTT kernels, which occupy
-// only 64 of the 148 SMs (phase 0 = whole backward, overlapped).
-struct AuxStream {
-  cudaStream_t s = nullptr;
-  cudaEvent_t ev[8] = {};
-  int init() {
-    if (s) return 0;
-    MMQG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    for (auto& e : ev) MMQG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    return 0;
-  }
-};
-static AuxStream g_aux;
-
 struct Bwd16 {
   const mmqg_dims& d; const mmqg_tensors& P; const mmqg_batch& bt; Ws16& w; mmqg_tensors& Gd;
   int B, H, G, E, Ep, Q, C, X0, R, Sp, L;
@@ -508,7 +568,45 @@ struct Bwd16 {
     return colsum_bf16(dG, G, Gd.text_b_ih[l], Gd.text_b_hh[l], d.T_t * B, G, 0.f, st);
   }
 
-  int emb_enc(cudaStream_t st) { return embedding_scatter_add(Gd.emb, w.idx_ctx, w.dx_text, d.T_t * B, E, d.V, st); }
+  // text layers pipelined over time chunks (mirror of the forward schedule): layer l runs chunk c
+  // once layer l+1 has produced the input gradient of that chunk.  Layer l uses stream S(l); the
+  // hoisted weight gradients of a finished layer go to `hoist`.
+  int text_pipelined(int NC, cudaStream_t st, cudaStream_t hoist) {
+    const int CL = (d.T_t + NC - 1) / NC;
+    auto S = [&](int l) { return l == L - 1 ? st : g_aux.s[l]; };
+    MMQG_CUDA(cudaEventRecord(g_aux.ev[1], st));
+    for (int l = 0; l < L - 1; ++l) MMQG_CUDA(cudaStreamWaitEvent(S(l), g_aux.ev[1], 0));
+    for (int c = NC - 1; c >= 0; --c) {
+      const int t0 = c * CL, nT = (d.T_t - t0 < CL) ? d.T_t - t0 : CL;
+      const bool tail = c == NC - 1;
+      for (int l = L - 1; l >= 0; --l) {
+        cudaStream_t s = S(l);
+        const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
+        if (l < L - 1) MMQG_CUDA(cudaStreamWaitEvent(s, ev_bwd(l + 1, c), 0));
+        if (tail)   // d loss / d h_final of this layer (decoder initial state, + step-0 attention query on top)
+          MMQG_TRY(sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, w.dh_last_l[l],
+                                B * H, s));
+        const float* ext = l == L - 1 ? w.dm_txt + (size_t)t0 * H : w.dx_text + (size_t)t0 * B * H;
+        const long long ts = l == L - 1 ? H : (long long)B * H, ld = l == L - 1 ? (long long)d.TM * H : H;
+        MMQG_TRY(lstm_seq_bwd_persist(w.acts_text[l] + (size_t)t0 * B * G, w.cs_text[l] + (size_t)t0 * B * H,
+                                      w.dg_text[l] + (size_t)t0 * B * G, w.wtp_b[l], ext, ts, ld, tail ? w.dh_last_l[l] : nullptr,
+                                      w.dc[l], w.flags_t[l], nT, B, H, tail ? 0 : 1, w.dc[l], s));
+        float* dx = l == 0 ? w.dx_emb + (size_t)t0 * B * E : w.dx_text + (size_t)t0 * B * H;
+        MMQG_TRY(Tc(w.dg_text[l] + (size_t)t0 * B * G, G, false, w.wt_ih[l], Ip, true, nT * B, I, G, dx, I).run(s));
+        MMQG_CUDA(cudaEventRecord(ev_bwd(l, c), s));
+        if (c == 0) {
+          MMQG_CUDA(cudaStreamWaitEvent(hoist, ev_bwd(l, 0), 0));
+          MMQG_TRY(text_hoisted(l, hoist));
+        }
+      }
+    }
+    for (int l = 0; l < L - 1; ++l) MMQG_CUDA(cudaStreamWaitEvent(st, ev_bwd(l, 0), 0));   // join the layer streams
+    return 0;
+  }
+
+  int emb_enc(cudaStream_t st, bool chunked) {
+    return embedding_scatter_add(Gd.emb, w.idx_ctx, chunked ? w.dx_emb : w.dx_text, d.T_t * B, E, d.V, st);
+  }
 };
 
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
@@ -522,30 +620,45 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
     return b.dec_hoisted(st);
   }
   if (phase == 2) return b.video(st);
+  const int NC = text_chunks(d);
   if (phase == 3) {
+    if (NC > 1) {
+      MMQG_TRY(g_aux.init());
+      cudaStream_t hoist = g_aux.s[AuxStream::NS - 1];
+      MMQG_CUDA(cudaEventRecord(g_aux.ev[2], st));
+      MMQG_CUDA(cudaStreamWaitEvent(hoist, g_aux.ev[2], 0));
+      MMQG_TRY(b.text_pipelined(NC, st, hoist));
+      MMQG_CUDA(cudaEventRecord(g_aux.ev[7], hoist));
+      MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[7], 0));
+      return b.emb_enc(st, true);
+    }
     for (int l = d.L - 1; l >= 0; --l) {
       MMQG_TRY(b.text_bptt(l, st));
       MMQG_TRY(b.text_hoisted(l, st));
     }
-    return b.emb_enc(st);
+    return b.emb_enc(st, false);
   }
-  // phase 0: the whole backward with the hoisted products overlapped on the auxiliary stream
+  // phase 0: the whole backward with the hoisted products overlapped on an auxiliary stream
   MMQG_TRY(g_aux.init());
-  cudaStream_t ax = g_aux.s;
+  cudaStream_t ax = g_aux.s[AuxStream::NS - 1];
   MMQG_TRY(b.dec_loop(st));
   MMQG_CUDA(cudaEventRecord(g_aux.ev[0], st));
   MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[0], 0));
   MMQG_TRY(b.dec_hoisted(ax));
   MMQG_TRY(b.video(ax));
-  for (int l = d.L - 1; l >= 0; --l) {
-    MMQG_TRY(b.text_bptt(l, st));
-    MMQG_CUDA(cudaEventRecord(g_aux.ev[1 + l], st));
-    MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[1 + l], 0));
-    MMQG_TRY(b.text_hoisted(l, ax));
+  if (NC > 1) {
+    MMQG_TRY(b.text_pipelined(NC, st, ax));
+  } else {
+    for (int l = d.L - 1; l >= 0; --l) {
+      MMQG_TRY(b.text_bptt(l, st));
+      MMQG_CUDA(cudaEventRecord(g_aux.ev[3 + l], st));
+      MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[3 + l], 0));
+      MMQG_TRY(b.text_hoisted(l, ax));
+    }
   }
   MMQG_CUDA(cudaEventRecord(g_aux.ev[7], ax));
   MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[7], 0));       // join: everything is ordered on `st` again
-  return b.emb_enc(st);
+  return b.emb_enc(st, NC > 1);
 }
 
 }  // namespace mmqg

@@ -114,6 +114,7 @@ struct LstmFwdP {
   long long mem_ld;
   uint32_t* flags;     // ((T+1) * n_mt) arrival counters, zeroed before launch
   int T, B, H, n_mt, n_slices, KB;
+  int load_c0;         // 1: c_{-1} is read from slab 0 of cs (continuing a sequence chunk), 0: zeros
   long long* trace;    // debug: per-step clock64 stamps of CTA (0,0), 8 per step (nullable)
 };
 
@@ -193,6 +194,11 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     float c[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) c[u] = 0.f;
+    if (p.load_c0) {
+      float4 c4[4];
+      coop_ldg(p.cs + (size_t)m0w * H + j0, H, rows_valid, lane, c4);
+      coop_to_row(stg, lane, c4, c);
+    }
     for (int t = 0; t < p.T; ++t) {
       // prefetch the hoisted pre-gates of this warp's 32 rows (independent of the recurrence)
       float* gbase = p.gates + ((size_t)t * B + m0w) * G + j0;
@@ -285,6 +291,8 @@ struct LstmBwdP {
   const float* dc_last; // (B,H) fp32 d loss / d c_{T-1} from the consumer of the final state (nullable)
   uint32_t* flags;      // (T * n_mt), zeroed before launch
   int T, B, H, n_mt, n_slices, NKB;   // NKB = 4H/64
+  int has_next;         // 1: dg slab T (first step of the following chunk) exists and feeds step T-1
+  float* dc_out;        // (B,H) receives d loss / d c_{-1} at the end (nullable)
 };
 
 static constexpr int BWD_STAGES = 6;     // 144 KB in flight: the streaming rate is ring bytes / TMA round trip
@@ -322,12 +330,14 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_expect_tx(&w_full, p.NKB * 2048);
       for (int kb = 0; kb < p.NKB; ++kb) tma_load_2d(sW + kb * 2048, &tmW, &w_full, kb * 64, slice * 16);
       int i = 0;
-      for (int t = T - 2; t >= 0; --t) {           // step t consumes dG_{t+1}
-        const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
-        while (ld_relaxed_gpu(f) < (uint32_t)p.n_slices) {
+      for (int t = T - 1 - (p.has_next ? 0 : 1); t >= 0; --t) {   // step t consumes dG_{t+1}
+        if (t + 1 < T) {                           // slab T comes from an earlier launch: already complete
+          const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
+          while (ld_relaxed_gpu(f) < (uint32_t)p.n_slices) {
+          }
+          fence_acq_rel_gpu();
+          fence_proxy_async();
         }
-        fence_acq_rel_gpu();
-        fence_proxy_async();
         for (int kb = 0; kb < p.NKB; ++kb, ++i) {
           const int s = i % BWD_STAGES, ph = (i / BWD_STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -341,7 +351,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       constexpr uint32_t idesc = umma_idesc_bf16(128, 16, 0, 0);
       mbar_wait(&w_full, 0);
       int i = 0, it = 0;
-      for (int t = T - 2; t >= 0; --t, ++it) {
+      for (int t = T - 1 - (p.has_next ? 0 : 1); t >= 0; --t, ++it) {
         if (it > 0) mbar_wait(&tmem_free, (it - 1) & 1);
         tc_fence_after_sync();
         for (int kb = 0; kb < p.NKB; ++kb, ++i) {
@@ -391,7 +401,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       coop_to_row(stg, lane, cp4, cp);
       coop_to_row(stg, lane, ex4, ex);
       float dh[16];
-      if (t == T - 1) {
+      if (t == T - 1 && !p.has_next) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) dh[u] = (p.dh_last && valid) ? p.dh_last[(size_t)m * H + j0 + u] : 0.f;
       } else {
@@ -434,6 +444,11 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         __threadfence();
         red_relaxed_gpu_add(p.flags + (size_t)t * p.n_mt + mt, 1u);
       }
+    }
+    if (p.dc_out) {
+      float4 tmp[4];
+      row_to_coop(stg, lane, dc, tmp);
+      coop_stg(p.dc_out + (size_t)m0w * H + j0, H, rows_valid, lane, tmp);
     }
   }
   tc_fence_before_sync();
@@ -531,9 +546,9 @@ static int launch_coop(Kern kern, dim3 grid, int threads, size_t smem, const CUt
 
 // gates: (T*B,4H) fp32 pre-gates -> activated gates.  wp_fwd: pack_whh forward layout.  hs slab 0 must be zeros.
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, long long mem_ld,
-                         uint32_t* flags, int T, int B, int H, cudaStream_t st) {
+                         uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
-  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, g_lstm_trace};
+  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace};
   CUtensorMap tmW, tmH;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_fwd, 4 * (uint64_t)H, H, H, 64, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmH, hs, (uint64_t)(T + 1) * B, H, H, 128, 64));
@@ -553,13 +568,13 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
 
 int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
-                         int T, int B, int H, cudaStream_t st) {
+                         int T, int B, int H, int has_next, float* dc_out, cudaStream_t st) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_bwd_persist: shape B=%d H=%d not supported", B, H);
   LstmBwdP p{acts, cs, reinterpret_cast<bf16*>(dg), dh_ext, ext_ts, ext_ld, dh_last, dc_last, flags,
-             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64};
+             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64, has_next, dc_out};
   CUtensorMap tmW, tmG;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_bwd, H, 4 * (uint64_t)H, 4 * (uint64_t)H, 16, 64));
-  MMQG_TRY(make_tmap_bf16_2d(&tmG, dg, (uint64_t)T * B, 4 * (uint64_t)H, 4 * (uint64_t)H, 128, 64));
+  MMQG_TRY(make_tmap_bf16_2d(&tmG, dg, (uint64_t)(T + (has_next ? 1 : 0)) * B, 4 * (uint64_t)H, 4 * (uint64_t)H, 128, 64));
   const size_t smem = (size_t)p.NKB * 2048 + BWD_STAGES * 16384 + 4 * STG_WARP * sizeof(float) + 1024;
   static bool attr = false;
   if (!attr) {
