@@ -29,13 +29,14 @@ import torch  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
-    ap.add_argument("--mode", default=os.environ.get("MMQG_MODE", "fp32"), choices=["fp32", "bf16"])
-    ap.add_argument("--cpu-samples", type=int, default=6, help="samples the CPU baseline leg times")
+    ap.add_argument("--mode", default=os.environ.get("MMQG_MODE", "bf16"), choices=["fp32", "bf16"],
+                    help="bf16 = tcgen05 path (BASELINE configs[1] names bf16); fp32 = SIMT parity mode")
+    ap.add_argument("--cpu-samples", type=int, default=32, help="samples the CPU baseline leg times")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--probe", type=int, default=None, help="kernel class the roofline probe times (see mmqg.h)")
@@ -63,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -121,7 +122,7 @@ def run_reference(args, d, rank, world):
     """--impl reference: the CPU path timed on the host cores, same metric/config keys."""
     if rank != 0:
         return
-    per_step = max(1, args.cpu_samples // 2)
+    per_step = max(1, min(8, args.cpu_samples // 4))
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_samples_per_s(d, 1)
     t_total, n_total = 0.0, 0
@@ -296,6 +297,8 @@ def main():
             roof.update({"kernel": names.get(args.probe), "launches_per_step": n.value // 2,
                          "avg_launch_us": 1e3 * tms.value / n.value,
                          "share_of_step": (tms.value / 2) / (ms / args.steps),
+                         "share_note": "summed kernel time / step time; launches of this class overlap on separate "
+                                       "streams, so the sum can exceed their wall-clock share",
                          "peak_source": pk["source"] + (" (sustained bf16 cuBLAS; this kernel is fp32 SIMT)"
                                                         if args.probe in (1, 2) and args.mode == "fp32" else "")})
 

@@ -206,6 +206,9 @@ int attn_fwd(float* scores, int lds, const float* M_txt, const float* M_aud, con
              const AttnShape& s, cudaStream_t st) {
   MMQG_REQUIRE(scores && M_txt && M_aud && M_vid && ctx, "attn_fwd: null pointer");
   MMQG_REQUIRE(s.B > 0 && s.T_t <= s.TM && s.T_v <= s.AM, "attn_fwd: bad shape");
+  if (s.m_txt16 && s.m_vid16 && attn_fast_ok(s, s.m_txt16, M_aud, s.m_vid16))
+    return attn_fwd_fast(scores, lds, s.m_txt16, M_aud, s.m_vid16, true, ctx, ldctx, s, st);
+  if (attn_fast_ok(s, M_txt, M_aud, M_vid)) return attn_fwd_fast(scores, lds, M_txt, M_aud, M_vid, false, ctx, ldctx, s, st);
   const int S = s.TM + 2 * s.AM;
   const size_t smem = (size_t)S * sizeof(float);
   MMQG_REQUIRE(smem <= 48 * 1024, "attn_fwd: %d attention slots exceed the 48 KB staging buffer", S);
@@ -223,6 +226,12 @@ int attn_bwd(const float* attn, float* ds_out, int lds, const float* dctx, int l
              const float* M_aud, const float* M_vid, float* dM_txt, float* dM_vid, const AttnShape& s,
              cudaStream_t st) {
   MMQG_REQUIRE(attn && ds_out && dctx && M_txt && M_aud && M_vid, "attn_bwd: null pointer");
+  if (!dM_txt && !dM_vid) {
+    if (s.m_txt16 && s.m_vid16 && attn_fast_ok(s, s.m_txt16, M_aud, s.m_vid16))
+      return attn_bwd_fast(attn, ds_out, lds, dctx, lddctx, s.m_txt16, M_aud, s.m_vid16, true, s, st);
+    if (attn_fast_ok(s, M_txt, M_aud, M_vid))
+      return attn_bwd_fast(attn, ds_out, lds, dctx, lddctx, M_txt, M_aud, M_vid, false, s, st);
+  }
   const int S = s.TM + 2 * s.AM, C = s.H + s.H_a + s.H_v;
   const size_t smem = (size_t)(2 * S + C) * sizeof(float);
   MMQG_REQUIRE(smem <= 48 * 1024, "attn_bwd: shape exceeds the 48 KB staging buffer");

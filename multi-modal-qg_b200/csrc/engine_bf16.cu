@@ -40,6 +40,7 @@ struct Ws16 {
   // persistent recurrent kernels: gate-slice packed W_hh (forward) and W_hh^T (backward),
   // arrival counters, and the summed d loss / d h_final handed to the text encoder
   b16 *wtp_f[MMQG_MAX_LAYERS], *wtp_b[MMQG_MAX_LAYERS], *wvp_f, *wvp_b;
+  b16 *m_txt16, *m_vid16;     // bf16 attention memories (what the attention kernels read in this mode)
   uint32_t *flags, *flags_v, *flags_t[MMQG_MAX_LAYERS];
   float *dh_last, *dh_last_l[MMQG_MAX_LAYERS], *dx_emb;
   int Sp, Ep, Vp, Rc;
@@ -119,6 +120,8 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
     w.dh_last_l[l] = c.take<float>(B * H);
   }
   w.dx_emb = c.take<float>(Rt * d.E);
+  w.m_txt16 = c.take<b16>(B * d.TM * H);
+  w.m_vid16 = c.take<b16>(B * d.AM * Hv);
   w.bytes = align_up(c.off, 256);
   return w;
 }
@@ -150,7 +153,12 @@ struct Tc {
   int run(cudaStream_t st) { return gemm_bf16(a, st); }
 };
 
-static AttnShape attn_shape16(const mmqg_dims& d) { return AttnShape{d.B, d.TM, d.AM, d.H, d.H_a, d.H_v, d.T_t, d.T_v}; }
+static AttnShape attn_shape16(const mmqg_dims& d, const Ws16& w) {
+  AttnShape a{d.B, d.TM, d.AM, d.H, d.H_a, d.H_v, d.T_t, d.T_v};
+  a.m_txt16 = w.m_txt16;
+  a.m_vid16 = w.m_vid16;
+  return a;
+}
 
 // The encoders run on the persistent recurrent kernels when the shape allows it (lstm_persist.cu);
 // MMQG_PERSIST=0 forces the one-GEMM-plus-pointwise-launch-per-step path (for A/B comparison).
@@ -192,7 +200,7 @@ static int pack_rec(const float* w_hh, void* fwd, void* bwd, int B, int H, cudaS
 static int rec_fwd(float* gates, float* cs, void* hs, const void* wp, float* mem, long long mem_ld, uint32_t* flags, int T, int B,
                    int H, cudaStream_t st) {
   if (persist_kind(B, H) == 2) return lstm_seq_fwd_cluster(gates, cs, hs, wp, mem, mem_ld, T, B, H, st);
-  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, mem_ld, flags, T, B, H, 0, st);
+  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, nullptr, mem_ld, flags, T, B, H, 0, st);
 }
 static int rec_bwd(const float* acts, const float* cs, void* dg, const void* wp, const float* ext, long long ts, long long ld,
                    const float* dh_last, const float* dc_last, uint32_t* flags, int T, int B, int H, cudaStream_t st) {
@@ -327,8 +335,8 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
         }
         MMQG_TRY(lstm_seq_fwd_persist(w.acts_text[l] + (size_t)t0 * B * G, w.cs_text[l] + (size_t)t0 * B * H,
                                       w.hs_text[l] + (size_t)t0 * B * H, w.wtp_f[l],
-                                      l == d.L - 1 ? w.m_txt + (size_t)t0 * H : nullptr, (long long)d.TM * H, w.flags_t[l], nT, B,
-                                      H, c > 0 ? 1 : 0, s));
+                                      nullptr, l == d.L - 1 ? w.m_txt16 + (size_t)t0 * H : nullptr, (long long)d.TM * H,
+                                      w.flags_t[l], nT, B, H, c > 0 ? 1 : 0, s));
         MMQG_CUDA(cudaEventRecord(ev_fwd(l, c), s));
       }
     }
@@ -355,6 +363,10 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
                                        l == d.L - 1 ? w.m_txt + (size_t)t * H : nullptr, d.TM * H, B, H, st));
     }
   }
+  // bf16 attention memories: the pipelined persistent path writes the text memory in bf16 directly;
+  // every other path produced fp32 rows, converted here (rows beyond T_t / T_v are never read)
+  if (NC <= 1) MMQG_TRY(cvt_f32_bf16_2d(w.m_txt, H, w.m_txt16, H, (long long)B * d.TM, H, H, st));
+  MMQG_TRY(cvt_f32_bf16_2d(w.m_vid, Hv, w.m_vid16, Hv, (long long)B * d.AM, Hv, Hv, st));
   // decoder state slab 0 := encoder final state (train.py:169)
   const size_t n = (size_t)B * H;
   for (int l = 0; l < d.L; ++l) {
@@ -380,7 +392,7 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
   MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_dec, w.e_dec, Ep, R, d.E, Ep, d.V, st));
   MMQG_TRY(Tc(w.e_dec, Ep, false, w.wd_e, Ep, false, R, G, Ep, w.acts_dec[0], G).bias(w.bsum_dec[0]).run(st));
   MMQG_TRY(Tc(w.e_dec, Ep, false, w.wa_e, Ep, false, R, Sp, Ep, w.attn_all, Sp).bias(w.attn_b_cat).run(st));
-  AttnShape as = attn_shape16(d);
+  AttnShape as = attn_shape16(d, w);
   as.ldctx16 = C;
   for (int t = 0; t < d.T_q; ++t) {
     StepGemmScope step_scope;
@@ -433,7 +445,7 @@ struct Bwd16 {
 
   // decoder BPTT, reverse of decoder.py:74-107 for t = T_q-1 .. 0
   int dec_loop(cudaStream_t st) {
-    AttnShape as = attn_shape16(d);
+    AttnShape as = attn_shape16(d, w);
     as.ldds16 = Sp;
     MMQG_CUDA(cudaMemsetAsync(w.ds_all, 0, sizeof(float) * (size_t)R * Sp, st));
     MMQG_CUDA(cudaMemsetAsync(w.ds16, 0, sizeof(b16) * (size_t)R * Sp, st));

@@ -31,7 +31,14 @@ struct AttnShape {
   // bf16 mode: optional bf16 copies of the outputs that feed tensor-core GEMMs
   void* ctx16; int ldctx16;     // attn_fwd: contexts
   void* ds16; int ldds16;       // attn_bwd: d loss / d scores
+  // bf16 mode: bf16 copies of the text / video memories (same shapes); read instead of the fp32 ones
+  const void* m_txt16; const void* m_vid16;
 };
+bool attn_fast_ok(const AttnShape& s, const void* M_txt, const void* M_aud, const void* M_vid);
+int attn_fwd_fast(float* scores, int lds, const void* M_txt, const float* M_aud, const void* M_vid, bool mem_bf16, float* ctx,
+                  int ldctx, const AttnShape& s, cudaStream_t st);
+int attn_bwd_fast(const float* attn, float* ds_out, int lds, const float* dctx, int lddctx, const void* M_txt, const float* M_aud,
+                  const void* M_vid, bool mem_bf16, const AttnShape& s, cudaStream_t st);
 
 // bf16-mode elementwise kernels (pointwise_bf16.cu)
 int cvt_f32_bf16_2d(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
@@ -49,7 +56,7 @@ int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, f
 bool lstm_persist_ok(int B, int H);
 int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st);
 int sum_partials(const float* a, int na, const float* b, int nb, long long stride, float* y, int n, cudaStream_t st);
-int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, long long mem_ld,
+int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,
                          uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st);
 int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,

@@ -111,6 +111,7 @@ struct LstmFwdP {
   float* cs;           // ((T+1)*B, H) fp32; slab t+1 receives c_t (slab 0 is not read: c_{-1} = 0)
   bf16* hs;            // ((T+1)*B, H) bf16; slab 0 = h_{-1} (zeros), slab t+1 receives h_t
   float* mem;          // optional batch-major fp32 copy of h_t: mem[b*mem_ld + t*H + j]
+  bf16* mem16;         // optional batch-major bf16 copy (same indexing)
   long long mem_ld;
   uint32_t* flags;     // ((T+1) * n_mt) arrival counters, zeroed before launch
   int T, B, H, n_mt, n_slices, KB;
@@ -235,15 +236,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         acc[u] = ig; acc[16 + u] = fg; acc[32 + u] = gg; acc[48 + u] = og;
       }
       // h_t first: it is the only thing the other CTAs are waiting for
-      {
-        uint32_t hp[8];
+      uint32_t hp[8];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(hv[2 * v], hv[2 * v + 1]);
-          hp[v] = *reinterpret_cast<uint32_t*>(&t2);
-        }
-        row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.hs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid);
+      for (int v = 0; v < 8; ++v) {
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(hv[2 * v], hv[2 * v + 1]);
+        hp[v] = *reinterpret_cast<uint32_t*>(&t2);
       }
+      row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.hs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid);
       if (tre) atomicMax((unsigned long long*)&tre[t * 8 + 6], (unsigned long long)gtime());
       // publish: CTA barrier, then ONE thread fences (cumulativity covers the CTA's h stores)
       // and bumps the arrival counter
@@ -268,6 +267,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           row_to_coop(stg, lane, hv, tmp);
           coop_stg(p.mem + (size_t)m0w * p.mem_ld + (size_t)t * H + j0, (size_t)p.mem_ld, rows_valid, lane, tmp);
         }
+        if (p.mem16)
+          row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.mem16 + (size_t)m0w * p.mem_ld + (size_t)t * H + j0,
+                             (size_t)p.mem_ld, rows_valid);
       }
       (void)valid;
     }
@@ -545,10 +547,10 @@ static int launch_coop(Kern kern, dim3 grid, int threads, size_t smem, const CUt
 }
 
 // gates: (T*B,4H) fp32 pre-gates -> activated gates.  wp_fwd: pack_whh forward layout.  hs slab 0 must be zeros.
-int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, long long mem_ld,
+int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,
                          uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
-  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace};
+  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, reinterpret_cast<bf16*>(mem16), mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace};
   CUtensorMap tmW, tmH;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_fwd, 4 * (uint64_t)H, H, H, 64, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmH, hs, (uint64_t)(T + 1) * B, H, H, 128, 64));
