@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(512) attn_fwd_fast_kernel(float* __restrict__ 
   float* a = sm;                 // S softmax weights
   float* part = sm + S;          // 8 x Hmax partial context sums
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   float* sc = scores + (size_t)b * lds;
   for (int j = tid; j < S; j += 512) a[j] = sc[j];
   __syncthreads();
@@ -140,6 +142,8 @@ __global__ void __launch_bounds__(512) attn_bwd_fast_kernel(const float* attn, f
   float* da = sm + S;
   float* dc = sm + 2 * S;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const float* at = attn + (size_t)b * lds;
   float* ds = ds_out + (size_t)b * lds;
   for (int j = tid; j < S; j += 512) { a[j] = at[j]; da[j] = 0.f; }
@@ -209,11 +213,11 @@ int attn_fwd_fast(float* scores, int lds, const void* M_txt, const float* M_aud,
   MMQG_PROBE(KC_ATTN, 2.0 * s.B * ((double)s.T_t * s.H + (double)s.T_v * (s.H_a + s.H_v)),
              s.B * (esz * ((double)s.T_t * s.H + (double)s.T_v * s.H_v) + 4.0 * s.T_v * s.H_a + 8.0 * S + 4.0 * (s.H + s.H_a + s.H_v)));
   if (mem_bf16)
-    attn_fwd_fast_kernel<bf16><<<s.B, 512, smem, st>>>(scores, lds, reinterpret_cast<const bf16*>(M_txt), M_aud,
-                                                       reinterpret_cast<const bf16*>(M_vid), ctx, ldctx, s);
+    MMQG_CUDA(launch_k(attn_fwd_fast_kernel<bf16>, dim3(s.B), dim3(512), smem, st, scores, lds, reinterpret_cast<const bf16*>(M_txt),
+                       M_aud, reinterpret_cast<const bf16*>(M_vid), ctx, ldctx, s));
   else
-    attn_fwd_fast_kernel<float><<<s.B, 512, smem, st>>>(scores, lds, reinterpret_cast<const float*>(M_txt), M_aud,
-                                                        reinterpret_cast<const float*>(M_vid), ctx, ldctx, s);
+    MMQG_CUDA(launch_k(attn_fwd_fast_kernel<float>, dim3(s.B), dim3(512), smem, st, scores, lds, reinterpret_cast<const float*>(M_txt),
+                       M_aud, reinterpret_cast<const float*>(M_vid), ctx, ldctx, s));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -227,11 +231,11 @@ int attn_bwd_fast(const float* attn, float* ds_out, int lds, const float* dctx, 
   MMQG_PROBE(KC_ATTN, 2.0 * s.B * ((double)s.T_t * s.H + (double)s.T_v * (s.H_a + s.H_v)),
              s.B * (esz * ((double)s.T_t * s.H + (double)s.T_v * s.H_v) + 4.0 * s.T_v * s.H_a + 8.0 * S + 4.0 * C));
   if (mem_bf16)
-    attn_bwd_fast_kernel<bf16><<<s.B, 512, smem, st>>>(attn, ds_out, lds, dctx, lddctx, reinterpret_cast<const bf16*>(M_txt), M_aud,
-                                                       reinterpret_cast<const bf16*>(M_vid), s);
+    MMQG_CUDA(launch_k(attn_bwd_fast_kernel<bf16>, dim3(s.B), dim3(512), smem, st, attn, ds_out, lds, dctx, lddctx,
+                       reinterpret_cast<const bf16*>(M_txt), M_aud, reinterpret_cast<const bf16*>(M_vid), s));
   else
-    attn_bwd_fast_kernel<float><<<s.B, 512, smem, st>>>(attn, ds_out, lds, dctx, lddctx, reinterpret_cast<const float*>(M_txt),
-                                                        M_aud, reinterpret_cast<const float*>(M_vid), s);
+    MMQG_CUDA(launch_k(attn_bwd_fast_kernel<float>, dim3(s.B), dim3(512), smem, st, attn, ds_out, lds, dctx, lddctx,
+                       reinterpret_cast<const float*>(M_txt), M_aud, reinterpret_cast<const float*>(M_vid), s));
   MMQG_LAUNCH_CHECK();
   return 0;
 }

@@ -37,6 +37,37 @@ struct StepGemmScope {                    // RAII: GEMMs issued inside are per-t
   StepGemmScope() : prev(tl_gemm_class) { tl_gemm_class = KC_GEMM_STEP; }
   ~StepGemmScope() { tl_gemm_class = prev; }
 };
+// Programmatic dependent launch (PDL): inside the decoder's per-step loops every kernel is
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, calls pdl_launch_dependents()
+// at its start and pdl_wait() before touching global memory, so its launch latency, block
+// scheduling and prologue (barrier init, TMEM allocation, descriptor prefetch) overlap the tail
+// of its predecessor.  Both calls are no-ops for kernels launched the ordinary way.
+extern thread_local int tl_pdl;
+struct PdlScope {
+  int prev;
+  explicit PdlScope(bool on) : prev(tl_pdl) { tl_pdl = on ? 1 : 0; }
+  ~PdlScope() { tl_pdl = prev; }
+};
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  int n = 0;
+  if (tl_pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    n = 1;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // Place directly before a launch on stream `st`; MMQG_LAUNCH_CHECK() closes it.
 #define MMQG_PROBE(cls, flops, bytes) ::mmqg::probe_open((cls), st, (double)(flops), (double)(bytes))
 

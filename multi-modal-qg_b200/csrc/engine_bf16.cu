@@ -394,6 +394,7 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
   MMQG_TRY(Tc(w.e_dec, Ep, false, w.wa_e, Ep, false, R, Sp, Ep, w.attn_all, Sp).bias(w.attn_b_cat).run(st));
   AttnShape as = attn_shape16(d, w);
   as.ldctx16 = C;
+  PdlScope pdl_scope(pdl_enabled());      // the T_q x 5 dependent launches below overlap prologue and tail
   for (int t = 0; t < d.T_q; ++t) {
     StepGemmScope step_scope;
     const b16* htop_prev = w.hs_dec[d.L - 1] + (size_t)t * B * H;
@@ -449,6 +450,7 @@ struct Bwd16 {
     as.ldds16 = Sp;
     MMQG_CUDA(cudaMemsetAsync(w.ds_all, 0, sizeof(float) * (size_t)R * Sp, st));
     MMQG_CUDA(cudaMemsetAsync(w.ds16, 0, sizeof(b16) * (size_t)R * Sp, st));
+    PdlScope pdl_scope(pdl_enabled());
     for (int t = d.T_q - 1; t >= 0; --t) {
       StepGemmScope step_scope;
       const bool last = t == d.T_q - 1;

@@ -57,6 +57,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; from here on we read / write
+  // memory the predecessor may still be producing
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -170,7 +174,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& b, const CUtensorM
     attr = true;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM), p.split_k);
-  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, 320, SMEM, st>>>(a, b, a2, b2, p);
+  MMQG_CUDA(launch_k(gemm_tc_kernel<BN, A_MN, B_MN>, grid, dim3(320), SMEM, st, a, b, a2, b2, p));
   MMQG_LAUNCH_CHECK();
   return 0;
 }

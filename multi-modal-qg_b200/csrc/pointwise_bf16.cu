@@ -35,6 +35,8 @@ __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x))
 __global__ void lstm_pointwise_fwd_bf16_kernel(float* __restrict__ gates, int ldg, const float* __restrict__ c_prev,
                                                int ldcp, float* __restrict__ c_out, int ldc, bf16* __restrict__ h_out,
                                                int ldh, float* __restrict__ h2, int ldh2, int B, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, j = idx % H;
@@ -55,6 +57,8 @@ __global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, i
                                                const float* __restrict__ dh1, int ldh1, int n1, long long s1,
                                                const float* __restrict__ dh2, int ldh2, float* __restrict__ dc, int lddc,
                                                int dc_is_zero, bf16* __restrict__ dg, int lddg, int B, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, j = idx % H;
@@ -181,8 +185,8 @@ int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp
   MMQG_REQUIRE(gates && c_out && h_out && B > 0 && H > 0, "lstm_pointwise_fwd_bf16: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (c_prev ? 10 : 9) + 2.0 * n + (h2 ? 4.0 * n : 0));
-  lstm_pointwise_fwd_bf16_kernel<<<ceil_div(n, 256), 256, 0, st>>>(gates, ldg, c_prev, ldcp, c_out, ldc,
-                                                                    reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H);
+  MMQG_CUDA(launch_k(lstm_pointwise_fwd_bf16_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, gates, ldg, c_prev, ldcp, c_out, ldc,
+                     reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -194,9 +198,9 @@ int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int
   MMQG_REQUIRE(acts && c_new && dc && dg && B > 0 && H > 0, "lstm_pointwise_bwd_bf16: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (6 + (c_prev ? 1 : 0) + (dh0 ? n0 : 0) + (dh1 ? n1 : 0) + (dh2 ? 1 : 0)) + 8.0 * n);
-  lstm_pointwise_bwd_bf16_kernel<<<ceil_div(n, 256), 256, 0, st>>>(acts, ldg, c_prev, ldcp, c_new, ldc, dh0, ldh0, n0, s0,
-                                                                    dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero,
-                                                                    reinterpret_cast<bf16*>(dg), lddg, B, H);
+  MMQG_CUDA(launch_k(lstm_pointwise_bwd_bf16_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, acts, ldg, c_prev, ldcp, c_new, ldc,
+                     dh0, ldh0, n0, s0, dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, reinterpret_cast<bf16*>(dg), lddg,
+                     B, H));
   MMQG_LAUNCH_CHECK();
   return 0;
 }

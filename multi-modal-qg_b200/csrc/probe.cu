@@ -3,12 +3,23 @@
 // achieved FLOP/s or GB/s of the dominant kernel measured live inside a run of the same
 // step (B200_PROFILING.md "Roofline arithmetic").  Off by default: zero overhead beyond a
 // branch.  Not for use under CUDA-graph capture.
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 
 namespace mmqg {
 
 thread_local int tl_gemm_class = KC_GEMM_SEQ;
+thread_local int tl_pdl = 0;
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMQG_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 namespace {
 struct ProbeState {
