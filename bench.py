@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--mode", default=os.environ.get("MMQG_MODE", "bf16"), choices=["fp32", "bf16"],
                     help="bf16 = tcgen05 path (BASELINE configs[1] names bf16); fp32 = SIMT parity mode")
     ap.add_argument("--cpu-samples", type=int, default=32, help="samples the CPU baseline leg times")
+    ap.add_argument("--dropout", type=float, default=None,
+                    help="inter-layer LSTM dropout (config.py text_lstm_dropout = dec_lstm_dropout); default 0.2 in "
+                         "bf16 mode (the reference's train-mode value), 0 in the fp32 parity mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--probe", type=int, default=None, help="kernel class the roofline probe times (see mmqg.h)")
@@ -98,7 +101,7 @@ def flops_per_sample(d):
     return text + video + dec
 
 
-def cpu_reference_samples_per_s(d, n_samples, seed=0):
+def cpu_reference_samples_per_s(d, n_samples, seed=0, dropout_p=0.0):
     """The reference's per-sample train iteration (train.py:149-177: zero_grad, encoder,
     teacher-forced decoder, loss.backward()) on the host cores, via the oracle's per-sample
     port (stock torch.nn modules, same call granularity).  The reference itself cannot
@@ -109,7 +112,7 @@ def cpu_reference_samples_per_s(d, n_samples, seed=0):
     dd = Dims(**{**d.asdict(), "B": n_samples})
     params = make_params(dd, seed=seed)
     batch = make_batch(dd, seed=1234)
-    ref = RefModules(params, dd.L, dropout_p=0.0)
+    ref = RefModules(params, dd.L, dropout_p=dropout_p)
     ref.train()
     train_samples(ref, batch, 1)                       # warm-up (oneDNN primitive caches)
     t0 = time.perf_counter()
@@ -124,10 +127,10 @@ def run_reference(args, d, rank, world):
         return
     per_step = max(1, min(8, args.cpu_samples // 4))
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_samples_per_s(d, 1)
+        cpu_reference_samples_per_s(d, 1, dropout_p=args.dropout)
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
-        sps, dt = cpu_reference_samples_per_s(d, per_step)
+        sps, dt = cpu_reference_samples_per_s(d, per_step, dropout_p=args.dropout)
         t_total += dt
         n_total += per_step
     v = n_total / t_total
@@ -151,7 +154,7 @@ def workload_config(d, args, world):
                         f"B={d.B}/GPU T_t={d.T_t} T_v={d.T_v}x{d.F_v} T_a={d.T_v}x{d.H_a} T_q={d.T_q} V={d.V} "
                         f"E={d.E} H={d.H} L={d.L} TM={d.TM} AM={d.AM}",
             "global_batch": d.B * world, "per_gpu_batch": d.B, "parallelism": f"dp{world}",
-            "dropout_p": 0.0, "mode": args.mode, "cuda_graph": world == 1 and not args.no_graph,
+            "dropout_p": args.dropout, "mode": args.mode, "cuda_graph": world == 1 and not args.no_graph,
             "l2": "working set (2 GB activations + 111 MB weights per step) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -159,6 +162,8 @@ def main():
     args = parse()
     if args.probe is None:
         args.probe = 7 if args.mode == "bf16" else 1       # dominant kernel class of each mode
+    if args.dropout is None:
+        args.dropout = 0.2 if args.mode == "bf16" else 0.0
     from mmqg.dims import config as cfg
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,7 +187,7 @@ def main():
     from mmqg.dp import GradReducer
 
     params = make_params(d, seed=0)
-    eng = TrainEngine(d, params, device=dev, mode=args.mode)
+    eng = TrainEngine(d, params, device=dev, mode=args.mode, dropout_p=args.dropout)
     host = make_batch(d, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     dbatch = eng.to_device(host)
@@ -326,7 +331,7 @@ def main():
         "algorithmic_gflop_per_sample": f_train / 1e9,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, dt = cpu_reference_samples_per_s(d, args.cpu_samples)
+        v, dt = cpu_reference_samples_per_s(d, args.cpu_samples, dropout_p=args.dropout)
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{args.cpu_samples} samples of the same workload through the per-sample "
                                           f"reference loop (train.py:149-177 semantics, stock torch.nn modules), "

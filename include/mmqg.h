@@ -138,6 +138,11 @@ int mmqg_greedy_decode(const mmqg_dims* d, const mmqg_tensors* params, const mmq
                        void* workspace, size_t workspace_bytes, int64_t* tokens_out, int max_len,
                        int mode, void* stream);
 
+/* The multiplicative inter-layer dropout mask (0 or 1/(1-p)) the train path applies for a given
+ * seed: stream `sid` = 10+l for the output of text-encoder layer l, 20+l for decoder layer l;
+ * element index (t*B + b)*H + j.  For tests (the mask is counter-based, not ATen's Philox). */
+int mmqg_dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, void* stream);
+
 /* ---- building blocks (what the step-wise drop-in modules call) ---- */
 
 /* C(M,N) = alpha * op(A) op(B) [+ op(A2) op(B2)] + beta * Cin + bias(N).

@@ -252,12 +252,12 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   MMQG_REQUIRE(batch && batch->context && batch->target && batch->frames && batch->audio, "batch: null pointer");
   MMQG_REQUIRE(workspace && loss_out, "null workspace / loss_out");
   MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
-  MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: inter-layer dropout is not implemented yet (use 0)", dropout_p);
-  (void)seed;
+  MMQG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p=%g not in [0,1)", dropout_p);
   if (want_grads) MMQG_TRY(check_tensors(d, grads, "grads"));
   if (mode == MMQG_MODE_BF16)
     return train_forward_bf16(d, *params, *batch, workspace, workspace_bytes, loss_out, want_grads, grads, grad_scale,
-                              as_stream(stream));
+                              dropout_p, seed, as_stream(stream));
+  MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: the fp32 parity mode runs without dropout (use the bf16 mode)", dropout_p);
   Ws w = carve(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
@@ -326,11 +326,11 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   MMQG_REQUIRE(batch && batch->frames, "batch: null pointer");
   MMQG_REQUIRE(workspace, "null workspace");
   MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
-  MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: not implemented yet", dropout_p);
+  MMQG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p=%g not in [0,1)", dropout_p);
   MMQG_REQUIRE(phase >= 0 && phase <= 3, "phase %d not in 0..3", phase);
-  (void)seed;
   if (mode == MMQG_MODE_BF16)
-    return train_backward_bf16(d, *params, *batch, workspace, workspace_bytes, *grads, phase, as_stream(stream));
+    return train_backward_bf16(d, *params, *batch, workspace, workspace_bytes, *grads, phase, dropout_p, seed, as_stream(stream));
+  MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: the fp32 parity mode runs without dropout (use the bf16 mode)", dropout_p);
   Ws w = carve(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);

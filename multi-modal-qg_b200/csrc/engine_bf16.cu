@@ -40,6 +40,7 @@ struct Ws16 {
   // persistent recurrent kernels: gate-slice packed W_hh (forward) and W_hh^T (backward),
   // arrival counters, and the summed d loss / d h_final handed to the text encoder
   b16 *wtp_f[MMQG_MAX_LAYERS], *wtp_b[MMQG_MAX_LAYERS], *wvp_f, *wvp_b;
+  b16 *xdrop_text[MMQG_MAX_LAYERS], *hdrop_dec[MMQG_MAX_LAYERS];   // dropped layer outputs (inputs of the next layer)
   b16 *m_txt16, *m_vid16;     // bf16 attention memories (what the attention kernels read in this mode)
   uint32_t *flags, *flags_v, *flags_t[MMQG_MAX_LAYERS];
   float *dh_last, *dh_last_l[MMQG_MAX_LAYERS], *dx_emb;
@@ -120,6 +121,7 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
     w.dh_last_l[l] = c.take<float>(B * H);
   }
   w.dx_emb = c.take<float>(Rt * d.E);
+  for (int l = 0; l + 1 < d.L; ++l) { w.xdrop_text[l] = c.take<b16>(Rt * H); w.hdrop_dec[l] = c.take<b16>(R * H); }
   w.m_txt16 = c.take<b16>(B * d.TM * H);
   w.m_vid16 = c.take<b16>(B * d.AM * Hv);
   w.bytes = align_up(c.off, 256);
@@ -159,6 +161,11 @@ static AttnShape attn_shape16(const mmqg_dims& d, const Ws16& w) {
   a.m_vid16 = w.m_vid16;
   return a;
 }
+
+// inter-layer dropout of the current call (set at the entry points; 0 = off)
+static thread_local float g_drop_p = 0.f;
+static thread_local unsigned long long g_drop_seed = 0;
+static const int kSidText = 10, kSidDec = 20;
 
 // The encoders run on the persistent recurrent kernels when the shape allows it (lstm_persist.cu);
 // MMQG_PERSIST=0 forces the one-GEMM-plus-pointwise-launch-per-step path (for A/B comparison).
@@ -330,20 +337,27 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
         cudaStream_t s = l == 0 ? st : g_aux.s[l - 1];
         if (l > 0) {
           MMQG_CUDA(cudaStreamWaitEvent(s, ev_fwd(l - 1, c), 0));
-          MMQG_TRY(Tc(w.hs_text[l - 1] + (size_t)(t0 + 1) * B * H, H, false, w.wt_ih[l], H, false, nT * B, G, H,
-                      w.acts_text[l] + (size_t)t0 * B * G, G).bias(w.bsum_text[l]).run(s));
+          const b16* X = g_drop_p > 0.f ? w.xdrop_text[l - 1] + (size_t)t0 * B * H : w.hs_text[l - 1] + (size_t)(t0 + 1) * B * H;
+          MMQG_TRY(Tc(X, H, false, w.wt_ih[l], H, false, nT * B, G, H, w.acts_text[l] + (size_t)t0 * B * G, G)
+                       .bias(w.bsum_text[l]).run(s));
         }
         MMQG_TRY(lstm_seq_fwd_persist(w.acts_text[l] + (size_t)t0 * B * G, w.cs_text[l] + (size_t)t0 * B * H,
                                       w.hs_text[l] + (size_t)t0 * B * H, w.wtp_f[l],
                                       nullptr, l == d.L - 1 ? w.m_txt16 + (size_t)t0 * H : nullptr, (long long)d.TM * H,
                                       w.flags_t[l], nT, B, H, c > 0 ? 1 : 0, s));
+        if (g_drop_p > 0.f && l + 1 < d.L)
+          MMQG_TRY(dropout_bf16(w.hs_text[l] + (size_t)(t0 + 1) * B * H, w.xdrop_text[l] + (size_t)t0 * B * H, (long long)nT * B * H,
+                                g_drop_seed, kSidText + l, (unsigned long long)t0 * B * H, g_drop_p, s));
         MMQG_CUDA(cudaEventRecord(ev_fwd(l, c), s));
       }
     }
     for (int l = 1; l < d.L; ++l) MMQG_CUDA(cudaStreamWaitEvent(st, ev_fwd(l, NC - 1), 0));   // join
   } else
   for (int l = 0; l < d.L; ++l) {
-    const b16* X = l == 0 ? w.x0 : w.hs_text[l - 1] + (size_t)B * H;
+    if (l > 0 && g_drop_p > 0.f)
+      MMQG_TRY(dropout_bf16(w.hs_text[l - 1] + (size_t)B * H, w.xdrop_text[l - 1], (long long)d.T_t * B * H, g_drop_seed,
+                            kSidText + l - 1, 0, g_drop_p, st));
+    const b16* X = l == 0 ? w.x0 : (g_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);
     const int Ip = l == 0 ? w.Ep : H;
     MMQG_TRY(Tc(X, Ip, false, w.wt_ih[l], Ip, false, d.T_t * B, G, Ip, w.acts_text[l], G).bias(w.bsum_text[l]).run(st));
     if (persist_text(d)) {
@@ -378,8 +392,10 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
 
 int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                        size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
-                       cudaStream_t st) {
+                       float dropout_p, unsigned long long seed, cudaStream_t st) {
   MMQG_TRY(check_dims_bf16(d));
+  g_drop_p = dropout_p;
+  g_drop_seed = seed;
   Ws16 w = carve16(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, R = d.T_q * B, Sp = w.Sp, Ep = w.Ep;
@@ -409,10 +425,15 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
       if (l == 0)
         MMQG_TRY(Tc(ctx, C, false, w.wd_c, C, false, B, G, C, acts, G).second(hprev, H, w.wd_hh[0], H, H).accumulate(true).run(st));
       else
-        MMQG_TRY(Tc(w.hs_dec[l - 1] + (size_t)(t + 1) * B * H, H, false, w.wd_ih[l], H, false, B, G, H, acts, G)
-                     .second(hprev, H, w.wd_hh[l], H, H).bias(w.bsum_dec[l]).run(st));
+        MMQG_TRY(Tc(g_drop_p > 0.f ? w.hdrop_dec[l - 1] + (size_t)t * B * H : w.hs_dec[l - 1] + (size_t)(t + 1) * B * H, H, false,
+                    w.wd_ih[l], H, false, B, G, H, acts, G).second(hprev, H, w.wd_hh[l], H, H).bias(w.bsum_dec[l]).run(st));
+      DropSpec dr;
+      if (g_drop_p > 0.f && l + 1 < d.L) {
+        dr.out = w.hdrop_dec[l] + (size_t)t * B * H; dr.ld = H; dr.seed = g_drop_seed; dr.sid = kSidDec + l;
+        dr.base = (unsigned long long)t * B * H; dr.p = g_drop_p;
+      }
       MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
-                                       w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st));
+                                       w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st, dr));
     }
   }
   // loss head in row chunks: logits (fp32, chunk only) -> NLL (+ bf16 dlogits -> dH, dW_out, db_out)
@@ -460,15 +481,19 @@ struct Bwd16 {
         const float* dh0 = last ? nullptr : w.dh_rec[l];
         const float* dh1 = nullptr; int n1 = 0;
         const float* dh2 = nullptr;
+        DropSpec dr;
         if (l == L - 1) {
           dh2 = w.dhtop + (size_t)t * B * H;
           if (!last) { dh1 = w.dq_h; n1 = kSplitB; }
         } else {
           dh1 = w.dx_above; n1 = kSplitB;
+          if (g_drop_p > 0.f) {   // dx_above is d/d(dropped h_l): back through the mask of layer l's output
+            dr.seed = g_drop_seed; dr.sid = kSidDec + l; dr.base = (unsigned long long)t * B * H; dr.p = g_drop_p;
+          }
         }
         MMQG_TRY(lstm_pointwise_bwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H,
                                          H, dh0, H, kSplitB, ps, dh1, H, n1, ps, dh2, H, w.dc[l], H, last ? 1 : 0, dg, G, B,
-                                         H, st));
+                                         H, st, dr));
         MMQG_TRY(Tc(dg, G, false, w.wd_hh[l], H, true, B, H, G, w.dh_rec[l], H).split(kSplitB, ps).run(st));
         if (l > 0)
           MMQG_TRY(Tc(dg, G, false, w.wd_ih[l], H, true, B, H, G, w.dx_above, H).split(kSplitB, ps).run(st));
@@ -491,7 +516,8 @@ struct Bwd16 {
       const b16* dG = w.dg_dec[l];
       MMQG_TRY(Tc(dG, G, true, w.hs_dec[l], H, true, G, H, R, Gd.dec_w_hh[l], H).run(st));
       if (l > 0) {
-        MMQG_TRY(Tc(dG, G, true, w.hs_dec[l - 1] + (size_t)B * H, H, true, G, H, R, Gd.dec_w_ih[l], H).run(st));
+        MMQG_TRY(Tc(dG, G, true, g_drop_p > 0.f ? w.hdrop_dec[l - 1] : w.hs_dec[l - 1] + (size_t)B * H, H, true, G, H, R,
+                    Gd.dec_w_ih[l], H).run(st));
       } else {
         MMQG_TRY(Tc(dG, G, true, w.e_dec, Ep, true, G, E, R, Gd.dec_w_ih[0], X0).run(st));
         MMQG_TRY(Tc(dG, G, true, w.ctx16, C, true, G, C, R, Gd.dec_w_ih[0] + E, X0).run(st));
@@ -544,6 +570,8 @@ struct Bwd16 {
   // BPTT of text layer l (encoder.py:95-100) and the input gradient the layer below needs
   int text_bptt(int l, cudaStream_t st) {
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
+    if (g_drop_p > 0.f && l < L - 1)   // dx_text holds d/d(dropped h_l): back through the mask
+      MMQG_TRY(dropout_scale_f32(w.dx_text, 1, 0, (long long)d.T_t * B * H, g_drop_seed, kSidText + l, 0, g_drop_p, st));
     if (persist_text(d)) {
       // d loss / d h_final = the decoder's gradient w.r.t. its initial state (train.py:169) plus,
       // for the top layer, the step-0 attention query; d loss / d c_final sits in dc[l].
@@ -573,7 +601,7 @@ struct Bwd16 {
   int text_hoisted(int l, cudaStream_t st) {
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
     const b16* dG = w.dg_text[l];
-    const b16* X = l == 0 ? w.x0 : w.hs_text[l - 1] + (size_t)B * H;
+    const b16* X = l == 0 ? w.x0 : (g_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);
     MMQG_TRY(Tc(dG, G, true, X, Ip, true, G, I, d.T_t * B, Gd.text_w_ih[l], I).run(st));
     if (d.T_t > 1)
       MMQG_TRY(Tc(dG + (size_t)B * G, G, true, w.hs_text[l] + (size_t)B * H, H, true, G, H, (d.T_t - 1) * B, Gd.text_w_hh[l], H).run(st));
@@ -596,7 +624,12 @@ struct Bwd16 {
       for (int l = L - 1; l >= 0; --l) {
         cudaStream_t s = S(l);
         const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
-        if (l < L - 1) MMQG_CUDA(cudaStreamWaitEvent(s, ev_bwd(l + 1, c), 0));
+        if (l < L - 1) {
+          MMQG_CUDA(cudaStreamWaitEvent(s, ev_bwd(l + 1, c), 0));
+          if (g_drop_p > 0.f)
+            MMQG_TRY(dropout_scale_f32(w.dx_text + (size_t)t0 * B * H, 1, 0, (long long)nT * B * H, g_drop_seed, kSidText + l,
+                                       (unsigned long long)t0 * B * H, g_drop_p, s));
+        }
         if (tail)   // d loss / d h_final of this layer (decoder initial state, + step-0 attention query on top)
           MMQG_TRY(sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, w.dh_last_l[l],
                                 B * H, s));
@@ -624,8 +657,11 @@ struct Bwd16 {
 };
 
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
-                        size_t workspace_bytes, mmqg_tensors& Gd, int phase, cudaStream_t st) {
+                        size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
+                        cudaStream_t st) {
   MMQG_TRY(check_dims_bf16(d));
+  g_drop_p = dropout_p;
+  g_drop_seed = seed;
   Ws16 w = carve16(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   Bwd16 b(d, P, bt, w, Gd);

@@ -45,13 +45,27 @@ int cvt_f32_bf16_2d(const float* src, long long ld_src, void* dst, long long ld_
                     int cols_dst, cudaStream_t st);
 int embedding_gather_bf16(const float* emb, const int64_t* idx, void* out, int ldo, int N, int E, int E_pad, int V,
                           cudaStream_t st);
+// Inter-layer dropout fused into the cell kernels: forward writes a dropped bf16 copy of h to
+// `out` (row pitch ld); backward multiplies the dh1 term by the same mask (p > 0).  Element
+// (b, j) of the call uses counter base + b*H + j of stream sid.
+struct DropSpec {
+  void* out = nullptr;
+  int ld = 0;
+  unsigned long long seed = 0, base = 0;
+  int sid = 0;
+  float p = 0.f;
+};
 int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, void* h_out,
-                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st);
+                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, DropSpec dr = DropSpec());
 int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                             const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1,
                             long long s1, const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, void* dg,
-                            int lddg, int B, int H, cudaStream_t st);
+                            int lddg, int B, int H, cudaStream_t st, DropSpec dr = DropSpec());
 int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
+int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, int sid, unsigned long long base, float p, cudaStream_t st);
+int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, int sid, unsigned long long base,
+                      float p, cudaStream_t st);
+int dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, cudaStream_t st);
 // persistent recurrent-cell kernels (lstm_persist.cu)
 bool lstm_persist_ok(int B, int H);
 int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st);
@@ -73,9 +87,10 @@ size_t train_workspace_bytes_bf16(const mmqg_dims& d, int T_q);
 int check_dims_bf16(const mmqg_dims& d);
 int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                        size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
-                       cudaStream_t st);
+                       float dropout_p, unsigned long long seed, cudaStream_t st);
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
-                        size_t workspace_bytes, mmqg_tensors& Gd, int phase, cudaStream_t st);
+                        size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
+                        cudaStream_t st);
 int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* nll, int R, int V, float scale,
                   void* dlogits, int lddl, cudaStream_t st);
 int attn_fwd(float* scores, int lds, const float* M_txt, const float* M_aud, const float* M_vid, float* ctx,

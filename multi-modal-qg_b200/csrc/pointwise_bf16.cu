@@ -30,11 +30,26 @@ __global__ void embedding_gather_bf16_kernel(const float* __restrict__ emb, cons
   for (int e = threadIdx.x; e < E_pad; e += blockDim.x) dst[e] = __float2bfloat16_rn(e < E ? src[e] : 0.f);
 }
 
+// ---- inter-layer dropout (torch.nn.LSTM(dropout=p): outputs of every layer but the last) ----
+// Counter-based mask: element `idx` of logical stream `sid` is kept iff u(seed, sid, idx) >= p, so
+// the forward (y = x * m / (1-p)) and the backward (dx *= m / (1-p)) regenerate the same mask from
+// the seed and chunked application equals whole-tensor application.  Not bit-compatible with
+// ATen's Philox stream (SURVEY section 7 "Hard parts"): validated against the oracle run with the
+// exported mask (mmqg_dropout_mask) and statistically.
+__device__ __forceinline__ float drop_scale(unsigned long long seed, int sid, unsigned long long idx, float p, float inv_keep) {
+  unsigned long long z = seed + (unsigned long long)sid * 0x9E3779B97F4A7C15ull + idx * 0xD1342543DE82EF95ull;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.f;
+}
+
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void lstm_pointwise_fwd_bf16_kernel(float* __restrict__ gates, int ldg, const float* __restrict__ c_prev,
                                                int ldcp, float* __restrict__ c_out, int ldc, bf16* __restrict__ h_out,
-                                               int ldh, float* __restrict__ h2, int ldh2, int B, int H) {
+                                               int ldh, float* __restrict__ h2, int ldh2, int B, int H, DropSpec dr) {
   pdl_launch_dependents();
   pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,6 +64,9 @@ __global__ void lstm_pointwise_fwd_bf16_kernel(float* __restrict__ gates, int ld
   c_out[(size_t)b * ldc + j] = c;
   h_out[(size_t)b * ldh + j] = __float2bfloat16_rn(h);
   if (h2) h2[(size_t)b * ldh2 + j] = h;
+  if (dr.out)   // dropped copy: the input of the next layer
+    reinterpret_cast<bf16*>(dr.out)[(size_t)b * dr.ld + j] =
+        __float2bfloat16_rn(h * drop_scale(dr.seed, dr.sid, dr.base + (unsigned long long)idx, dr.p, 1.0f / (1.0f - dr.p)));
 }
 
 __global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, int ldg, const float* __restrict__ c_prev,
@@ -56,7 +74,7 @@ __global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, i
                                                const float* __restrict__ dh0, int ldh0, int n0, long long s0,
                                                const float* __restrict__ dh1, int ldh1, int n1, long long s1,
                                                const float* __restrict__ dh2, int ldh2, float* __restrict__ dc, int lddc,
-                                               int dc_is_zero, bf16* __restrict__ dg, int lddg, int B, int H) {
+                                               int dc_is_zero, bf16* __restrict__ dg, int lddg, int B, int H, DropSpec dr) {
   pdl_launch_dependents();
   pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,8 +83,12 @@ __global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, i
   float dh = 0.f;
   if (dh0)
     for (int s = 0; s < n0; ++s) dh += dh0[(size_t)s * s0 + (size_t)b * ldh0 + j];
-  if (dh1)
-    for (int s = 0; s < n1; ++s) dh += dh1[(size_t)s * s1 + (size_t)b * ldh1 + j];
+  if (dh1) {   // gradient from the layer above, through this layer's dropout mask when dr.p > 0
+    float d1 = 0.f;
+    for (int s = 0; s < n1; ++s) d1 += dh1[(size_t)s * s1 + (size_t)b * ldh1 + j];
+    if (dr.p > 0.f) d1 *= drop_scale(dr.seed, dr.sid, dr.base + (unsigned long long)idx, dr.p, 1.0f / (1.0f - dr.p));
+    dh += d1;
+  }
   if (dh2) dh += dh2[(size_t)b * ldh2 + j];
   const float* a = acts + (size_t)b * ldg;
   float i = a[j], f = a[H + j], gg = a[2 * H + j], o = a[3 * H + j];
@@ -160,6 +182,47 @@ __global__ void __launch_bounds__(256) nll_rows_bf16_kernel(const float* __restr
   }
 }
 
+__global__ void dropout_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n, unsigned long long seed, int sid,
+                                    unsigned long long base, float p, float inv_keep) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * drop_scale(seed, sid, base + i, p, inv_keep));
+}
+
+// x[k*stride + i] *= mask(i) for k < n_part (gradient w.r.t. a dropped tensor, possibly split-K partials)
+__global__ void dropout_scale_f32_kernel(float* __restrict__ x, int n_part, long long stride, long long n, unsigned long long seed,
+                                         int sid, unsigned long long base, float p, float inv_keep) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float m = drop_scale(seed, sid, base + i, p, inv_keep);
+  for (int k = 0; k < n_part; ++k) x[(size_t)k * stride + i] *= m;
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, unsigned long long seed, int sid, float p, float inv_keep) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = drop_scale(seed, sid, i, p, inv_keep);
+}
+
+int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, int sid, unsigned long long base, float p, cudaStream_t st) {
+  MMQG_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout_bf16: bad args");
+  dropout_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), n, seed,
+                                                                  sid, base, p, 1.0f / (1.0f - p));
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, int sid, unsigned long long base,
+                      float p, cudaStream_t st) {
+  MMQG_REQUIRE(x && n > 0 && n_part > 0 && p >= 0.f && p < 1.f, "dropout_scale_f32: bad args");
+  dropout_scale_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n_part, stride, n, seed, sid, base, p, 1.0f / (1.0f - p));
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+int dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, cudaStream_t st) {
+  MMQG_REQUIRE(out && n > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad args");
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, seed, sid, p, 1.0f / (1.0f - p));
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 int cvt_f32_bf16_2d(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
                     int cols_dst, cudaStream_t st) {
@@ -181,12 +244,12 @@ int embedding_gather_bf16(const float* emb, const int64_t* idx, void* out, int l
 }
 
 int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, void* h_out,
-                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st) {
+                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, DropSpec dr) {
   MMQG_REQUIRE(gates && c_out && h_out && B > 0 && H > 0, "lstm_pointwise_fwd_bf16: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (c_prev ? 10 : 9) + 2.0 * n + (h2 ? 4.0 * n : 0));
   MMQG_CUDA(launch_k(lstm_pointwise_fwd_bf16_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, gates, ldg, c_prev, ldcp, c_out, ldc,
-                     reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H));
+                     reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H, dr));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -194,13 +257,13 @@ int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp
 int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                             const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1,
                             long long s1, const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, void* dg,
-                            int lddg, int B, int H, cudaStream_t st) {
+                            int lddg, int B, int H, cudaStream_t st, DropSpec dr) {
   MMQG_REQUIRE(acts && c_new && dc && dg && B > 0 && H > 0, "lstm_pointwise_bwd_bf16: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (6 + (c_prev ? 1 : 0) + (dh0 ? n0 : 0) + (dh1 ? n1 : 0) + (dh2 ? 1 : 0)) + 8.0 * n);
   MMQG_CUDA(launch_k(lstm_pointwise_bwd_bf16_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, acts, ldg, c_prev, ldcp, c_new, ldc,
                      dh0, ldh0, n0, s0, dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, reinterpret_cast<bf16*>(dg), lddg,
-                     B, H));
+                     B, H, dr));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -232,3 +295,9 @@ int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* n
 }
 
 }  // namespace mmqg
+
+// Exported for tests: the multiplicative mask (0 or 1/(1-p)) of dropout stream `sid` (text layer l:
+// 10+l, decoder layer l: 20+l), element index (t*B + b)*H + j.
+extern "C" int mmqg_dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, void* stream) {
+  return mmqg::dropout_mask(out, n, seed, sid, p, mmqg::as_stream(stream));
+}

@@ -60,6 +60,7 @@ class TrainEngine:
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._greedy_ws = None
         self.seed = 0
+        self.auto_seed = True
 
     # -- batches -------------------------------------------------------------------------
     def to_device(self, batch: dict, non_blocking=False) -> dict:
@@ -102,12 +103,27 @@ class TrainEngine:
         loss = self.forward(batch, True, grad_scale)
         if on_phase is None:
             self.backward(batch, 0)          # whole backward, hoisted products overlapped internally
-            return loss
-        on_phase(0)
-        for ph in (1, 2, 3):
-            self.backward(batch, ph)
-            on_phase(ph)
+        else:
+            on_phase(0)
+            for ph in (1, 2, 3):
+                self.backward(batch, ph)
+                on_phase(ph)
+        if self.dropout_p > 0 and self.auto_seed:
+            self.seed += 1                   # fresh masks next step (a captured CUDA graph replays one seed)
         return loss
+
+    def dropout_masks(self, seed=None):
+        """The multiplicative inter-layer dropout masks (0 or 1/(1-p)) a step with `seed` applies:
+        {"text": (L-1,T_t,B,H), "dec": (L-1,T_q,B,H)} -- what tests feed the oracle."""
+        d, seed = self.d, self.seed if seed is None else seed
+        out = {}
+        for key, sid0, T in (("text", 10, d.T_t), ("dec", 20, d.T_q)):
+            m = torch.empty(max(d.L - 1, 0), T, d.B, d.H, dtype=torch.float32, device=self.device)
+            for l in range(d.L - 1):
+                _cabi.check(self.lib.mmqg_dropout_mask(m[l].data_ptr(), m[l].numel(), seed, sid0 + l, self.dropout_p,
+                                                      _stream_ptr()))
+            out[key] = m
+        return out
 
     # -- greedy decode ---------------------------------------------------------------------
     def greedy(self, batch, max_len):

@@ -107,23 +107,28 @@ def decoder_step(p, L, word, h, c, M_txt, M_aud, M_vid, drop_masks=None):
     return logits, h, c, a_txt, a_aud, a_vid
 
 
-def encode(p, batch, L, TM, AM):
+def encode(p, batch, L, TM, AM, text_drop=None):
+    """text_drop: multiplicative inter-layer dropout masks (L-1, T_t, B, H) or None."""
     M_vid = video_encode(p, batch["frames"], AM)
     M_aud = audio_memory(batch["audio"], AM)
-    M_txt, h, c = text_encode(p, batch["context"], L, TM)
+    masks = None if text_drop is None else [[text_drop[l, t] for l in range(L - 1)] for t in range(text_drop.shape[1])]
+    M_txt, h, c = text_encode(p, batch["context"], L, TM, masks)
     return M_txt, M_aud, M_vid, h, c
 
 
-def teacher_forced_loss(p, batch, L, TM, AM, return_steps=False):
-    """loss = sum_t mean_b NLL(b,t)  (train.py:171-175 with CrossEntropyLoss() mean)."""
-    M_txt, M_aud, M_vid, h, c = encode(p, batch, L, TM, AM)
+def teacher_forced_loss(p, batch, L, TM, AM, return_steps=False, drop=None):
+    """loss = sum_t mean_b NLL(b,t)  (train.py:171-175 with CrossEntropyLoss() mean).
+    drop: None (eval / p=0) or {"text": (L-1,T_t,B,H), "dec": (L-1,T_q,B,H)} multiplicative
+    masks (0 or 1/(1-p)) of torch.nn.LSTM's inter-layer dropout (encoder.py:62, decoder.py:57)."""
+    M_txt, M_aud, M_vid, h, c = encode(p, batch, L, TM, AM, None if drop is None else drop["text"])
     tgt = batch["target"]
     B, T_q = tgt.shape
     word = torch.full((B,), START, dtype=torch.int64)
     loss = 0
     steps = []
     for t in range(T_q):
-        logits, h, c, a_txt, a_aud, a_vid = decoder_step(p, L, word, h, c, M_txt, M_aud, M_vid)
+        dm = None if drop is None else [drop["dec"][l, t] for l in range(L - 1)]
+        logits, h, c, a_txt, a_aud, a_vid = decoder_step(p, L, word, h, c, M_txt, M_aud, M_vid, dm)
         lse = torch.logsumexp(logits, 1)
         nll = lse - logits.gather(1, tgt[:, t:t + 1]).squeeze(1)
         loss = loss + nll.mean()
@@ -136,11 +141,13 @@ def teacher_forced_loss(p, batch, L, TM, AM, return_steps=False):
     return loss
 
 
-def loss_and_grads(params, batch, L, TM, AM, dtype=torch.float64):
+def loss_and_grads(params, batch, L, TM, AM, dtype=torch.float64, drop=None):
     """Loss and d loss / d every parameter, computed in `dtype` on the CPU."""
     p = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in params.items()}
     b = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in batch.items()}
-    loss = teacher_forced_loss(p, b, L, TM, AM)
+    if drop is not None:
+        drop = {k: v.to(dtype) for k, v in drop.items()}
+    loss = teacher_forced_loss(p, b, L, TM, AM, drop=drop)
     names = list(p)
     grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
     g = {n: (torch.zeros_like(p[n]) if gr is None else gr).detach() for n, gr in zip(names, grads)}

@@ -46,6 +46,50 @@ def test_bf16_step_matches_rounded_oracle(eng_mod, cfg):
     assert worst[1] < GRAD_TOL, errs
 
 
+@pytest.mark.parametrize("chunks", ["1", "3"])
+@pytest.mark.parametrize("cfg", [
+    dict(B=8, T_t=17, T_v=5, T_q=7, V=1003, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101),
+    dict(B=130, T_t=5, T_v=2, T_q=3, V=520, E=52, H=64, L=2, H_a=24, H_v=128, F_v=40, TM=11, AM=6),
+])
+def test_bf16_dropout_step_matches_oracle_with_same_masks(eng_mod, cfg, chunks, monkeypatch):
+    """Inter-layer LSTM dropout p=0.2 (encoder.py:62, decoder.py:57): the engine's counter-based
+    masks are exported and fed to the oracle, so loss and gradients must agree to the bf16 bar."""
+    from oracle import mmqg_oracle as O
+    monkeypatch.setenv("MMQG_CHUNKS", chunks)
+    d = Dims(**cfg)
+    params = make_params(d, seed=51)
+    batch = make_batch(d, seed=52)
+    eng = eng_mod.TrainEngine(d, params, mode="bf16", dropout_p=0.2)
+    eng.seed, eng.auto_seed = 1234, False
+    masks = {k: v.cpu() for k, v in eng.dropout_masks().items()}
+    keep = torch.cat([m.flatten() for m in masks.values()])
+    assert set(keep.unique().tolist()) <= {0.0, 1.25}
+    assert abs(float((keep > 0).float().mean()) - 0.8) < 0.02
+    loss_ref, grads_ref = O.loss_and_grads(round_params_bf16(params), batch, d.L, d.TM, d.AM, torch.float64, drop=masks)
+    loss_nodrop, _ = O.loss_and_grads(round_params_bf16(params), batch, d.L, d.TM, d.AM, torch.float64)
+    loss = float(eng.step(eng.to_device(batch)))
+    torch.cuda.synchronize()
+    assert abs(loss - float(loss_ref)) < LOSS_TOL * abs(float(loss_ref)), (loss, float(loss_ref), float(loss_nodrop))
+    errs = {k: rel(eng.grads[k], g) for k, g in grads_ref.items()}
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print("bf16+dropout worst grad rel err", worst, "loss", loss, float(loss_ref), "no-drop", float(loss_nodrop))
+    assert worst[1] < GRAD_TOL, errs
+    # a different seed draws different masks -> a different loss; the same seed repeats
+    again = float(eng.step(eng.to_device(batch)))
+    assert abs(again - loss) < 1e-4 * abs(loss)
+    eng.seed = 99
+    other = float(eng.step(eng.to_device(batch)))
+    assert other != loss
+
+
+def test_fp32_mode_rejects_dropout(eng_mod):
+    from mmqg import _cabi
+    d = Dims(B=2, T_t=3, T_v=2, T_q=2, V=11, E=10, H=12, L=2, H_a=6, H_v=12, F_v=10, TM=4, AM=3)
+    eng = eng_mod.TrainEngine(d, make_params(d), mode="fp32", dropout_p=0.2)
+    with pytest.raises(_cabi.MmqgError):
+        eng.step(eng.to_device(make_batch(d)))
+
+
 def test_bf16_close_to_fp32_engine(eng_mod):
     d = Dims(B=16, T_t=12, T_v=4, T_q=5, V=2000, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101)
     params = make_params(d, seed=43)

@@ -84,3 +84,37 @@ def test_oracle_fp32_noise_floor():
     assert abs(float(l32) - float(fx["loss"])) < 1e-5 * abs(float(fx["loss"]))
     for k, g in fx["grads"].items():
         assert O.rel_err(g32[k], g) < 1e-4, k
+
+
+def test_oracle_dropout_masks_semantics():
+    """drop=ones is the eval path; the masks scale the input of layers 1.. (torch.nn.LSTM
+    inter-layer dropout), so the result equals nn.LSTM fed the same masked activations."""
+    import torch
+    from mmqg.dims import Dims
+    from mmqg.synth import make_batch, make_params
+    from oracle import mmqg_oracle as O
+    d = Dims(B=3, T_t=4, T_v=2, T_q=3, V=23, E=6, H=8, L=3, H_a=4, H_v=8, F_v=5, TM=6, AM=3)
+    params, batch = make_params(d, seed=3), make_batch(d, seed=4)
+    ones = {"text": torch.ones(d.L - 1, d.T_t, d.B, d.H), "dec": torch.ones(d.L - 1, d.T_q, d.B, d.H)}
+    l0, g0 = O.loss_and_grads(params, batch, d.L, d.TM, d.AM)
+    l1, g1 = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, drop=ones)
+    assert float(l0) == float(l1)
+    assert all(torch.equal(g0[k], g1[k]) for k in g0)
+    gen = torch.Generator().manual_seed(0)
+    drop = {k: (torch.rand(v.shape, generator=gen) >= 0.2).float() / 0.8 for k, v in ones.items()}
+    l2, g2 = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, drop=drop)
+    assert float(l2) != float(l0)
+    # cross-check the text stack against a manual layer-by-layer nn.LSTM evaluation with the same masks
+    p64 = {k: v.double() for k, v in params.items()}
+    x = p64["emb.weight"][batch["context"]].transpose(0, 1)          # (T,B,E)
+    for l in range(d.L):
+        lstm = torch.nn.LSTM(x.shape[2], d.H, 1).double()
+        with torch.no_grad():
+            lstm.weight_ih_l0.copy_(p64[f"text.lstm.weight_ih_l{l}"]); lstm.weight_hh_l0.copy_(p64[f"text.lstm.weight_hh_l{l}"])
+            lstm.bias_ih_l0.copy_(p64[f"text.lstm.bias_ih_l{l}"]); lstm.bias_hh_l0.copy_(p64[f"text.lstm.bias_hh_l{l}"])
+            x, _ = lstm(x)
+            if l < d.L - 1:
+                x = x * drop["text"][l].double()
+    masks = [[drop["text"][l, t].double() for l in range(d.L - 1)] for t in range(d.T_t)]
+    mem, _, _ = O.text_encode(p64, batch["context"], d.L, d.TM, masks)
+    assert torch.allclose(mem[:, :d.T_t].transpose(0, 1), x, atol=1e-12)
