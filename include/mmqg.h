@@ -14,7 +14,9 @@
  *   - scratch memory comes from a caller-provided workspace whose size is returned by
  *     the matching *_workspace_bytes() function.
  *   - `stream` is a cudaStream_t passed as void*.  All work is enqueued asynchronously
- *     on it; there are no hidden synchronisations and no internal streams.
+ *     and is ordered on it: there are no hidden synchronisations.  The bf16 train path forks
+ *     library-owned auxiliary streams from `stream` and joins them back with events before
+ *     the call returns, so callers (and CUDA-graph capture) see single-stream semantics.
  *   - return value: 0 = enqueued OK, otherwise an mmqg_status; mmqg_last_error()
  *     gives a thread-local message.
  *   - parameters are fp32 in PyTorch layout: LSTM weights (4H, in) row-major with gate
