@@ -154,7 +154,7 @@ def workload_config(d, args, world):
                         f"B={d.B}/GPU T_t={d.T_t} T_v={d.T_v}x{d.F_v} T_a={d.T_v}x{d.H_a} T_q={d.T_q} V={d.V} "
                         f"E={d.E} H={d.H} L={d.L} TM={d.TM} AM={d.AM}",
             "global_batch": d.B * world, "per_gpu_batch": d.B, "parallelism": f"dp{world}",
-            "dropout_p": args.dropout, "mode": args.mode, "cuda_graph": world == 1 and not args.no_graph,
+            "dropout_p": args.dropout, "mode": args.mode, "cuda_graph": not args.no_graph,
             "l2": "working set (2 GB activations + 111 MB weights per step) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -196,16 +196,16 @@ def main():
 
     def eager_step(b):
         if reducer:
-            loss = eng.step(b, grad_scale=gscale, on_phase=reducer.on_phase)
+            loss = eng.step_dp(b, reducer, gscale)     # all-reduce per gradient group behind its ready event
             reducer.finish()
         else:
             loss = eng.step(b)
         return loss
 
-    # One step is ~1.3-1.7k kernel launches on one stream; replaying them as a CUDA graph takes the
-    # host launch path out of the loop (single-GPU only: the NCCL overlap path stays eager).
-    use_graph = world == 1 and not args.no_graph
-    graph = None
+    # One step is ~550 kernel launches; replaying them as a CUDA graph takes the host launch path out
+    # of the loop.  With N > 1 the NCCL all-reduces are captured in the same graph.
+    use_graph = not args.no_graph
+    graph_holder = []
     n_before = launch_count()
     eager_step(dbatch)
     torch.cuda.synchronize()
@@ -216,14 +216,14 @@ def main():
         with torch.cuda.stream(side):
             eager_step(dbatch)
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            eng.step(dbatch)
+        graph_holder.append(torch.cuda.CUDAGraph())
+        with torch.cuda.graph(graph_holder[0]):
+            eager_step(dbatch)
 
     def one_step(b):
         """b must be dbatch (the graph is bound to its buffers)."""
-        if graph is not None:
-            graph.replay()
+        if graph_holder:
+            graph_holder[0].replay()
             return eng.loss
         return eager_step(b)
 
@@ -308,10 +308,7 @@ def main():
                                                         if args.probe in (1, 2) and args.mode == "fp32" else "")})
 
     if rank != 0:
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            dist.destroy_process_group()
+        teardown(world, graph_holder)
         return
     sps = d.B * world * args.steps / (ms * 1e-3)
     sps_e2e = d.B * world * args.steps / (ms_e2e * 1e-3)
@@ -337,10 +334,27 @@ def main():
                                           f"reference loop (train.py:149-177 semantics, stock torch.nn modules), "
                                           f"{dt:.1f} s; host has {os.cpu_count()} cpus"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    teardown(world, graph_holder)
+
+
+def teardown(world, graph_holder):
+    """Release the captured graph (it holds NCCL kernels) BEFORE the communicator goes away; the
+    result line is already printed, so a communicator that refuses to shut down must not turn a
+    finished run into a hang: a timer ends the process with status 0."""
+    if world <= 1:
+        return
+    import threading
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    t = threading.Timer(30.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    torch.cuda.synchronize()
+    graph_holder.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

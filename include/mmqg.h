@@ -131,6 +131,17 @@ int mmqg_train_backward(const mmqg_dims* d, const mmqg_tensors* params, const mm
                         void* workspace, size_t workspace_bytes, mmqg_tensors* grads,
                         int phase, float dropout_p, unsigned long long seed, int mode, void* stream);
 
+/* The whole backward (as phase 0, with its internal overlap) for data-parallel callers:
+ * ready_events[i] (a cudaEvent_t created by the caller, or NULL) is recorded at the point
+ * where gradient group i+1 (1 decoder, 2 video, 3 text + embedding) is final -- on
+ * whichever stream finalises it -- so the caller can make its communication stream wait on
+ * the event and start that group's all-reduce under the rest of the backward
+ * (SURVEY.md section 8e).  All work is joined back onto `stream` before the call returns. */
+int mmqg_train_backward_events(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,
+                               void* workspace, size_t workspace_bytes, mmqg_tensors* grads,
+                               void* const* ready_events, float dropout_p, unsigned long long seed,
+                               int mode, void* stream);
+
 size_t mmqg_greedy_workspace_bytes(const mmqg_dims* d, int max_len, int mode);
 
 /* Greedy decode (reference train.py:101-110, evaluate.py:70-80): encoder pass, then

@@ -316,6 +316,28 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   return 0;
 }
 
+int mmqg_train_backward_events(const mmqg_dims* dp, const mmqg_tensors* params, const mmqg_batch* batch, void* workspace,
+                               size_t workspace_bytes, mmqg_tensors* grads, void* const* ready_events, float dropout_p,
+                               unsigned long long seed, int mode, void* stream) {
+  MMQG_REQUIRE(ready_events, "ready_events: null pointer (use mmqg_train_backward phase 0)");
+  cudaEvent_t ev[3];
+  for (int i = 0; i < 3; ++i) ev[i] = reinterpret_cast<cudaEvent_t>(ready_events[i]);
+  if (mode == MMQG_MODE_BF16) {
+    MMQG_TRY(check_dims(dp));
+    MMQG_TRY(check_tensors(*dp, params, "params"));
+    MMQG_TRY(check_tensors(*dp, grads, "grads"));
+    MMQG_REQUIRE(batch && batch->frames, "batch: null pointer");
+    MMQG_REQUIRE(workspace, "null workspace");
+    MMQG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p=%g not in [0,1)", dropout_p);
+    return train_backward_bf16(*dp, *params, *batch, workspace, workspace_bytes, *grads, 0, dropout_p, seed, as_stream(stream), ev);
+  }
+  for (int ph = 1; ph <= 3; ++ph) {     // fp32 parity mode: phases in order on the caller's stream
+    MMQG_TRY(mmqg_train_backward(dp, params, batch, workspace, workspace_bytes, grads, ph, dropout_p, seed, mode, stream));
+    if (ev[ph - 1]) MMQG_CUDA(cudaEventRecord(ev[ph - 1], as_stream(stream)));
+  }
+  return 0;
+}
+
 int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const mmqg_batch* batch, void* workspace,
                         size_t workspace_bytes, mmqg_tensors* grads, int phase, float dropout_p,
                         unsigned long long seed, int mode, void* stream) {

@@ -658,7 +658,7 @@ struct Bwd16 {
 
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                         size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
-                        cudaStream_t st) {
+                        cudaStream_t st, cudaEvent_t const* ready) {
   MMQG_TRY(check_dims_bf16(d));
   g_drop_p = dropout_p;
   g_drop_seed = seed;
@@ -695,7 +695,9 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
   MMQG_CUDA(cudaEventRecord(g_aux.ev[0], st));
   MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[0], 0));
   MMQG_TRY(b.dec_hoisted(ax));
+  if (ready && ready[0]) MMQG_CUDA(cudaEventRecord(ready[0], ax));     // decoder group final
   MMQG_TRY(b.video(ax));
+  if (ready && ready[1]) MMQG_CUDA(cudaEventRecord(ready[1], ax));     // video group final
   if (NC > 1) {
     MMQG_TRY(b.text_pipelined(NC, st, ax));
   } else {
@@ -708,7 +710,9 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
   }
   MMQG_CUDA(cudaEventRecord(g_aux.ev[7], ax));
   MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[7], 0));       // join: everything is ordered on `st` again
-  return b.emb_enc(st, NC > 1);
+  MMQG_TRY(b.emb_enc(st, NC > 1));
+  if (ready && ready[2]) MMQG_CUDA(cudaEventRecord(ready[2], st));     // text + embedding group final
+  return 0;
 }
 
 }  // namespace mmqg

@@ -90,7 +90,7 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
                        float dropout_p, unsigned long long seed, cudaStream_t st);
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                         size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
-                        cudaStream_t st);
+                        cudaStream_t st, cudaEvent_t const* ready = nullptr);
 int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* nll, int R, int V, float scale,
                   void* dlogits, int lddl, cudaStream_t st);
 int attn_fwd(float* scores, int lds, const float* M_txt, const float* M_aud, const float* M_vid, float* ctx,

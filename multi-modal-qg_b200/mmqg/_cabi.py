@@ -64,6 +64,8 @@ SYMBOLS = {
                                 _f, _f, _ull, _i, _fp]),
     "mmqg_train_backward": (_i, [_P(MmqgDims), _P(MmqgTensors), _P(MmqgBatch), _fp, _sz, _P(MmqgTensors), _i, _f,
                                  _ull, _i, _fp]),
+    "mmqg_train_backward_events": (_i, [_P(MmqgDims), _P(MmqgTensors), _P(MmqgBatch), _fp, _sz, _P(MmqgTensors),
+                                        _P(_fp), _f, _ull, _i, _fp]),
     "mmqg_greedy_workspace_bytes": (_sz, [_P(MmqgDims), _i, _i]),
     "mmqg_greedy_decode": (_i, [_P(MmqgDims), _P(MmqgTensors), _P(MmqgBatch), _fp, _sz, _fp, _i, _i, _fp]),
     "mmqg_dropout_mask": (_i, [_fp, _ll, _ull, _i, _f, _fp]),

@@ -16,6 +16,15 @@ class GradReducer:
         self.world = world_size
         self.group = group
         self.works = []
+        self.events, self.side = None, None
+        if self.buckets[0].is_cuda:
+            # ready events the library records where each gradient group becomes final, and the
+            # stream the all-reduces are issued from (so they are ordered after the event only,
+            # not after the rest of the backward on the compute stream)
+            self.events = [torch.cuda.Event() for _ in range(3)]
+            for e in self.events:
+                e.record()                     # torch creates the cudaEvent_t lazily, at first record
+            self.side = torch.cuda.Stream()
 
     def on_phase(self, i):
         """Called right after gradient group i has been enqueued on the compute stream.
@@ -23,11 +32,21 @@ class GradReducer:
         under the kernels of the next backward phase (NVLink5/NVSwitch, one flat ring/NVLS)."""
         self.works.append(dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def after_backward(self):
+        """After engine.backward_events(): start the all-reduce of groups 1..3, each behind its
+        ready event on the side stream."""
+        for i in (1, 2, 3):
+            self.side.wait_event(self.events[i - 1])
+            with torch.cuda.stream(self.side):
+                self.works.append(dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
     def finish(self):
         """Make the compute stream wait for the outstanding all-reduces."""
         for w in self.works:
             w.wait()
         self.works.clear()
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
 
 
 def shard_batch(batch: dict, rank: int, world: int) -> dict:

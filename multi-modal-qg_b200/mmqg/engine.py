@@ -96,6 +96,26 @@ class TrainEngine:
             C.byref(self._cd), C.byref(self._cp), C.byref(cb), self.ws.data_ptr(), self.ws.numel(),
             C.byref(self._cg), int(phase), self.dropout_p, self.seed, self.mode, _stream_ptr()))
 
+    def backward_events(self, batch, events):
+        """Whole backward with its internal overlap; events[i] (torch.cuda.Event, already created)
+        is recorded where gradient group i+1 becomes final (mmqg_train_backward_events)."""
+        cb = self._cbatch(batch)
+        arr = (C.c_void_p * 3)(*[e.cuda_event for e in events])
+        _cabi.check(self.lib.mmqg_train_backward_events(
+            C.byref(self._cd), C.byref(self._cp), C.byref(cb), self.ws.data_ptr(), self.ws.numel(),
+            C.byref(self._cg), arr, self.dropout_p, self.seed, self.mode, _stream_ptr()))
+
+    def step_dp(self, batch, reducer, grad_scale):
+        """Data-parallel step: forward, all-reduce of the loss-head bucket, then the overlapped
+        backward with one all-reduce per gradient group started from the group's ready event."""
+        loss = self.forward(batch, True, grad_scale)
+        reducer.on_phase(0)
+        self.backward_events(batch, reducer.events)
+        reducer.after_backward()
+        if self.dropout_p > 0 and self.auto_seed:
+            self.seed += 1
+        return loss
+
     def step(self, batch, grad_scale=1.0, on_phase=None):
         """forward + full backward.  Gradients land in self.grads (overwritten).  on_phase(i)
         is called after the gradient group i (0 loss head, 1 decoder, 2 video, 3 text+emb)

@@ -1,0 +1,25 @@
+"""Data-parallel step on real GPUs (NCCL): runs tools/check_dp.py under torchrun when the box has
+at least two GPUs (the single-GPU round-end tier skips it; tests/test_dp_gloo.py covers the host
+logic on CPU).  The tool compares the all-reduced gradients of the sharded step -- eager
+event-driven overlap, the same step replayed as one CUDA graph with the NCCL all-reduces captured,
+phase-wise overlap and no overlap -- with the whole global batch on one GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_dp_two_gpus_matches_single_gpu(mode):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541" if mode == "bf16" else "29542", os.path.join(ROOT, "tools", "check_dp.py"), "--mode", mode]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("dp world=2") == 4, out.stdout

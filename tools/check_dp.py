@@ -38,8 +38,30 @@ def main():
     eng = TrainEngine(dl, params, device=dev, mode=args.mode)
     red = GradReducer(eng, world)
     local_batch = eng.to_device(shard_batch(gbatch, rank, world))
-    for overlap in (True, False):
-        if overlap:
+    graph = None
+    for overlap in ("events", "graph", True, False):
+        if overlap == "events":                     # event-driven overlap (mmqg_train_backward_events)
+            loss = eng.step_dp(local_batch, red, 1.0 / world)
+            red.finish()
+        elif overlap == "graph":                    # the same step captured, NCCL all-reduces included
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                eng.step_dp(local_batch, red, 1.0 / world)
+                red.finish()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                eng.step_dp(local_batch, red, 1.0 / world)
+                red.finish()
+            for g in eng.grad_buckets:
+                g.zero_()
+            graph.replay()
+            graph.replay()
+            loss = eng.loss
+        elif overlap:
             loss = eng.step(local_batch, grad_scale=1.0 / world, on_phase=red.on_phase)
             red.finish()
         else:                                       # same step, all-reduce only after the whole backward
@@ -62,8 +84,15 @@ def main():
             assert abs(float(gl) - ref_loss) < tol * abs(ref_loss)
             assert worst[0] < tol, worst
             del ref
+    print(f"rank {rank}: all variants done", flush=True)
+    import threading
+    threading.Timer(20.0, lambda: os._exit(0)).start()      # a stuck communicator must not hang a finished check
+    torch.cuda.synchronize()
+    del graph
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
+    os._exit(0)
 
 
 if __name__ == "__main__":
