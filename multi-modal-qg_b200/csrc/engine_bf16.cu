@@ -30,7 +30,12 @@ struct Ws16 {
   int64_t *idx_ctx, *idx_dec, *tgt_tm, *idx_cur;
   float *bsum_text[MMQG_MAX_LAYERS], *bsum_dec[MMQG_MAX_LAYERS], *bsum_vid, *attn_b_cat, *attn_dw_cat, *attn_db_cat;
   b16 *wt_ih[MMQG_MAX_LAYERS], *wt_hh[MMQG_MAX_LAYERS], *wv_ih, *wv_hh;
-  b16 *wd_e, *wd_c, *wd_ih[MMQG_MAX_LAYERS], *wd_hh[MMQG_MAX_LAYERS], *wa_e, *wa_h, *wo;
+  // decoder LSTM weights of layer l as ONE bf16 matrix [W_hh | W_in] (4H x (H + I_l)), I_0 = context
+  // columns of W_ih_l0 (the embedding columns are hoisted: wd_e), I_l = H: the forward step reads
+  // the two column blocks as separate K-major operands, the backward step multiplies dG by the
+  // whole matrix in one launch (dh_rec and dx side by side).
+  b16 *wd_e, *wd_cat[MMQG_MAX_LAYERS], *wa_e, *wa_h, *wo;
+  float* dcat[MMQG_MAX_LAYERS];      // split-K partials of dG_l [W_hh | W_ih], (kSplitB, B, 2H), l > 0
   b16 *x0, *frames16, *hs_text[MMQG_MAX_LAYERS], *hs_v, *e_dec, *ds16, *ctx16, *hs_dec[MMQG_MAX_LAYERS], *dlogits16;
   b16 *dg_text[MMQG_MAX_LAYERS], *dg_v, *dg_dec[MMQG_MAX_LAYERS];
   float *acts_text[MMQG_MAX_LAYERS], *cs_text[MMQG_MAX_LAYERS], *m_txt, *m_aud, *m_vid, *acts_v, *cs_v;
@@ -74,10 +79,11 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.attn_b_cat = c.take<float>(Sp); w.attn_dw_cat = c.take<float>(Sp * Q); w.attn_db_cat = c.take<float>(Sp);
   for (int l = 0; l < d.L; ++l) {
     w.wt_ih[l] = c.take<b16>(G * (l == 0 ? Ep : H)); w.wt_hh[l] = c.take<b16>(G * H);
-    w.wd_ih[l] = l == 0 ? nullptr : c.take<b16>(G * H); w.wd_hh[l] = c.take<b16>(G * H);
+    w.wd_cat[l] = c.take<b16>(G * (H + (l == 0 ? C : H)));
+    w.dcat[l] = l == 0 ? nullptr : c.take<float>(kSplitB * B * 2 * H);
   }
   w.wv_ih = c.take<b16>(Gv * d.F_v); w.wv_hh = c.take<b16>(Gv * Hv);
-  w.wd_e = c.take<b16>(G * Ep); w.wd_c = c.take<b16>(G * C);
+  w.wd_e = c.take<b16>(G * Ep);
   w.wa_e = c.take<b16>(Sp * Ep); w.wa_h = c.take<b16>(Sp * H);
   w.wo = c.take<b16>((size_t)d.V * H);
   w.x0 = c.take<b16>(Rt * Ep);
@@ -105,7 +111,7 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.nll = c.take<float>(R); w.dhtop = c.take<float>(R * H);
   for (int l = 0; l < d.L; ++l) { w.dh_rec[l] = c.take<float>(kSplitB * B * H); w.dc[l] = c.take<float>(B * H); }
   w.dx_above = c.take<float>(kSplitB * B * H); w.dq_h = c.take<float>(kSplitB * B * H);
-  w.dctx_all = c.take<float>(R * C);
+  w.dctx_all = c.take<float>(R * (H + C));     // rows [d h_rec of layer 0 | d context] (one product per step)
   w.dm_txt = c.take<float>(B * d.TM * H); w.dm_vid = c.take<float>(B * d.AM * Hv);
   w.de_dec = c.take<float>(R * d.E);
   w.dh_rec_enc = c.take<float>(kSplitB * B * H); w.dh_rec_vid = c.take<float>(kSplitB * B * Hv);
@@ -223,8 +229,8 @@ static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cuda
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
     MMQG_TRY(cvt_f32_bf16_2d(P.text_w_ih[l], I, w.wt_ih[l], Ip, G, I, Ip, st));
     MMQG_TRY(cvt_f32_bf16_2d(P.text_w_hh[l], H, w.wt_hh[l], H, G, H, H, st));
-    MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_hh[l], H, w.wd_hh[l], H, G, H, H, st));
-    if (l > 0) MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[l], H, w.wd_ih[l], H, G, H, H, st));
+    MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_hh[l], H, w.wd_cat[l], H + (l == 0 ? C : H), G, H, H, st));
+    if (l > 0) MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[l], H, w.wd_cat[l] + H, 2 * H, G, H, H, st));
     MMQG_TRY(add2(P.text_b_ih[l], P.text_b_hh[l], w.bsum_text[l], G, st));
     MMQG_TRY(add2(P.dec_b_ih[l], P.dec_b_hh[l], w.bsum_dec[l], G, st));
   }
@@ -232,7 +238,7 @@ static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cuda
   MMQG_TRY(cvt_f32_bf16_2d(P.vid_w_hh, Hv, w.wv_hh, Hv, Gv, Hv, Hv, st));
   MMQG_TRY(add2(P.vid_b_ih, P.vid_b_hh, w.bsum_vid, Gv, st));
   MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[0], X0, w.wd_e, Ep, G, E, Ep, st));
-  MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[0] + E, X0, w.wd_c, C, G, C, C, st));
+  MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[0] + E, X0, w.wd_cat[0] + H, H + C, G, C, C, st));
   MMQG_CUDA(cudaMemsetAsync(w.wa_e, 0, sizeof(b16) * (size_t)Sp * Ep, st));
   MMQG_CUDA(cudaMemsetAsync(w.wa_h, 0, sizeof(b16) * (size_t)Sp * H, st));
   MMQG_CUDA(cudaMemsetAsync(w.attn_b_cat, 0, sizeof(float) * Sp, st));
@@ -423,10 +429,11 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
       float* acts = w.acts_dec[l] + (size_t)t * B * G;
       const b16* hprev = w.hs_dec[l] + (size_t)t * B * H;
       if (l == 0)
-        MMQG_TRY(Tc(ctx, C, false, w.wd_c, C, false, B, G, C, acts, G).second(hprev, H, w.wd_hh[0], H, H).accumulate(true).run(st));
+        MMQG_TRY(Tc(ctx, C, false, w.wd_cat[0] + H, H + C, false, B, G, C, acts, G).second(hprev, H, w.wd_cat[0], H + C, H)
+                     .accumulate(true).run(st));
       else
         MMQG_TRY(Tc(g_drop_p > 0.f ? w.hdrop_dec[l - 1] + (size_t)t * B * H : w.hs_dec[l - 1] + (size_t)(t + 1) * B * H, H, false,
-                    w.wd_ih[l], H, false, B, G, H, acts, G).second(hprev, H, w.wd_hh[l], H, H).bias(w.bsum_dec[l]).run(st));
+                    w.wd_cat[l] + H, 2 * H, false, B, G, H, acts, G).second(hprev, H, w.wd_cat[l], 2 * H, H).bias(w.bsum_dec[l]).run(st));
       DropSpec dr;
       if (g_drop_p > 0.f && l + 1 < d.L) {
         dr.out = w.hdrop_dec[l] + (size_t)t * B * H; dr.ld = H; dr.seed = g_drop_seed; dr.sid = kSidDec + l;
@@ -475,39 +482,59 @@ struct Bwd16 {
     for (int t = d.T_q - 1; t >= 0; --t) {
       StepGemmScope step_scope;
       const bool last = t == d.T_q - 1;
+      // t > 0: ONE product per layer, dG_l [W_hh | W_in] -> (d h_rec for step t-1 | d input of this step);
+      // t == 0 writes the recurrent part where the text encoder's BPTT picks it up (dh_rec[l]).
+      const bool fused = t > 0;
+      const int Cd = H + C;
+      const long long pc = (long long)B * 2 * H;     // partial stride of dcat
       for (int l = L - 1; l >= 0; --l) {
         const float* acts = w.acts_dec[l] + (size_t)t * B * G;
         b16* dg = w.dg_dec[l] + (size_t)t * B * G;
-        const float* dh0 = last ? nullptr : w.dh_rec[l];
-        const float* dh1 = nullptr; int n1 = 0;
+        // recurrent gradient from step t+1 (always produced by a fused launch)
+        const float* dh0 = nullptr; int ld0 = H, n0 = kSplitB; long long s0 = ps;
+        if (!last) {
+          if (l > 0) { dh0 = w.dcat[l]; ld0 = 2 * H; s0 = pc; }
+          else { dh0 = w.dctx_all + (size_t)(t + 1) * B * Cd; ld0 = Cd; n0 = 1; s0 = 0; }
+        }
+        const float* dh1 = nullptr; int ld1 = H, n1 = 0; long long s1 = ps;
         const float* dh2 = nullptr;
         DropSpec dr;
         if (l == L - 1) {
           dh2 = w.dhtop + (size_t)t * B * H;
           if (!last) { dh1 = w.dq_h; n1 = kSplitB; }
         } else {
-          dh1 = w.dx_above; n1 = kSplitB;
-          if (g_drop_p > 0.f) {   // dx_above is d/d(dropped h_l): back through the mask of layer l's output
+          n1 = kSplitB;               // d input of layer l+1, this step
+          if (fused) { dh1 = w.dcat[l + 1] + H; ld1 = 2 * H; s1 = pc; }
+          else dh1 = w.dx_above;
+          if (g_drop_p > 0.f) {   // it is d/d(dropped h_l): back through the mask of layer l's output
             dr.seed = g_drop_seed; dr.sid = kSidDec + l; dr.base = (unsigned long long)t * B * H; dr.p = g_drop_p;
           }
         }
         MMQG_TRY(lstm_pointwise_bwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H,
-                                         H, dh0, H, kSplitB, ps, dh1, H, n1, ps, dh2, H, w.dc[l], H, last ? 1 : 0, dg, G, B,
+                                         H, dh0, ld0, n0, s0, dh1, ld1, n1, s1, dh2, H, w.dc[l], H, last ? 1 : 0, dg, G, B,
                                          H, st, dr));
-        MMQG_TRY(Tc(dg, G, false, w.wd_hh[l], H, true, B, H, G, w.dh_rec[l], H).split(kSplitB, ps).run(st));
-        if (l > 0)
-          MMQG_TRY(Tc(dg, G, false, w.wd_ih[l], H, true, B, H, G, w.dx_above, H).split(kSplitB, ps).run(st));
-        else
-          MMQG_TRY(Tc(dg, G, false, w.wd_c, C, true, B, C, G, w.dctx_all + (size_t)t * B * C, C).run(st));
+        float* dctx = w.dctx_all + (size_t)t * B * Cd;
+        if (fused) {
+          if (l > 0)
+            MMQG_TRY(Tc(dg, G, false, w.wd_cat[l], 2 * H, true, B, 2 * H, G, w.dcat[l], 2 * H).split(kSplitB, pc).run(st));
+          else
+            MMQG_TRY(Tc(dg, G, false, w.wd_cat[0], Cd, true, B, Cd, G, dctx, Cd).run(st));
+        } else {
+          MMQG_TRY(Tc(dg, G, false, w.wd_cat[l], l > 0 ? 2 * H : Cd, true, B, H, G, w.dh_rec[l], H).split(kSplitB, ps).run(st));
+          if (l > 0)
+            MMQG_TRY(Tc(dg, G, false, w.wd_cat[l] + H, 2 * H, true, B, H, G, w.dx_above, H).split(kSplitB, ps).run(st));
+          else
+            MMQG_TRY(Tc(dg, G, false, w.wd_cat[0] + H, Cd, true, B, C, G, dctx + H, Cd).run(st));
+        }
       }
       float* ds = w.ds_all + (size_t)t * B * Sp;
       as.ds16 = w.ds16 + (size_t)t * B * Sp;
-      MMQG_TRY(attn_bwd(w.attn_all + (size_t)t * B * Sp, ds, Sp, w.dctx_all + (size_t)t * B * C, C, w.m_txt, w.m_aud, w.m_vid,
-                        nullptr, nullptr, as, st));
+      MMQG_TRY(attn_bwd(w.attn_all + (size_t)t * B * Sp, ds, Sp, w.dctx_all + (size_t)t * B * (H + C) + H, H + C, w.m_txt,
+                        w.m_aud, w.m_vid, nullptr, nullptr, as, st));
       MMQG_TRY(Tc(as.ds16, Sp, false, w.wa_h, H, true, B, H, Sp, w.dq_h, H).split(kSplitB, ps).run(st));
     }
     // memory gradients feed the encoders' BPTT
-    return attn_dmem(w.attn_all, Sp, w.dctx_all, C, w.dm_txt, w.dm_vid, d.T_q, as, st);
+    return attn_dmem(w.attn_all, Sp, w.dctx_all + H, H + C, w.dm_txt, w.dm_vid, d.T_q, as, st);
   }
 
   // hoisted decoder gradients: LSTM weights/biases, attention Linears, decoder-side embedding rows
