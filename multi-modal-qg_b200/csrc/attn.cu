@@ -113,7 +113,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* attn, float*
   const float* at = attn + (size_t)b * lds;
   float* ds = ds_out + (size_t)b * lds;
   for (int j = tid; j < S; j += 256) { a[j] = at[j]; da[j] = 0.f; }
-  for (int o = tid; o < C; o += 256) dc[o] = dctx[(size_t)b * lddctx + o];
+  for (int o = tid; o < C; o += 256) {
+    float v = dctx[(size_t)b * lddctx + o];
+    for (int k = 1; k < s.dctx_parts; ++k) v += dctx[(size_t)k * s.dctx_part_stride + (size_t)b * lddctx + o];
+    dc[o] = v;
+    if (s.dctx_sum) s.dctx_sum[(size_t)b * s.lddsum + o] = v;
+  }
   __syncthreads();
   const float* mt = M_txt + (size_t)b * s.TM * s.H;
   const float* ma = M_aud + (size_t)b * s.AM * s.H_a;

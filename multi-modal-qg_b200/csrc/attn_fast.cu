@@ -140,30 +140,55 @@ __global__ void __launch_bounds__(512) attn_bwd_fast_kernel(const float* attn, f
   const int S = s.TM + 2 * s.AM, C = s.H + s.H_a + s.H_v;
   float* a = sm;
   float* da = sm + S;
-  float* dc = sm + 2 * S;
+  float* dc = sm + ((2 * S + 3) & ~3);      // 16-byte aligned: read as float4 below
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();
   const float* at = attn + (size_t)b * lds;
   float* ds = ds_out + (size_t)b * lds;
   for (int j = tid; j < S; j += 512) { a[j] = at[j]; da[j] = 0.f; }
-  for (int o = tid; o < C; o += 512) dc[o] = dctx[(size_t)b * lddctx + o];
+  for (int o = tid; o < C; o += 512) {
+    float v = dctx[(size_t)b * lddctx + o];
+    for (int k = 1; k < s.dctx_parts; ++k) v += dctx[(size_t)k * s.dctx_part_stride + (size_t)b * lddctx + o];
+    dc[o] = v;
+    if (s.dctx_sum) s.dctx_sum[(size_t)b * s.lddsum + o] = v;
+  }
   __syncthreads();
-  // da(j) = <dctx_head, M(b,j,:)> over the real rows; one warp per row, 16 warps
+  // da(j) = <dctx_head, M(b,j,:)> over the real rows.  Text rows: each of the 16 warps takes rows
+  // j0, j0+16, j0+32, j0+48 together, so four independent 16-byte loads per lane are in flight
+  // (the kernel is bound by load latency, not bytes: the rows of one sample are only ~100 KB).
+  for (int j0 = warp; j0 < s.T_t; j0 += 64) {
+    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int h = 8 * lane; h < s.H; h += 256) {
+      float v[4][8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = j0 + 16 * r;
+        if (j < s.T_t) load8(M_txt + ((size_t)b * s.TM + j) * s.H + h, v[r]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[r][i] = 0.f;
+        }
+      }
+      const float4 d0 = *reinterpret_cast<const float4*>(dc + h), d1 = *reinterpret_cast<const float4*>(dc + h + 4);
+      const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc4[r] = fmaf(dv[i], v[r][i], acc4[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float t = fw_sum(acc4[r]);
+      if (lane == 0 && j0 + 16 * r < s.T_t) da[j0 + 16 * r] = t;
+    }
+  }
+  // audio / video rows: one warp per row
   const int n_rows = s.T_t + 2 * s.T_v;
-  for (int j = warp; j < n_rows; j += 16) {
+  for (int j = s.T_t + warp; j < n_rows; j += 16) {
     float acc = 0.f;
     int slot;
-    if (j < s.T_t) {
-      const MT* row = M_txt + ((size_t)b * s.TM + j) * s.H;
-      for (int h = 8 * lane; h < s.H; h += 256) {
-        float v[8];
-        load8(row + h, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(dc[h + i], v[i], acc);
-      }
-      slot = j;
-    } else if (j < s.T_t + s.T_v) {
+    if (j < s.T_t + s.T_v) {
       const int k = j - s.T_t;
       const float* row = M_aud + ((size_t)b * s.AM + k) * s.H_a;
       for (int h = lane; h < s.H_a; h += 32) acc = fmaf(dc[s.H + h], row[h], acc);
@@ -225,7 +250,7 @@ int attn_fwd_fast(float* scores, int lds, const void* M_txt, const float* M_aud,
 int attn_bwd_fast(const float* attn, float* ds_out, int lds, const float* dctx, int lddctx, const void* M_txt, const float* M_aud,
                   const void* M_vid, bool mem_bf16, const AttnShape& s, cudaStream_t st) {
   const int S = s.TM + 2 * s.AM, C = s.H + s.H_a + s.H_v;
-  const size_t smem = (size_t)(2 * S + C) * sizeof(float);
+  const size_t smem = (size_t)(2 * S + 4 + C) * sizeof(float);
   MMQG_REQUIRE(smem <= 48 * 1024, "attn_bwd_fast: shape exceeds the 48 KB staging buffer");
   const double esz = mem_bf16 ? 2.0 : 4.0;
   MMQG_PROBE(KC_ATTN, 2.0 * s.B * ((double)s.T_t * s.H + (double)s.T_v * (s.H_a + s.H_v)),

@@ -35,7 +35,8 @@ struct Ws16 {
   // the two column blocks as separate K-major operands, the backward step multiplies dG by the
   // whole matrix in one launch (dh_rec and dx side by side).
   b16 *wd_e, *wd_cat[MMQG_MAX_LAYERS], *wa_e, *wa_h, *wo;
-  float* dcat[MMQG_MAX_LAYERS];      // split-K partials of dG_l [W_hh | W_ih], (kSplitB, B, 2H), l > 0
+  float* gpart;                      // split-K partials of the decoder's forward step product, (2, B, 4H)
+  float* dcat[MMQG_MAX_LAYERS];      // split-K partials of dG_l [W_hh | W_in]: (kSplitB, B, H + I_l)
   b16 *x0, *frames16, *hs_text[MMQG_MAX_LAYERS], *hs_v, *e_dec, *ds16, *ctx16, *hs_dec[MMQG_MAX_LAYERS], *dlogits16;
   b16 *dg_text[MMQG_MAX_LAYERS], *dg_v, *dg_dec[MMQG_MAX_LAYERS];
   float *acts_text[MMQG_MAX_LAYERS], *cs_text[MMQG_MAX_LAYERS], *m_txt, *m_aud, *m_vid, *acts_v, *cs_v;
@@ -80,7 +81,7 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   for (int l = 0; l < d.L; ++l) {
     w.wt_ih[l] = c.take<b16>(G * (l == 0 ? Ep : H)); w.wt_hh[l] = c.take<b16>(G * H);
     w.wd_cat[l] = c.take<b16>(G * (H + (l == 0 ? C : H)));
-    w.dcat[l] = l == 0 ? nullptr : c.take<float>(kSplitB * B * 2 * H);
+    w.dcat[l] = c.take<float>(kSplitB * B * (H + (l == 0 ? C : H)));
   }
   w.wv_ih = c.take<b16>(Gv * d.F_v); w.wv_hh = c.take<b16>(Gv * Hv);
   w.wd_e = c.take<b16>(G * Ep);
@@ -111,7 +112,8 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.nll = c.take<float>(R); w.dhtop = c.take<float>(R * H);
   for (int l = 0; l < d.L; ++l) { w.dh_rec[l] = c.take<float>(kSplitB * B * H); w.dc[l] = c.take<float>(B * H); }
   w.dx_above = c.take<float>(kSplitB * B * H); w.dq_h = c.take<float>(kSplitB * B * H);
-  w.dctx_all = c.take<float>(R * (H + C));     // rows [d h_rec of layer 0 | d context] (one product per step)
+  w.dctx_all = c.take<float>(R * C);
+  w.gpart = c.take<float>(2 * B * G);
   w.dm_txt = c.take<float>(B * d.TM * H); w.dm_vid = c.take<float>(B * d.AM * Hv);
   w.de_dec = c.take<float>(R * d.E);
   w.dh_rec_enc = c.take<float>(kSplitB * B * H); w.dh_rec_vid = c.take<float>(kSplitB * B * Hv);
@@ -168,6 +170,25 @@ static AttnShape attn_shape16(const mmqg_dims& d, const Ws16& w) {
   return a;
 }
 
+// Debug hook (tools/sections.py; not used by the product path): CUDA events at the section
+// boundaries of one eager step on the caller's stream -- 0 start, 1 weights packed, 2 encoders done,
+// 3 decoder hoisted products, 4 decoder step loop, 5 loss head, 6 backward start, 7 decoder BPTT
+// loop, 8 text BPTT (main-stream part), 9 end.
+struct SectionMarks {
+  bool on = false;
+  cudaEvent_t ev[10] = {};
+  bool created = false;
+};
+static SectionMarks g_sec;
+static void mark(int i, cudaStream_t st) {
+  if (!g_sec.on) return;
+  if (!g_sec.created) {
+    for (auto& e : g_sec.ev) cudaEventCreate(&e);
+    g_sec.created = true;
+  }
+  cudaEventRecord(g_sec.ev[i], st);
+}
+
 // inter-layer dropout of the current call (set at the entry points; 0 = off)
 static thread_local float g_drop_p = 0.f;
 static thread_local unsigned long long g_drop_seed = 0;
@@ -221,17 +242,27 @@ static int rec_bwd(const float* acts, const float* cs, void* dg, const void* wp,
   return lstm_seq_bwd_persist(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, flags, T, B, H, 0, nullptr, st);
 }
 
-// fp32 parameters -> packed bf16 caches + summed biases + concatenated attention bias
-static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cudaStream_t st) {
-  const int H = d.H, G = 4 * d.H, Hv = d.H_v, Gv = 4 * d.H_v, E = d.E, Ep = w.Ep, Q = d.E + d.H;
-  const int C = d.H + d.H_a + d.H_v, X0 = E + C, Sp = w.Sp;
+// fp32 parameters -> packed bf16 caches + summed biases + concatenated attention bias.
+// Two halves so that only what the text encoder needs sits in front of it on the caller's
+// stream; the rest is packed on an auxiliary stream beside the text encoder.
+static int pack_weights_text(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cudaStream_t st) {
+  const int H = d.H, G = 4 * d.H, E = d.E, Ep = w.Ep;
   for (int l = 0; l < d.L; ++l) {
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
     MMQG_TRY(cvt_f32_bf16_2d(P.text_w_ih[l], I, w.wt_ih[l], Ip, G, I, Ip, st));
     MMQG_TRY(cvt_f32_bf16_2d(P.text_w_hh[l], H, w.wt_hh[l], H, G, H, H, st));
+    MMQG_TRY(add2(P.text_b_ih[l], P.text_b_hh[l], w.bsum_text[l], G, st));
+  }
+  if (persist_text(d))
+    for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_rec(P.text_w_hh[l], w.wtp_f[l], w.wtp_b[l], d.B, H, st));
+  return 0;
+}
+static int pack_weights_rest(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cudaStream_t st) {
+  const int H = d.H, G = 4 * d.H, Hv = d.H_v, Gv = 4 * d.H_v, E = d.E, Ep = w.Ep, Q = d.E + d.H;
+  const int C = d.H + d.H_a + d.H_v, X0 = E + C, Sp = w.Sp;
+  for (int l = 0; l < d.L; ++l) {
     MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_hh[l], H, w.wd_cat[l], H + (l == 0 ? C : H), G, H, H, st));
     if (l > 0) MMQG_TRY(cvt_f32_bf16_2d(P.dec_w_ih[l], H, w.wd_cat[l] + H, 2 * H, G, H, H, st));
-    MMQG_TRY(add2(P.text_b_ih[l], P.text_b_hh[l], w.bsum_text[l], G, st));
     MMQG_TRY(add2(P.dec_b_ih[l], P.dec_b_hh[l], w.bsum_dec[l], G, st));
   }
   MMQG_TRY(cvt_f32_bf16_2d(P.vid_w_ih, d.F_v, w.wv_ih, d.F_v, Gv, d.F_v, d.F_v, st));
@@ -249,8 +280,6 @@ static int pack_weights(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cuda
     MMQG_CUDA(cudaMemcpyAsync(w.attn_b_cat + off[i], P.attn_b[i], sizeof(float) * len[i], cudaMemcpyDeviceToDevice, st));
   }
   MMQG_TRY(cvt_f32_bf16_2d(P.out_w, H, w.wo, H, d.V, H, H, st));
-  if (persist_text(d))
-    for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_rec(P.text_w_hh[l], w.wtp_f[l], w.wtp_b[l], d.B, H, st));
   if (persist_video(d)) MMQG_TRY(pack_rec(P.vid_w_hh, w.wvp_f, w.wvp_b, d.B, Hv, st));
   return 0;
 }
@@ -295,8 +324,9 @@ static int text_chunks(const mmqg_dims& d) {
   return nc;
 }
 
-static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, Ws16& w, cudaStream_t st) {
-  const int B = d.B, H = d.H, G = 4 * d.H, Hv = d.H_v, Gv = 4 * d.H_v;
+// audio pass-through + video LSTM -> zero-padded attention memories (train.py:155-157)
+static int video_forward16(const mmqg_dims& d, const mmqg_batch& bt, Ws16& w, cudaStream_t st) {
+  const int B = d.B, Hv = d.H_v, Gv = 4 * d.H_v;
   MMQG_CUDA(cudaMemcpy2DAsync(w.m_aud, sizeof(float) * (size_t)d.AM * d.H_a, bt.audio,
                               sizeof(float) * (size_t)d.T_v * d.H_a, sizeof(float) * (size_t)d.T_v * d.H_a, B,
                               cudaMemcpyDeviceToDevice, st));
@@ -310,7 +340,7 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
                   w.acts_v + (size_t)t * B * Gv, Gv).bias(w.bsum_vid).run(st));
     MMQG_CUDA(cudaMemsetAsync(w.hs_v, 0, sizeof(b16) * (size_t)B * Hv, st));
     MMQG_CUDA(cudaMemsetAsync(w.cs_v, 0, sizeof(float) * (size_t)B * Hv, st));
-    MMQG_TRY(rec_fwd(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags, d.T_v, B, Hv, st));
+    MMQG_TRY(rec_fwd(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags_v, d.T_v, B, Hv, st));
   } else
   for (int t = 0; t < d.T_v; ++t) {
     StepGemmScope step_scope;
@@ -323,7 +353,12 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
                                      w.cs_v + (size_t)(t + 1) * B * Hv, Hv, w.hs_v + (size_t)(t + 1) * B * Hv, Hv,
                                      w.m_vid + (size_t)t * Hv, d.AM * Hv, B, Hv, st));
   }
-  // text LSTM stack (encoder.py:95-100): hoisted input projection per layer, recurrent part per step
+  return cvt_f32_bf16_2d(w.m_vid, Hv, w.m_vid16, Hv, (long long)B * d.AM, Hv, Hv, st);
+}
+
+// text LSTM stack (encoder.py:95-100): hoisted input projection per layer, recurrent part per step
+static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cudaStream_t st) {
+  const int B = d.B, H = d.H, G = 4 * d.H;
   MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_ctx, w.x0, w.Ep, d.T_t * B, d.E, w.Ep, d.V, st));
   const int NC = text_chunks(d);
   if (NC > 1) {
@@ -386,7 +421,6 @@ static int encoder_forward16(const mmqg_dims& d, const mmqg_tensors& P, const mm
   // bf16 attention memories: the pipelined persistent path writes the text memory in bf16 directly;
   // every other path produced fp32 rows, converted here (rows beyond T_t / T_v are never read)
   if (NC <= 1) MMQG_TRY(cvt_f32_bf16_2d(w.m_txt, H, w.m_txt16, H, (long long)B * d.TM, H, H, st));
-  MMQG_TRY(cvt_f32_bf16_2d(w.m_vid, Hv, w.m_vid16, Hv, (long long)B * d.AM, Hv, Hv, st));
   // decoder state slab 0 := encoder final state (train.py:169)
   const size_t n = (size_t)B * H;
   for (int l = 0; l < d.L; ++l) {
@@ -406,17 +440,60 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, R = d.T_q * B, Sp = w.Sp, Ep = w.Ep;
 
+  mark(0, st);
+  MMQG_TRY(g_aux.init());
+  cudaStream_t ax = g_aux.s[AuxStream::NS - 1], lh = g_aux.s[AuxStream::NS - 2];
   MMQG_TRY(build_indices(bt.context, bt.target, w.idx_ctx, w.idx_dec, w.tgt_tm, B, d.T_t, d.T_q, st));
-  MMQG_TRY(pack_weights(d, P, w, st));
-  MMQG_TRY(encoder_forward16(d, P, bt, w, st));
-
-  // decoder: hoisted embedding-column products over all teacher-forced steps
-  MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_dec, w.e_dec, Ep, R, d.E, Ep, d.V, st));
-  MMQG_TRY(Tc(w.e_dec, Ep, false, w.wd_e, Ep, false, R, G, Ep, w.acts_dec[0], G).bias(w.bsum_dec[0]).run(st));
-  MMQG_TRY(Tc(w.e_dec, Ep, false, w.wa_e, Ep, false, R, Sp, Ep, w.attn_all, Sp).bias(w.attn_b_cat).run(st));
+  // fork: everything the text encoder does not need -- the other weight packs, the video LSTM
+  // and the decoder's hoisted embedding-column products over all teacher-forced steps -- runs on
+  // an auxiliary stream beside the text encoder and is joined in front of the decoder loop
+  MMQG_CUDA(cudaEventRecord(g_aux.ev[8], st));
+  MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[8], 0));
+  MMQG_TRY(pack_weights_rest(d, P, w, ax));
+  MMQG_TRY(video_forward16(d, bt, w, ax));
+  MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_dec, w.e_dec, Ep, R, d.E, Ep, d.V, ax));
+  MMQG_TRY(Tc(w.e_dec, Ep, false, w.wd_e, Ep, false, R, G, Ep, w.acts_dec[0], G).bias(w.bsum_dec[0]).run(ax));
+  MMQG_TRY(Tc(w.e_dec, Ep, false, w.wa_e, Ep, false, R, Sp, Ep, w.attn_all, Sp).bias(w.attn_b_cat).run(ax));
+  MMQG_CUDA(cudaEventRecord(g_aux.ev[9], ax));
+  MMQG_TRY(pack_weights_text(d, P, w, st));
+  mark(1, st);
+  MMQG_TRY(text_forward16(d, P, w, st));
+  mark(2, st);
+  MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[9], 0));
+  mark(3, st);
   AttnShape as = attn_shape16(d, w);
   as.ldctx16 = C;
-  PdlScope pdl_scope(pdl_enabled());      // the T_q x 5 dependent launches below overlap prologue and tail
+  // loss head over rows [r0, r0+n) of h_top (row = t*B + b), in chunks of at most Rc rows: logits
+  // (fp32, chunk only) -> NLL (+ bf16 dlogits -> dH, dW_out, db_out); full-vocabulary logits are
+  // never stored (decoder.py:106, train.py:174).
+  const b16* htop = w.hs_dec[d.L - 1] + (size_t)B * H;
+  const float dscale = want_grads ? grad_scale / (float)B : 0.f;
+  auto loss_head = [&](int r0, int n, bool first, cudaStream_t s) -> int {
+    PdlScope no_pdl(false);
+    for (int q0 = r0; q0 < r0 + n; q0 += w.Rc, first = false) {
+      const int rc = r0 + n - q0 < w.Rc ? r0 + n - q0 : w.Rc;
+      MMQG_TRY(Tc(htop + (size_t)q0 * H, H, false, w.wo, H, false, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(s));
+      MMQG_TRY(nll_rows_bf16(w.logits, d.V, w.tgt_tm + q0, w.nll + q0, rc, d.V, dscale, want_grads ? w.dlogits16 : nullptr,
+                             w.Vp, s));
+      if (want_grads) {
+        MMQG_TRY(Tc(w.dlogits16, w.Vp, false, w.wo, H, true, rc, H, d.V, w.dhtop + (size_t)q0 * H, H).run(s));
+        MMQG_TRY(Tc(w.dlogits16, w.Vp, true, htop + (size_t)q0 * H, H, true, d.V, H, rc, grads->out_w, H).accumulate(!first).run(s));
+        MMQG_TRY(colsum_bf16(w.dlogits16, w.Vp, grads->out_b, nullptr, rc, d.V, first ? 0.f : 1.f, s));
+      }
+    }
+    return 0;
+  };
+  // The loss head of the steps already decoded runs on its own stream under the remaining
+  // (latency-bound, 64-CTA) decoder steps: groups of `lh_steps` whole steps, at most Rc rows.
+  static const bool lh_env = []() { const char* e = getenv("MMQG_LOSS_OVERLAP"); return !(e && e[0] == '0'); }();
+  const int lh_steps = w.Rc / B;
+  const bool lh_overlap = lh_env && lh_steps >= 1 && d.T_q > 1;
+  int lh_done = 0;      // steps whose loss head has been issued
+  PdlScope pdl_scope(pdl_enabled());      // the dependent launches below overlap prologue and tail
+  // MMQG_STEP_FUSE: 0 = product + cell kernel, 1 = one fused launch (lstm_step_tc.cu), 2 = split-K product + summing cell kernel
+  static const int step_mode_env = []() { const char* e = getenv("MMQG_STEP_FUSE"); return e ? atoi(e) : 1; }();
+  const int step_mode = step_mode_env;
+  const bool step_fused = step_mode == 1 && lstm_step_tc_ok(H, G, H, H, H, G);
   for (int t = 0; t < d.T_q; ++t) {
     StepGemmScope step_scope;
     const b16* htop_prev = w.hs_dec[d.L - 1] + (size_t)t * B * H;
@@ -428,36 +505,52 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
     for (int l = 0; l < d.L; ++l) {
       float* acts = w.acts_dec[l] + (size_t)t * B * G;
       const b16* hprev = w.hs_dec[l] + (size_t)t * B * H;
-      if (l == 0)
-        MMQG_TRY(Tc(ctx, C, false, w.wd_cat[0] + H, H + C, false, B, G, C, acts, G).second(hprev, H, w.wd_cat[0], H + C, H)
-                     .accumulate(true).run(st));
-      else
-        MMQG_TRY(Tc(g_drop_p > 0.f ? w.hdrop_dec[l - 1] + (size_t)t * B * H : w.hs_dec[l - 1] + (size_t)(t + 1) * B * H, H, false,
-                    w.wd_cat[l] + H, 2 * H, false, B, G, H, acts, G).second(hprev, H, w.wd_cat[l], 2 * H, H).bias(w.bsum_dec[l]).run(st));
+      const b16* xin = l == 0 ? ctx : (g_drop_p > 0.f ? w.hdrop_dec[l - 1] + (size_t)t * B * H : w.hs_dec[l - 1] + (size_t)(t + 1) * B * H);
+      const int Kin = l == 0 ? C : H, Nl = H + Kin;      // wd_cat[l] = [W_hh | W_in], row pitch Nl
       DropSpec dr;
       if (g_drop_p > 0.f && l + 1 < d.L) {
         dr.out = w.hdrop_dec[l] + (size_t)t * B * H; dr.ld = H; dr.seed = g_drop_seed; dr.sid = kSidDec + l;
         dr.base = (unsigned long long)t * B * H; dr.p = g_drop_p;
       }
-      MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
-                                       w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st, dr));
+      float* c_prev = w.cs_dec[l] + (size_t)t * B * H;
+      float* c_new = w.cs_dec[l] + (size_t)(t + 1) * B * H;
+      b16* h_new = w.hs_dec[l] + (size_t)(t + 1) * B * H;
+      if (step_fused) {      // GEMM + cell update in one launch; layer 0 adds the hoisted embedding product (in acts)
+        MMQG_TRY(lstm_step_tc(xin, Kin, Kin, w.wd_cat[l] + H, Nl, hprev, H, w.wd_cat[l], Nl, l == 0 ? nullptr : w.bsum_dec[l],
+                              l == 0 ? acts : nullptr, G, acts, G, c_prev, H, c_new, H, h_new, H, B, H, dr, st));
+        continue;
+      }
+      if (step_mode == 2) {  // split-K over twice as many CTAs (the product is bound by per-SM operand ingest); the
+                             // cell kernel sums the partials, the bias and (layer 0) the hoisted embedding product
+        MMQG_TRY(Tc(xin, Kin, false, w.wd_cat[l] + H, Nl, false, B, G, Kin, w.gpart, G).second(hprev, H, w.wd_cat[l], Nl, H)
+                     .split(2, (long long)B * G).run(st));
+        PreSpec pre;
+        pre.part = w.gpart; pre.n_part = 2; pre.ld = G; pre.stride = (long long)B * G;
+        pre.bias = l == 0 ? nullptr : w.bsum_dec[l]; pre.add_gates = l == 0 ? 1 : 0;
+        MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, c_prev, H, c_new, H, h_new, H, nullptr, 0, B, H, st, dr, pre));
+        continue;
+      }
+      if (l == 0)
+        MMQG_TRY(Tc(xin, Kin, false, w.wd_cat[0] + H, Nl, false, B, G, Kin, acts, G).second(hprev, H, w.wd_cat[0], Nl, H)
+                     .accumulate(true).run(st));
+      else
+        MMQG_TRY(Tc(xin, Kin, false, w.wd_cat[l] + H, Nl, false, B, G, Kin, acts, G).second(hprev, H, w.wd_cat[l], Nl, H)
+                     .bias(w.bsum_dec[l]).run(st));
+      MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, c_prev, H, c_new, H, h_new, H, nullptr, 0, B, H, st, dr));
+    }
+    if (lh_overlap && (t + 1 - lh_done == lh_steps || t == d.T_q - 1)) {
+      MMQG_CUDA(cudaEventRecord(g_aux.ev[10], st));
+      MMQG_CUDA(cudaStreamWaitEvent(lh, g_aux.ev[10], 0));
+      MMQG_TRY(loss_head(lh_done * B, (t + 1 - lh_done) * B, lh_done == 0, lh));
+      lh_done = t + 1;
+      if (t == d.T_q - 1) MMQG_CUDA(cudaEventRecord(g_aux.ev[11], lh));
     }
   }
-  // loss head in row chunks: logits (fp32, chunk only) -> NLL (+ bf16 dlogits -> dH, dW_out, db_out)
-  const b16* htop = w.hs_dec[d.L - 1] + (size_t)B * H;
-  const float dscale = want_grads ? grad_scale / (float)B : 0.f;
-  for (int r0 = 0, first = 1; r0 < R; r0 += w.Rc, first = 0) {
-    const int rc = R - r0 < w.Rc ? R - r0 : w.Rc;
-    MMQG_TRY(Tc(htop + (size_t)r0 * H, H, false, w.wo, H, false, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(st));
-    MMQG_TRY(nll_rows_bf16(w.logits, d.V, w.tgt_tm + r0, w.nll + r0, rc, d.V, dscale, want_grads ? w.dlogits16 : nullptr,
-                           w.Vp, st));
-    if (want_grads) {
-      MMQG_TRY(Tc(w.dlogits16, w.Vp, false, w.wo, H, true, rc, H, d.V, w.dhtop + (size_t)r0 * H, H).run(st));
-      MMQG_TRY(Tc(w.dlogits16, w.Vp, true, htop + (size_t)r0 * H, H, true, d.V, H, rc, grads->out_w, H).accumulate(!first).run(st));
-      MMQG_TRY(colsum_bf16(w.dlogits16, w.Vp, grads->out_b, nullptr, rc, d.V, first ? 0.f : 1.f, st));
-    }
-  }
+  mark(4, st);
+  if (!lh_overlap) MMQG_TRY(loss_head(0, R, true, st));
+  else MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[11], 0));      // join the loss-head stream
   MMQG_TRY(sum_scale(w.nll, R, 1.0f / (float)B, loss_out, st));
+  mark(5, st);
   return 0;
 }
 
@@ -486,15 +579,16 @@ struct Bwd16 {
       // t == 0 writes the recurrent part where the text encoder's BPTT picks it up (dh_rec[l]).
       const bool fused = t > 0;
       const int Cd = H + C;
-      const long long pc = (long long)B * 2 * H;     // partial stride of dcat
+      const long long pc = (long long)B * 2 * H, pc0 = (long long)B * Cd;     // partial strides of dcat[l > 0], dcat[0]
       for (int l = L - 1; l >= 0; --l) {
         const float* acts = w.acts_dec[l] + (size_t)t * B * G;
         b16* dg = w.dg_dec[l] + (size_t)t * B * G;
         // recurrent gradient from step t+1 (always produced by a fused launch)
         const float* dh0 = nullptr; int ld0 = H, n0 = kSplitB; long long s0 = ps;
         if (!last) {
-          if (l > 0) { dh0 = w.dcat[l]; ld0 = 2 * H; s0 = pc; }
-          else { dh0 = w.dctx_all + (size_t)(t + 1) * B * Cd; ld0 = Cd; n0 = 1; s0 = 0; }
+          dh0 = w.dcat[l];
+          if (l > 0) { ld0 = 2 * H; s0 = pc; }
+          else { ld0 = Cd; s0 = pc0; }
         }
         const float* dh1 = nullptr; int ld1 = H, n1 = 0; long long s1 = ps;
         const float* dh2 = nullptr;
@@ -513,28 +607,30 @@ struct Bwd16 {
         MMQG_TRY(lstm_pointwise_bwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H,
                                          H, dh0, ld0, n0, s0, dh1, ld1, n1, s1, dh2, H, w.dc[l], H, last ? 1 : 0, dg, G, B,
                                          H, st, dr));
-        float* dctx = w.dctx_all + (size_t)t * B * Cd;
         if (fused) {
-          if (l > 0)
-            MMQG_TRY(Tc(dg, G, false, w.wd_cat[l], 2 * H, true, B, 2 * H, G, w.dcat[l], 2 * H).split(kSplitB, pc).run(st));
-          else
-            MMQG_TRY(Tc(dg, G, false, w.wd_cat[0], Cd, true, B, Cd, G, dctx, Cd).run(st));
+          const int Nl = l > 0 ? 2 * H : Cd;
+          MMQG_TRY(Tc(dg, G, false, w.wd_cat[l], Nl, true, B, Nl, G, w.dcat[l], Nl).split(kSplitB, l > 0 ? pc : pc0).run(st));
         } else {
           MMQG_TRY(Tc(dg, G, false, w.wd_cat[l], l > 0 ? 2 * H : Cd, true, B, H, G, w.dh_rec[l], H).split(kSplitB, ps).run(st));
           if (l > 0)
             MMQG_TRY(Tc(dg, G, false, w.wd_cat[l] + H, 2 * H, true, B, H, G, w.dx_above, H).split(kSplitB, ps).run(st));
           else
-            MMQG_TRY(Tc(dg, G, false, w.wd_cat[0] + H, Cd, true, B, C, G, dctx + H, Cd).run(st));
+            MMQG_TRY(Tc(dg, G, false, w.wd_cat[0] + H, Cd, true, B, C, G, w.dctx_all + (size_t)t * B * C, C).run(st));
         }
       }
       float* ds = w.ds_all + (size_t)t * B * Sp;
       as.ds16 = w.ds16 + (size_t)t * B * Sp;
-      MMQG_TRY(attn_bwd(w.attn_all + (size_t)t * B * Sp, ds, Sp, w.dctx_all + (size_t)t * B * (H + C) + H, H + C, w.m_txt,
-                        w.m_aud, w.m_vid, nullptr, nullptr, as, st));
+      // fused steps hand the context gradient over as split-K partials next to d h_rec; the attention
+      // kernel sums them and leaves the sum in dctx_all for the hoisted memory gradient
+      float* dctx = w.dctx_all + (size_t)t * B * C;
+      if (fused) { as.dctx_parts = kSplitB; as.dctx_part_stride = pc0; as.dctx_sum = dctx; as.lddsum = C; }
+      else { as.dctx_parts = 1; as.dctx_sum = nullptr; }
+      MMQG_TRY(attn_bwd(w.attn_all + (size_t)t * B * Sp, ds, Sp, fused ? w.dcat[0] + H : dctx, fused ? Cd : C, w.m_txt, w.m_aud,
+                        w.m_vid, nullptr, nullptr, as, st));
       MMQG_TRY(Tc(as.ds16, Sp, false, w.wa_h, H, true, B, H, Sp, w.dq_h, H).split(kSplitB, ps).run(st));
     }
     // memory gradients feed the encoders' BPTT
-    return attn_dmem(w.attn_all, Sp, w.dctx_all + H, H + C, w.dm_txt, w.dm_vid, d.T_q, as, st);
+    return attn_dmem(w.attn_all, Sp, w.dctx_all, C, w.dm_txt, w.dm_vid, d.T_q, as, st);
   }
 
   // hoisted decoder gradients: LSTM weights/biases, attention Linears, decoder-side embedding rows
@@ -718,7 +814,9 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
   // phase 0: the whole backward with the hoisted products overlapped on an auxiliary stream
   MMQG_TRY(g_aux.init());
   cudaStream_t ax = g_aux.s[AuxStream::NS - 1];
+  mark(6, st);
   MMQG_TRY(b.dec_loop(st));
+  mark(7, st);
   MMQG_CUDA(cudaEventRecord(g_aux.ev[0], st));
   MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[0], 0));
   MMQG_TRY(b.dec_hoisted(ax));
@@ -735,11 +833,25 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
       MMQG_TRY(b.text_hoisted(l, ax));
     }
   }
+  mark(8, st);
   MMQG_CUDA(cudaEventRecord(g_aux.ev[7], ax));
   MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[7], 0));       // join: everything is ordered on `st` again
   MMQG_TRY(b.emb_enc(st, NC > 1));
+  mark(9, st);
   if (ready && ready[2]) MMQG_CUDA(cudaEventRecord(ready[2], st));     // text + embedding group final
   return 0;
 }
 
 }  // namespace mmqg
+
+// Debug hooks for tools/sections.py: switch the section marks on/off; read the elapsed time (ms)
+// from mark 0 to each mark after a synchronised eager step.
+extern "C" void mmqg_debug_sections(int enable) { mmqg::g_sec.on = enable != 0; }
+extern "C" int mmqg_debug_section_times(float* ms_out) {
+  if (!mmqg::g_sec.created) return 1;
+  for (int i = 0; i < 10; ++i) {
+    ms_out[i] = 0.f;
+    if (cudaEventElapsedTime(&ms_out[i], mmqg::g_sec.ev[0], mmqg::g_sec.ev[i]) != cudaSuccess) { cudaGetLastError(); ms_out[i] = -1.f; }
+  }
+  return 0;
+}

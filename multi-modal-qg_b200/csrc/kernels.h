@@ -33,6 +33,9 @@ struct AttnShape {
   void* ds16; int ldds16;       // attn_bwd: d loss / d scores
   // bf16 mode: bf16 copies of the text / video memories (same shapes); read instead of the fp32 ones
   const void* m_txt16; const void* m_vid16;
+  // attn_bwd: dctx may arrive as `dctx_parts` split-K partial sums `dctx_part_stride` floats apart
+  // (0/1 = a single tensor); the summed rows are then also written to dctx_sum (row pitch lddsum)
+  int dctx_parts; long long dctx_part_stride; float* dctx_sum; int lddsum;
 };
 bool attn_fast_ok(const AttnShape& s, const void* M_txt, const void* M_aud, const void* M_vid);
 int attn_fwd_fast(float* scores, int lds, const void* M_txt, const float* M_aud, const void* M_vid, bool mem_bf16, float* ctx,
@@ -55,12 +58,27 @@ struct DropSpec {
   int sid = 0;
   float p = 0.f;
 };
+// Pre-activations handed to the forward cell kernel as split-K partial sums: pre = (gates if
+// add_gates) + bias + sum_k part[k*stride + b*ld + .]; the activated gates still land in `gates`.
+struct PreSpec {
+  const float* part = nullptr;
+  int n_part = 0, ld = 0;
+  long long stride = 0;
+  const float* bias = nullptr;
+  int add_gates = 0;
+};
 int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, void* h_out,
-                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, DropSpec dr = DropSpec());
+                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, DropSpec dr = DropSpec(),
+                            PreSpec ps = PreSpec());
 int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                             const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1,
                             long long s1, const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, void* dg,
                             int lddg, int B, int H, cudaStream_t st, DropSpec dr = DropSpec());
+// one decoder LSTM layer step, GEMM + cell update in one launch (lstm_step_tc.cu)
+bool lstm_step_tc_ok(int H, int ldg, int ldc, int ldh, int ldcp, int ldpre);
+int lstm_step_tc(const void* X, int ldx, int K1, const void* W_in, int ldw1, const void* Hprev, int ldhp, const void* W_hh,
+                 int ldw2, const float* bias, const float* pre, int ldpre, float* acts, int ldg, const float* c_prev, int ldcp,
+                 float* c_out, int ldc, void* h_out, int ldh, int B, int H, DropSpec dr, cudaStream_t st);
 int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
 int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, int sid, unsigned long long base, float p, cudaStream_t st);
 int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, int sid, unsigned long long base,

@@ -49,14 +49,27 @@ __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x))
 
 __global__ void lstm_pointwise_fwd_bf16_kernel(float* __restrict__ gates, int ldg, const float* __restrict__ c_prev,
                                                int ldcp, float* __restrict__ c_out, int ldc, bf16* __restrict__ h_out,
-                                               int ldh, float* __restrict__ h2, int ldh2, int B, int H, DropSpec dr) {
+                                               int ldh, float* __restrict__ h2, int ldh2, int B, int H, DropSpec dr,
+                                               PreSpec ps) {
   pdl_launch_dependents();
   pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, j = idx % H;
   float* g = gates + (size_t)b * ldg;
-  float i = sigm(g[j]), f = sigm(g[H + j]), gg = tanhf(g[2 * H + j]), o = sigm(g[3 * H + j]);
+  float pi, pf, pg, po;
+  if (ps.part) {       // pre-activations arrive as split-K partial sums (+ bias, + what `gates` already holds)
+    pi = pf = pg = po = 0.f;
+    if (ps.add_gates) { pi = g[j]; pf = g[H + j]; pg = g[2 * H + j]; po = g[3 * H + j]; }
+    if (ps.bias) { pi += ps.bias[j]; pf += ps.bias[H + j]; pg += ps.bias[2 * H + j]; po += ps.bias[3 * H + j]; }
+    for (int k = 0; k < ps.n_part; ++k) {
+      const float* q = ps.part + (size_t)k * ps.stride + (size_t)b * ps.ld;
+      pi += q[j]; pf += q[H + j]; pg += q[2 * H + j]; po += q[3 * H + j];
+    }
+  } else {
+    pi = g[j]; pf = g[H + j]; pg = g[2 * H + j]; po = g[3 * H + j];
+  }
+  float i = sigm(pi), f = sigm(pf), gg = tanhf(pg), o = sigm(po);
   float cp = c_prev ? c_prev[(size_t)b * ldcp + j] : 0.f;
   float c = f * cp + i * gg;
   float h = o * tanhf(c);
@@ -244,12 +257,12 @@ int embedding_gather_bf16(const float* emb, const int64_t* idx, void* out, int l
 }
 
 int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, void* h_out,
-                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, DropSpec dr) {
+                            int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, DropSpec dr, PreSpec ps) {
   MMQG_REQUIRE(gates && c_out && h_out && B > 0 && H > 0, "lstm_pointwise_fwd_bf16: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (c_prev ? 10 : 9) + 2.0 * n + (h2 ? 4.0 * n : 0));
   MMQG_CUDA(launch_k(lstm_pointwise_fwd_bf16_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, gates, ldg, c_prev, ldcp, c_out, ldc,
-                     reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H, dr));
+                     reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H, dr, ps));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
