@@ -14,6 +14,7 @@
 namespace mmqg {
 
 static const int kSplitB = 4;
+static const int kSplitW = 8;    // split-K of the text encoder's hoisted dW products (K = T_t*B rows)
 typedef uint16_t b16;   // storage type for bf16 buffers on the host side of this file
 
 struct Carver16 {
@@ -35,6 +36,7 @@ struct Ws16 {
   // the two column blocks as separate K-major operands, the backward step multiplies dG by the
   // whole matrix in one launch (dh_rec and dx side by side).
   b16 *wd_e, *wd_cat[MMQG_MAX_LAYERS], *wa_e, *wa_h, *wo;
+  float* dw_part;                    // split-K partials of a hoisted text weight-gradient product, (kSplitW, 4H, H)
   float* gpart;                      // split-K partials of the decoder's forward step product, (2, B, 4H)
   float* dcat[MMQG_MAX_LAYERS];      // split-K partials of dG_l [W_hh | W_in]: (kSplitB, B, H + I_l)
   b16 *x0, *frames16, *hs_text[MMQG_MAX_LAYERS], *hs_v, *e_dec, *ds16, *ctx16, *hs_dec[MMQG_MAX_LAYERS], *dlogits16;
@@ -114,6 +116,7 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.dx_above = c.take<float>(kSplitB * B * H); w.dq_h = c.take<float>(kSplitB * B * H);
   w.dctx_all = c.take<float>(R * C);
   w.gpart = c.take<float>(2 * B * G);
+  w.dw_part = c.take<float>((size_t)kSplitW * G * (H > Ep ? H : Ep));
   w.dm_txt = c.take<float>(B * d.TM * H); w.dm_vid = c.take<float>(B * d.AM * Hv);
   w.de_dec = c.take<float>(R * d.E);
   w.dh_rec_enc = c.take<float>(kSplitB * B * H); w.dh_rec_vid = c.take<float>(kSplitB * B * Hv);
@@ -288,16 +291,45 @@ static int pack_weights_rest(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w,
 // caller's stream, so the calls stay CUDA-graph capturable).  They let (a) the hoisted
 // weight-gradient products run beside the latency-bound persistent BPTT kernels, which occupy
 // only 64 of the 148 SMs, and (b) consecutive LSTM layers overlap chunk by chunk in time.
+// Priorities: the serial chains (persistent recurrent kernels, decoder step loops) are latency-bound
+// and own the critical path, the hoisted products are throughput work that only has to finish by
+// the end of the step -- so the chain streams (s[0..NS-3] and `chain`, onto which the work of the
+// caller's stream is moved for the duration of a call) get the highest stream priority and the
+// auxiliary streams s[NS-2] (loss head) and s[NS-1] (hoisted products) the lowest: when SMs free up,
+// waiting chain CTAs are placed first.  MMQG_PRIO=0 creates all streams alike.
 struct AuxStream {
   static constexpr int NS = 4, NE = 96;
   cudaStream_t s[NS] = {};
+  cudaStream_t chain = nullptr;
   cudaEvent_t ev[NE] = {};
-  bool ready = false;
+  bool ready = false, prio = false;
   int init() {
     if (ready) return 0;
-    for (auto& x : s) MMQG_CUDA(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
-    for (auto& e : ev) MMQG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const char* e = getenv("MMQG_PRIO");
+    prio = !(e && e[0] == '0');
+    int lo = 0, hi = 0;
+    MMQG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least (numerically largest), hi = greatest
+    for (int i = 0; i < NS; ++i)
+      MMQG_CUDA(cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, prio ? (i >= NS - 2 ? lo : hi) : lo));
+    MMQG_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, hi));
+    for (auto& e2 : ev) MMQG_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
     ready = true;
+    return 0;
+  }
+  // move the caller's stream onto the high-priority chain stream for one call ...
+  int enter(cudaStream_t user, cudaStream_t* st) {
+    MMQG_TRY(init());
+    if (!prio) { *st = user; return 0; }
+    MMQG_CUDA(cudaEventRecord(ev[12], user));
+    MMQG_CUDA(cudaStreamWaitEvent(chain, ev[12], 0));
+    *st = chain;
+    return 0;
+  }
+  // ... and back: everything issued during the call is ordered on the caller's stream again
+  int leave(cudaStream_t user, cudaStream_t st) {
+    if (st == user) return 0;
+    MMQG_CUDA(cudaEventRecord(ev[13], st));
+    MMQG_CUDA(cudaStreamWaitEvent(user, ev[13], 0));
     return 0;
   }
 };
@@ -314,7 +346,7 @@ static int text_chunks(const mmqg_dims& d) {
   static int want = -1;
   if (want < 0) {
     const char* e = getenv("MMQG_CHUNKS");
-    want = e ? atoi(e) : 4;
+    want = e ? atoi(e) : 6;
     if (want < 1) want = 1;
     if (want > kMaxChunks) want = kMaxChunks;
   }
@@ -430,9 +462,22 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
   return 0;
 }
 
+static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                                 size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
+                                 float dropout_p, unsigned long long seed, cudaStream_t st);
+
 int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                        size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
-                       float dropout_p, unsigned long long seed, cudaStream_t st) {
+                       float dropout_p, unsigned long long seed, cudaStream_t user) {
+  cudaStream_t st;
+  MMQG_TRY(g_aux.enter(user, &st));
+  MMQG_TRY(train_forward_bf16_on(d, P, bt, workspace, workspace_bytes, loss_out, want_grads, grads, grad_scale, dropout_p, seed, st));
+  return g_aux.leave(user, st);
+}
+
+static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                                 size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
+                                 float dropout_p, unsigned long long seed, cudaStream_t st) {
   MMQG_TRY(check_dims_bf16(d));
   g_drop_p = dropout_p;
   g_drop_seed = seed;
@@ -491,7 +536,7 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
   int lh_done = 0;      // steps whose loss head has been issued
   PdlScope pdl_scope(pdl_enabled());      // the dependent launches below overlap prologue and tail
   // MMQG_STEP_FUSE: 0 = product + cell kernel, 1 = one fused launch (lstm_step_tc.cu), 2 = split-K product + summing cell kernel
-  static const int step_mode_env = []() { const char* e = getenv("MMQG_STEP_FUSE"); return e ? atoi(e) : 1; }();
+  static const int step_mode_env = []() { const char* e = getenv("MMQG_STEP_FUSE"); return e ? atoi(e) : 2; }();
   const int step_mode = step_mode_env;
   const bool step_fused = step_mode == 1 && lstm_step_tc_ok(H, G, H, H, H, G);
   for (int t = 0; t < d.T_q; ++t) {
@@ -725,6 +770,19 @@ struct Bwd16 {
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
     const b16* dG = w.dg_text[l];
     const b16* X = l == 0 ? w.x0 : (g_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);
+    // K = T_t*B is long and the output small (64 tiles): split K so that no CTA lives longer than a
+    // few microseconds -- these products share the SMs with the latency-bound BPTT kernels, which
+    // can only start once 64 SMs are free -- and reduce the partial tiles afterwards.
+    static const bool splitw_env = []() { const char* e = getenv("MMQG_SPLITW"); return !(e && e[0] == '0'); }();
+    const bool splitw = splitw_env && (long long)d.T_t * B >= 64ll * 64 * kSplitW;
+    if (splitw) {
+      MMQG_TRY(Tc(dG, G, true, X, Ip, true, G, I, d.T_t * B, w.dw_part, I).split(kSplitW, (long long)G * I).run(st));
+      MMQG_TRY(reduce_partials(w.dw_part, kSplitW, (long long)G * I, Gd.text_w_ih[l], I, G, I, st));
+      MMQG_TRY(Tc(dG + (size_t)B * G, G, true, w.hs_text[l] + (size_t)B * H, H, true, G, H, (d.T_t - 1) * B, w.dw_part, H)
+                   .split(kSplitW, (long long)G * H).run(st));
+      MMQG_TRY(reduce_partials(w.dw_part, kSplitW, (long long)G * H, Gd.text_w_hh[l], H, G, H, st));
+      return colsum_bf16(dG, G, Gd.text_b_ih[l], Gd.text_b_hh[l], d.T_t * B, G, 0.f, st);
+    }
     MMQG_TRY(Tc(dG, G, true, X, Ip, true, G, I, d.T_t * B, Gd.text_w_ih[l], I).run(st));
     if (d.T_t > 1)
       MMQG_TRY(Tc(dG + (size_t)B * G, G, true, w.hs_text[l] + (size_t)B * H, H, true, G, H, (d.T_t - 1) * B, Gd.text_w_hh[l], H).run(st));
@@ -779,9 +837,22 @@ struct Bwd16 {
   }
 };
 
+static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                                  size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
+                                  cudaStream_t st, cudaEvent_t const* ready);
+
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                         size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
-                        cudaStream_t st, cudaEvent_t const* ready) {
+                        cudaStream_t user, cudaEvent_t const* ready) {
+  cudaStream_t st;
+  MMQG_TRY(g_aux.enter(user, &st));
+  MMQG_TRY(train_backward_bf16_on(d, P, bt, workspace, workspace_bytes, Gd, phase, dropout_p, seed, st, ready));
+  return g_aux.leave(user, st);
+}
+
+static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
+                                  size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
+                                  cudaStream_t st, cudaEvent_t const* ready) {
   MMQG_TRY(check_dims_bf16(d));
   g_drop_p = dropout_p;
   g_drop_seed = seed;

@@ -83,6 +83,7 @@ int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, f
 int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, int sid, unsigned long long base, float p, cudaStream_t st);
 int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, int sid, unsigned long long base,
                       float p, cudaStream_t st);
+int reduce_partials(const float* part, int n_part, long long stride, float* out, int ldo, long long rows, int N, cudaStream_t st);
 int dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, cudaStream_t st);
 // persistent recurrent-cell kernels (lstm_persist.cu)
 bool lstm_persist_ok(int B, int H);

@@ -236,6 +236,39 @@ int dropout_mask(float* out, long long n, unsigned long long seed, int sid, floa
   return 0;
 }
 
+// out(r, c) = sum_k part[k*stride + r*N + c]   (split-K partial tiles -> the gradient tensor)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int n_part, long long stride, float* __restrict__ out,
+                                       int ldo, long long rows, int N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 (or tail) per thread
+  const int n4 = (N + 3) / 4;
+  if (i >= rows * n4) return;
+  const long long r = i / n4;
+  const int c = (int)(i % n4) * 4;
+  if (c + 4 <= N && (N & 3) == 0 && (ldo & 3) == 0) {
+    float4 a = *reinterpret_cast<const float4*>(part + r * N + c);
+    for (int k = 1; k < n_part; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(part + (size_t)k * stride + r * N + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(out + r * ldo + c) = a;
+  } else {
+    for (int j = c; j < N && j < c + 4; ++j) {
+      float a = 0.f;
+      for (int k = 0; k < n_part; ++k) a += part[(size_t)k * stride + r * N + j];
+      out[r * ldo + j] = a;
+    }
+  }
+}
+int reduce_partials(const float* part, int n_part, long long stride, float* out, int ldo, long long rows, int N, cudaStream_t st) {
+  MMQG_REQUIRE(part && out && n_part > 0 && rows > 0 && N > 0, "reduce_partials: bad args");
+  MMQG_REQUIRE((N & 3) != 0 || ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 || (ldo & 3) != 0,
+               "reduce_partials: unaligned pointers");
+  const long long n = rows * ((N + 3) / 4);
+  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n_part, stride, out, ldo, rows, N);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 int cvt_f32_bf16_2d(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
                     int cols_dst, cudaStream_t st) {
