@@ -210,22 +210,34 @@ def main():
     eager_step(dbatch)
     torch.cuda.synchronize()
     launches_per_step = launch_count() - n_before
-    if use_graph:
+
+    def make_step(b):
+        """A callable running one step on device batch b (a graph is bound to the buffers it captured)."""
+        if not use_graph:
+            return lambda: eager_step(b)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            eager_step(dbatch)
+            eager_step(b)
         torch.cuda.current_stream().wait_stream(side)
-        graph_holder.append(torch.cuda.CUDAGraph())
-        with torch.cuda.graph(graph_holder[0]):
-            eager_step(dbatch)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eager_step(b)
+        idx = len(graph_holder)
+        graph_holder.append(g)
+        del g                                               # teardown() must be able to drop the last reference
+
+        def replay():
+            graph_holder[idx].replay()
+            return eng.loss
+        return replay
+
+    step_resident = make_step(dbatch)
 
     def one_step(b):
         """b must be dbatch (the graph is bound to its buffers)."""
-        if graph_holder:
-            graph_holder[0].replay()
-            return eng.loss
-        return eager_step(b)
+        return step_resident()
 
     def barrier():
         if world > 1:
@@ -254,16 +266,23 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed region 2: end to end from pinned host buffers ---------------------------
+    # Every step's inputs are copied host -> device from pinned memory and its loss is read back on
+    # the host; the copy of step i+1 runs on a copy stream under the compute of step i (HostFeed).
+    from mmqg.engine import HostFeed
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
-    dst = dbatch                                             # the step (and its graph) reads these buffers
+    feed = HostFeed(eng, host, make_step)
+    for _ in range(2):                                       # warm both buffers / graphs
+        feed.prefetch(pinned)
+        feed.step()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     host_loss = 0.0
-    for _ in range(args.steps):
-        for k in dst:
-            dst[k].copy_(pinned[k], non_blocking=True)
-        loss = one_step(dst)
+    feed.prefetch(pinned)                                    # inputs of the first timed step
+    for i in range(args.steps):
+        loss = feed.step()
+        if i + 1 < args.steps:
+            feed.prefetch(pinned)                            # inputs of step i+1, under step i
         host_loss = float(loss.item())                      # device -> host read of the step's result
     e3.record()
     barrier()

@@ -178,3 +178,48 @@ def grad_group(name: str) -> int:
 
 def launch_count():
     return int(_cabi.lib().mmqg_launch_count())
+
+
+class HostFeed:
+    """Feeds train steps from HOST batches (pinned memory): two device batch buffers, the
+    host->device copy of step i+1 runs on a copy stream under the compute of step i.
+
+        feed = HostFeed(engine, example_batch, make_step)    # make_step(device_batch) -> callable() -> loss
+        feed.prefetch(host_batch_0)
+        for i in range(n):
+            loss = feed.step()                 # step i on the buffer prefetched for it
+            feed.prefetch(host_batch_i_plus_1) # enqueued behind the step that last read that buffer
+            value = float(loss)                # device->host read of step i's result
+
+    make_step is called once per buffer (a CUDA graph is bound to the buffers it was captured on)."""
+
+    def __init__(self, engine, example_batch, make_step):
+        self.bufs = [engine.to_device(example_batch) for _ in range(2)]
+        self.steps = [make_step(b) for b in self.bufs]
+        self.copy_stream = torch.cuda.Stream()
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.n_prefetched = 0
+        self.n_stepped = 0
+
+    def prefetch(self, host_batch):
+        k = self.n_prefetched % 2
+        assert self.n_prefetched - self.n_stepped < 2, "both buffers hold batches that have not been consumed"
+        cs = self.copy_stream
+        cs.wait_event(self.done[k])            # the step that last read buffer k (no-op before its first use)
+        with torch.cuda.stream(cs):
+            for name, dst in self.bufs[k].items():
+                dst.copy_(host_batch[name], non_blocking=True)
+            self.copied[k].record(cs)
+        self.n_prefetched += 1
+
+    def step(self):
+        assert self.n_stepped < self.n_prefetched, "prefetch() the batch first"
+        k = self.n_stepped % 2
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.copied[k])
+        loss = self.steps[k]()
+        self.done[k].record(cur)
+        self.n_stepped += 1
+        return loss
+

@@ -112,3 +112,26 @@ def test_bf16_rejects_unaligned_dims(eng_mod):
     d = Dims(B=2, T_t=3, T_v=2, T_q=2, V=11, E=10, H=12, L=1, H_a=6, H_v=12, F_v=10, TM=4, AM=3)
     with pytest.raises(_cabi.MmqgError):
         eng_mod.TrainEngine(d, make_params(d), mode="bf16")
+
+
+def test_host_feed_matches_direct_steps(eng_mod):
+    """HostFeed (double-buffered host->device prefetch under the previous step) must hand every
+    step exactly the batch it was given: losses equal those of direct steps on the same batches."""
+    d = Dims(B=16, T_t=9, T_v=3, T_q=4, V=500, E=52, H=64, L=2, H_a=24, H_v=64, F_v=40, TM=12, AM=5)
+    params = make_params(d, seed=61)
+    batches = [make_batch(d, seed=70 + i) for i in range(5)]
+    eng = eng_mod.TrainEngine(d, params, mode="bf16")
+    want = []
+    for b in batches:
+        want.append(float(eng.step(eng.to_device(b))))
+    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in batches]
+    feed = eng_mod.HostFeed(eng, batches[0], lambda dev_batch: (lambda: eng.step(dev_batch)))
+    got = []
+    feed.prefetch(pinned[0])
+    for i in range(len(batches)):
+        loss = feed.step()
+        if i + 1 < len(batches):
+            feed.prefetch(pinned[i + 1])
+        got.append(float(loss.item()))
+    assert got == pytest.approx(want, rel=1e-6), (got, want)
+    assert len(set(round(x, 4) for x in got)) == len(got)      # the batches really differ
