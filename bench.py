@@ -149,6 +149,19 @@ def run_reference(args, d, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def committed_traffic(kernel_class, launches_per_step):
+    """DRAM bytes per launch of the probed kernel class from the committed ncu --set full capture
+    (profiles/r01_traffic.json), or None when no capture covers that class."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("kernel_class") == kernel_class and launches_per_step > 0:
+            return t["bytes_per_step"] / launches_per_step
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def workload_config(d, args, world):
     return {"workload": f"BASELINE.json configs[{args.config - 1}]: teacher-forced train step fwd+bwd, "
                         f"B={d.B}/GPU T_t={d.T_t} T_v={d.T_v}x{d.F_v} T_a={d.T_v}x{d.H_a} T_q={d.T_q} V={d.V} "
@@ -313,7 +326,7 @@ def main():
             if args.probe in (1, 2, 7):
                 ach = fl.value / (tms.value * 1e-3) / 1e12
                 roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                        "frac": ach / pk["tflops"], "traffic": None}
+                        "frac": ach / pk["tflops"], "traffic": committed_traffic(args.probe, n.value / 2)}
             else:
                 ach = by.value / (tms.value * 1e-3) / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
