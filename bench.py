@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--dropout", type=float, default=None,
                     help="inter-layer LSTM dropout (config.py text_lstm_dropout = dec_lstm_dropout); default 0.2 in "
                          "bf16 mode (the reference's train-mode value), 0 in the fp32 parity mode")
+    ap.add_argument("--adam", action="store_true",
+                    help="also run the fused Adam step (SURVEY section 8 f1) inside every step; off by default: the "
+                         "metric is forward + backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--probe", type=int, default=None, help="kernel class the roofline probe times (see mmqg.h)")
@@ -167,7 +170,8 @@ def workload_config(d, args, world):
                         f"B={d.B}/GPU T_t={d.T_t} T_v={d.T_v}x{d.F_v} T_a={d.T_v}x{d.H_a} T_q={d.T_q} V={d.V} "
                         f"E={d.E} H={d.H} L={d.L} TM={d.TM} AM={d.AM}",
             "global_batch": d.B * world, "per_gpu_batch": d.B, "parallelism": f"dp{world}",
-            "dropout_p": args.dropout, "mode": args.mode, "cuda_graph": not args.no_graph,
+            "dropout_p": args.dropout, "optimizer": "fused adam" if args.adam else "none (metric is fwd+bwd)",
+            "mode": args.mode, "cuda_graph": not args.no_graph,
             "l2": "working set (2 GB activations + 111 MB weights per step) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -207,12 +211,17 @@ def main():
     reducer = GradReducer(eng, world) if world > 1 else None
     gscale = 1.0 / world
 
+    if args.adam:
+        eng.adam_init()
+
     def eager_step(b):
         if reducer:
             loss = eng.step_dp(b, reducer, gscale)     # all-reduce per gradient group behind its ready event
             reducer.finish()
         else:
             loss = eng.step(b)
+        if args.adam:
+            eng.adam_step(lr=1e-4)
         return loss
 
     # One step is ~550 kernel launches; replaying them as a CUDA graph takes the host launch path out

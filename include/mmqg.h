@@ -151,6 +151,16 @@ int mmqg_greedy_decode(const mmqg_dims* d, const mmqg_tensors* params, const mmq
                        void* workspace, size_t workspace_bytes, int64_t* tokens_out, int max_len,
                        int mode, void* stream);
 
+/* Fused multi-tensor Adam over flat fp32 buffers of identical layout (reference train.py:179-181
+ * with the three torch.optim.Adam(lr=1e-4) of train.py:265-267; no weight decay, no amsgrad).
+ * Elements [rep_lo, rep_hi) receive the update twice -- the shared embedding is registered with
+ * two of the reference's optimisers (train.py:236,245,255).  `state`: 3 device floats, zeroed once
+ * by the caller: the step count (as int bits) and the two bias-correction scalars the call derives
+ * from it on the device, so a captured CUDA graph replays correctly.  n must be a multiple of 4. */
+int mmqg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                   long long rep_lo, long long rep_hi, float lr, float beta1, float beta2, float eps,
+                   float* state, void* stream);
+
 /* The multiplicative inter-layer dropout mask (0 or 1/(1-p)) the train path applies for a given
  * seed: stream `sid` = 10+l for the output of text-encoder layer l, 20+l for decoder layer l;
  * element index (t*B + b)*H + j.  For tests (the mask is counter-based, not ATen's Philox). */

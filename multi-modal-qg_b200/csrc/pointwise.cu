@@ -371,3 +371,67 @@ int mmqg_colsum(const float* X, int ldx, float* out, int M, int N, float beta, v
 }
 
 }  // extern "C"
+
+// ---- fused multi-tensor Adam (reference train.py:179-181, 265-267) -------------
+// One launch updates every parameter of the model: parameters, gradients and both moments live in
+// flat fp32 buffers with identical layout.  torch.optim.Adam semantics (no weight decay, no
+// amsgrad): m += (1-b1)(g-m); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+// Elements in [rep_lo, rep_hi) are stepped TWICE: the reference registers the shared embedding
+// with two optimisers (train.py:236,245,255,266-267), whose moments are
+// identical by construction, so the second update equals the first.
+// The step count lives in device memory (state[0]) and is advanced by the prep kernel, so a
+// captured CUDA graph replays correct bias corrections.  HBM-bound: 28 bytes per element.
+namespace mmqg {
+__global__ void adam_prep_kernel(float* state, float lr, float beta1, float beta2) {
+  int t = __float_as_int(state[0]) + 1;
+  state[0] = __int_as_float(t);
+  const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+  state[1] = (float)((double)lr / bc1);        // step size
+  state[2] = (float)sqrt(bc2);                 // sqrt of the second bias correction
+}
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, long long n, long long rep_lo, long long rep_hi,
+                                                        const float* __restrict__ state, float beta1, float beta2, float eps) {
+  const float step_size = state[1], bc2_sqrt = state[2];
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] = mm[k] + (1.0f - beta1) * (gg[k] - mm[k]);
+      vv[k] = beta2 * vv[k] + (1.0f - beta2) * gg[k] * gg[k];
+      const float upd = step_size * (mm[k] / (sqrtf(vv[k]) / bc2_sqrt + eps));
+      pp[k] -= upd;
+      const long long e = 4 * i + k;
+      if (e >= rep_lo && e < rep_hi) pp[k] -= upd;
+    }
+    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+  }
+}
+}  // namespace mmqg
+
+extern "C" int mmqg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                              long long rep_lo, long long rep_hi, float lr, float beta1, float beta2, float eps,
+                              float* state, void* stream) {
+  using namespace mmqg;
+  MMQG_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && n > 0, "adam_step: null pointer");
+  MMQG_REQUIRE(n % 4 == 0, "adam_step: n=%lld must be a multiple of 4 (pad the flat buffers)", n);
+  MMQG_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+                 reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, "adam_step: buffers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  adam_prep_kernel<<<1, 1, 0, st>>>(state, lr, beta1, beta2);
+  MMQG_LAUNCH_CHECK();
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;      // grid-stride: 16 resident CTAs of 256 threads on each of the 148 SMs
+  MMQG_PROBE(KC_OTHER, 0, 28.0 * n);
+  adam_step_kernel<<<(unsigned)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, rep_lo, rep_hi, state, beta1, beta2, eps);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+

@@ -69,6 +69,7 @@ SYMBOLS = {
     "mmqg_greedy_workspace_bytes": (_sz, [_P(MmqgDims), _i, _i]),
     "mmqg_greedy_decode": (_i, [_P(MmqgDims), _P(MmqgTensors), _P(MmqgBatch), _fp, _sz, _fp, _i, _i, _fp]),
     "mmqg_dropout_mask": (_i, [_fp, _ll, _ull, _i, _f, _fp]),
+    "mmqg_adam_step": (_i, [_fp, _fp, _fp, _fp, _ll, _ll, _ll, _f, _f, _f, _f, _fp, _fp]),
     "mmqg_gemm_f32": (_i, [_P(MmqgGemmArgs), _fp]),
     "mmqg_gemm_bf16": (_i, [_P(MmqgGemmBf16Args), _fp]),
     "mmqg_embedding_gather": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp]),

@@ -31,25 +31,31 @@ class TrainEngine:
         self.mode = {"fp32": _cabi.MODE_FP32, "bf16": _cabi.MODE_BF16}[mode]
         self.dropout_p = float(dropout_p)
         shapes = param_shapes(dims)
-        self.params, self.grads = {}, {}
         for name, shape in shapes.items():
-            t = params[name]
-            if tuple(t.shape) != tuple(shape):
-                raise _cabi.MmqgError(f"{name}: shape {tuple(t.shape)} != {shape}")
-            self.params[name] = t.detach().to(self.device, torch.float32).contiguous()
-        # Gradients live in four flat buckets, one per readiness group,
-        # so the data-parallel all-reduce is one NCCL call per group; self.grads are views.
-        self.grad_buckets = []
+            if tuple(params[name].shape) != tuple(shape):
+                raise _cabi.MmqgError(f"{name}: shape {tuple(params[name].shape)} != {shape}")
+        # Parameters and gradients live in ONE flat fp32 buffer each with identical layout, cut into
+        # four buckets, one per gradient readiness group: the data-parallel
+        # all-reduce is one NCCL call per bucket and the fused Adam is one launch over everything;
+        # self.params / self.grads are views with the reference's names and shapes.
+        self.offsets, total, bucket_range = {}, 0, []
         for g in range(4):
-            names = [n for n in shapes if grad_group(n) == g]
-            offs, total = {}, 0
-            for n in names:
-                offs[n] = total
-                total += (self.params[n].numel() + 63) // 64 * 64
-            flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-            for n in names:
-                self.grads[n] = flat[offs[n]:offs[n] + self.params[n].numel()].view(shapes[n])
-            self.grad_buckets.append(flat)
+            lo = total
+            for n in shapes:
+                if grad_group(n) == g:
+                    self.offsets[n] = total
+                    total += (int(torch.Size(shapes[n]).numel()) + 63) // 64 * 64
+            bucket_range.append((lo, total))
+        self.flat_params = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.flat_grads = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.params, self.grads = {}, {}
+        for n, shape in shapes.items():
+            o, k = self.offsets[n], int(torch.Size(shape).numel())
+            self.params[n] = self.flat_params[o:o + k].view(shape)
+            self.params[n].copy_(params[n].detach().to(self.device, torch.float32))
+            self.grads[n] = self.flat_grads[o:o + k].view(shape)
+        self.grad_buckets = [self.flat_grads[lo:hi] for lo, hi in bucket_range]
+        self._adam = None
         self._cd = _cabi.c_dims(dims)
         self._cp = _cabi.c_tensors(self.params, dims.L)
         self._cg = _cabi.c_tensors(self.grads, dims.L)
@@ -131,6 +137,28 @@ class TrainEngine:
         if self.dropout_p > 0 and self.auto_seed:
             self.seed += 1                   # fresh masks next step (a captured CUDA graph replays one seed)
         return loss
+
+    # -- optimiser -------------------------------------------------
+    def adam_init(self):
+        """Allocate the optimiser state (zero moments, step count 0).  Call before capturing a CUDA
+        graph that contains adam_step(): allocations and their zero-fill must not be captured."""
+        if self._adam is None:
+            z = torch.zeros_like(self.flat_params)
+            self._adam = {"m": z, "v": z.clone(), "state": torch.zeros(4, dtype=torch.float32, device=self.device)}
+        return self._adam
+
+    def adam_step(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        """The reference's three torch.optim.Adam(lr=1e-4) steps (train.py:179-181, 265-267) as
+        one fused launch over the flat parameter buffer; the shared embedding, registered with two
+        of those optimisers, is stepped twice.  Uses self.grads as they are (after the
+        all-reduce in data-parallel runs).  CUDA-graph capturable (step count on the device)."""
+        a = self.adam_init()
+        lo = self.offsets["emb.weight"]
+        hi = lo + self.params["emb.weight"].numel()
+        _cabi.check(self.lib.mmqg_adam_step(
+            self.flat_params.data_ptr(), self.flat_grads.data_ptr(), a["m"].data_ptr(), a["v"].data_ptr(),
+            self.flat_params.numel(), lo, hi, float(lr), float(betas[0]), float(betas[1]), float(eps),
+            a["state"].data_ptr(), _stream_ptr()))
 
     def dropout_masks(self, seed=None):
         """The multiplicative inter-layer dropout masks (0 or 1/(1-p)) a step with `seed` applies:
