@@ -28,6 +28,7 @@ struct Carver16 {
 };
 
 struct Ws16 {
+  unsigned long long* seed_ctr;       // FIRST 8 bytes of the workspace: number of forward calls (dropout call counter), zeroed by the caller
   int64_t *idx_ctx, *idx_dec, *tgt_tm, *idx_cur;
   float *bsum_text[MMQG_MAX_LAYERS], *bsum_dec[MMQG_MAX_LAYERS], *bsum_vid, *attn_b_cat, *attn_dw_cat, *attn_db_cat;
   b16 *wt_ih[MMQG_MAX_LAYERS], *wt_hh[MMQG_MAX_LAYERS], *wv_ih, *wv_hh;
@@ -67,6 +68,7 @@ static int vocab_chunk_rows16(int R, int V) {
 static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   Ws16 w{};
   Carver16 c{reinterpret_cast<char*>(base), 0};
+  w.seed_ctr = c.take<unsigned long long>(1);
   const size_t B = d.B, H = d.H, G = 4 * (size_t)d.H, Hv = d.H_v, Gv = 4 * (size_t)d.H_v;
   const int S = d.TM + 2 * d.AM;
   w.Sp = (S + 7) / 8 * 8;
@@ -195,6 +197,7 @@ static void mark(int i, cudaStream_t st) {
 // inter-layer dropout of the current call (set at the entry points; 0 = off)
 static thread_local float g_drop_p = 0.f;
 static thread_local unsigned long long g_drop_seed = 0;
+static thread_local const unsigned long long* g_drop_ctr = nullptr;
 static const int kSidText = 10, kSidDec = 20;
 
 // The encoders run on the persistent recurrent kernels when the shape allows it (lstm_persist.cu);
@@ -420,7 +423,7 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
                                       w.flags_t[l], nT, B, H, c > 0 ? 1 : 0, s));
         if (g_drop_p > 0.f && l + 1 < d.L)
           MMQG_TRY(dropout_bf16(w.hs_text[l] + (size_t)(t0 + 1) * B * H, w.xdrop_text[l] + (size_t)t0 * B * H, (long long)nT * B * H,
-                                g_drop_seed, kSidText + l, (unsigned long long)t0 * B * H, g_drop_p, s));
+                                g_drop_seed, g_drop_ctr, kSidText + l, (unsigned long long)t0 * B * H, g_drop_p, s));
         MMQG_CUDA(cudaEventRecord(ev_fwd(l, c), s));
       }
     }
@@ -429,7 +432,7 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
   for (int l = 0; l < d.L; ++l) {
     if (l > 0 && g_drop_p > 0.f)
       MMQG_TRY(dropout_bf16(w.hs_text[l - 1] + (size_t)B * H, w.xdrop_text[l - 1], (long long)d.T_t * B * H, g_drop_seed,
-                            kSidText + l - 1, 0, g_drop_p, st));
+                            g_drop_ctr, kSidText + l - 1, 0, g_drop_p, st));
     const b16* X = l == 0 ? w.x0 : (g_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);
     const int Ip = l == 0 ? w.Ep : H;
     MMQG_TRY(Tc(X, Ip, false, w.wt_ih[l], Ip, false, d.T_t * B, G, Ip, w.acts_text[l], G).bias(w.bsum_text[l]).run(st));
@@ -485,7 +488,9 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, R = d.T_q * B, Sp = w.Sp, Ep = w.Ep;
 
+  g_drop_ctr = w.seed_ctr;
   mark(0, st);
+  if (dropout_p > 0.f) MMQG_TRY(bump_counter(w.seed_ctr, st));     // this call's masks: seed + (calls so far)
   MMQG_TRY(g_aux.init());
   cudaStream_t ax = g_aux.s[AuxStream::NS - 1], lh = g_aux.s[AuxStream::NS - 2];
   MMQG_TRY(build_indices(bt.context, bt.target, w.idx_ctx, w.idx_dec, w.tgt_tm, B, d.T_t, d.T_q, st));
@@ -554,7 +559,7 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
       const int Kin = l == 0 ? C : H, Nl = H + Kin;      // wd_cat[l] = [W_hh | W_in], row pitch Nl
       DropSpec dr;
       if (g_drop_p > 0.f && l + 1 < d.L) {
-        dr.out = w.hdrop_dec[l] + (size_t)t * B * H; dr.ld = H; dr.seed = g_drop_seed; dr.sid = kSidDec + l;
+        dr.out = w.hdrop_dec[l] + (size_t)t * B * H; dr.ld = H; dr.seed = g_drop_seed; dr.ctr = g_drop_ctr; dr.sid = kSidDec + l;
         dr.base = (unsigned long long)t * B * H; dr.p = g_drop_p;
       }
       float* c_prev = w.cs_dec[l] + (size_t)t * B * H;
@@ -646,7 +651,7 @@ struct Bwd16 {
           if (fused) { dh1 = w.dcat[l + 1] + H; ld1 = 2 * H; s1 = pc; }
           else dh1 = w.dx_above;
           if (g_drop_p > 0.f) {   // it is d/d(dropped h_l): back through the mask of layer l's output
-            dr.seed = g_drop_seed; dr.sid = kSidDec + l; dr.base = (unsigned long long)t * B * H; dr.p = g_drop_p;
+            dr.seed = g_drop_seed; dr.ctr = g_drop_ctr; dr.sid = kSidDec + l; dr.base = (unsigned long long)t * B * H; dr.p = g_drop_p;
           }
         }
         MMQG_TRY(lstm_pointwise_bwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H,
@@ -739,7 +744,7 @@ struct Bwd16 {
   int text_bptt(int l, cudaStream_t st) {
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
     if (g_drop_p > 0.f && l < L - 1)   // dx_text holds d/d(dropped h_l): back through the mask
-      MMQG_TRY(dropout_scale_f32(w.dx_text, 1, 0, (long long)d.T_t * B * H, g_drop_seed, kSidText + l, 0, g_drop_p, st));
+      MMQG_TRY(dropout_scale_f32(w.dx_text, 1, 0, (long long)d.T_t * B * H, g_drop_seed, g_drop_ctr, kSidText + l, 0, g_drop_p, st));
     if (persist_text(d)) {
       // d loss / d h_final = the decoder's gradient w.r.t. its initial state (train.py:169) plus,
       // for the top layer, the step-0 attention query; d loss / d c_final sits in dc[l].
@@ -808,7 +813,7 @@ struct Bwd16 {
         if (l < L - 1) {
           MMQG_CUDA(cudaStreamWaitEvent(s, ev_bwd(l + 1, c), 0));
           if (g_drop_p > 0.f)
-            MMQG_TRY(dropout_scale_f32(w.dx_text + (size_t)t0 * B * H, 1, 0, (long long)nT * B * H, g_drop_seed, kSidText + l,
+            MMQG_TRY(dropout_scale_f32(w.dx_text + (size_t)t0 * B * H, 1, 0, (long long)nT * B * H, g_drop_seed, g_drop_ctr, kSidText + l,
                                        (unsigned long long)t0 * B * H, g_drop_p, s));
         }
         if (tail)   // d loss / d h_final of this layer (decoder initial state, + step-0 attention query on top)
@@ -858,6 +863,7 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   g_drop_seed = seed;
   Ws16 w = carve16(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
+  g_drop_ctr = w.seed_ctr;      // unchanged since the forward of this step: the same masks
   Bwd16 b(d, P, bt, w, Gd);
   if (phase == 1) {
     MMQG_TRY(b.dec_loop(st));

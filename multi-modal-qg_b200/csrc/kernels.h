@@ -55,6 +55,7 @@ struct DropSpec {
   void* out = nullptr;
   int ld = 0;
   unsigned long long seed = 0, base = 0;
+  const unsigned long long* ctr = nullptr;   // device call counter added to seed (fresh masks per step, also under graph replay)
   int sid = 0;
   float p = 0.f;
 };
@@ -80,8 +81,10 @@ int lstm_step_tc(const void* X, int ldx, int K1, const void* W_in, int ldw1, con
                  int ldw2, const float* bias, const float* pre, int ldpre, float* acts, int ldg, const float* c_prev, int ldcp,
                  float* c_out, int ldc, void* h_out, int ldh, int B, int H, DropSpec dr, cudaStream_t st);
 int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
-int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, int sid, unsigned long long base, float p, cudaStream_t st);
-int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, int sid, unsigned long long base,
+int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, const unsigned long long* ctr, int sid,
+                 unsigned long long base, float p, cudaStream_t st);
+int bump_counter(unsigned long long* ctr, cudaStream_t st);
+int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, const unsigned long long* ctr, int sid, unsigned long long base,
                       float p, cudaStream_t st);
 int reduce_partials(const float* part, int n_part, long long stride, float* out, int ldo, long long rows, int N, cudaStream_t st);
 int dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, cudaStream_t st);

@@ -182,11 +182,12 @@ lstm_step_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       *reinterpret_cast<uint4*>(p.h_out + (size_t)r * p.ldh + u) = *reinterpret_cast<const uint4*>(hb);
       if (p.dr.out) {
         const float inv_keep = 1.0f / (1.0f - p.dr.p);
+        const unsigned long long sd = p.dr.seed + (p.dr.ctr ? *p.dr.ctr : 0ull);
         const unsigned long long base = p.dr.base + (unsigned long long)r * p.H + u;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          hb[j] = __floats2bfloat162_rn(hn[2 * j] * drop_scale(p.dr.seed, p.dr.sid, base + 2 * j, p.dr.p, inv_keep),
-                                        hn[2 * j + 1] * drop_scale(p.dr.seed, p.dr.sid, base + 2 * j + 1, p.dr.p, inv_keep));
+          hb[j] = __floats2bfloat162_rn(hn[2 * j] * drop_scale(sd, p.dr.sid, base + 2 * j, p.dr.p, inv_keep),
+                                        hn[2 * j + 1] * drop_scale(sd, p.dr.sid, base + 2 * j + 1, p.dr.p, inv_keep));
         *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.dr.out) + (size_t)r * p.dr.ld + u) = *reinterpret_cast<const uint4*>(hb);
       }
     }

@@ -79,7 +79,7 @@ __global__ void lstm_pointwise_fwd_bf16_kernel(float* __restrict__ gates, int ld
   if (h2) h2[(size_t)b * ldh2 + j] = h;
   if (dr.out)   // dropped copy: the input of the next layer
     reinterpret_cast<bf16*>(dr.out)[(size_t)b * dr.ld + j] =
-        __float2bfloat16_rn(h * drop_scale(dr.seed, dr.sid, dr.base + (unsigned long long)idx, dr.p, 1.0f / (1.0f - dr.p)));
+        __float2bfloat16_rn(h * drop_scale(dr.seed + (dr.ctr ? *dr.ctr : 0ull), dr.sid, dr.base + (unsigned long long)idx, dr.p, 1.0f / (1.0f - dr.p)));
 }
 
 __global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, int ldg, const float* __restrict__ c_prev,
@@ -99,7 +99,7 @@ __global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, i
   if (dh1) {   // gradient from the layer above, through this layer's dropout mask when dr.p > 0
     float d1 = 0.f;
     for (int s = 0; s < n1; ++s) d1 += dh1[(size_t)s * s1 + (size_t)b * ldh1 + j];
-    if (dr.p > 0.f) d1 *= drop_scale(dr.seed, dr.sid, dr.base + (unsigned long long)idx, dr.p, 1.0f / (1.0f - dr.p));
+    if (dr.p > 0.f) d1 *= drop_scale(dr.seed + (dr.ctr ? *dr.ctr : 0ull), dr.sid, dr.base + (unsigned long long)idx, dr.p, 1.0f / (1.0f - dr.p));
     dh += d1;
   }
   if (dh2) dh += dh2[(size_t)b * ldh2 + j];
@@ -195,18 +195,27 @@ __global__ void __launch_bounds__(256) nll_rows_bf16_kernel(const float* __restr
   }
 }
 
-__global__ void dropout_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n, unsigned long long seed, int sid,
+__global__ void bump_counter_kernel(unsigned long long* ctr) { *ctr += 1ull; }
+int bump_counter(unsigned long long* ctr, cudaStream_t st) {
+  bump_counter_kernel<<<1, 1, 0, st>>>(ctr);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void dropout_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n, unsigned long long seed,
+                                    const unsigned long long* __restrict__ ctr, int sid,
                                     unsigned long long base, float p, float inv_keep) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * drop_scale(seed, sid, base + i, p, inv_keep));
+  if (i < n) y[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * drop_scale(seed + (ctr ? *ctr : 0ull), sid, base + i, p, inv_keep));
 }
 
 // x[k*stride + i] *= mask(i) for k < n_part (gradient w.r.t. a dropped tensor, possibly split-K partials)
 __global__ void dropout_scale_f32_kernel(float* __restrict__ x, int n_part, long long stride, long long n, unsigned long long seed,
+                                         const unsigned long long* __restrict__ ctr,
                                          int sid, unsigned long long base, float p, float inv_keep) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float m = drop_scale(seed, sid, base + i, p, inv_keep);
+  const float m = drop_scale(seed + (ctr ? *ctr : 0ull), sid, base + i, p, inv_keep);
   for (int k = 0; k < n_part; ++k) x[(size_t)k * stride + i] *= m;
 }
 
@@ -215,17 +224,18 @@ __global__ void dropout_mask_kernel(float* __restrict__ out, long long n, unsign
   if (i < n) out[i] = drop_scale(seed, sid, i, p, inv_keep);
 }
 
-int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, int sid, unsigned long long base, float p, cudaStream_t st) {
+int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, const unsigned long long* ctr, int sid,
+                 unsigned long long base, float p, cudaStream_t st) {
   MMQG_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout_bf16: bad args");
-  dropout_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), n, seed,
+  dropout_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), n, seed, ctr,
                                                                   sid, base, p, 1.0f / (1.0f - p));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
-int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, int sid, unsigned long long base,
+int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, const unsigned long long* ctr, int sid, unsigned long long base,
                       float p, cudaStream_t st) {
   MMQG_REQUIRE(x && n > 0 && n_part > 0 && p >= 0.f && p < 1.f, "dropout_scale_f32: bad args");
-  dropout_scale_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n_part, stride, n, seed, sid, base, p, 1.0f / (1.0f - p));
+  dropout_scale_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n_part, stride, n, seed, ctr, sid, base, p, 1.0f / (1.0f - p));
   MMQG_LAUNCH_CHECK();
   return 0;
 }

@@ -62,11 +62,11 @@ class TrainEngine:
         nbytes = self.lib.mmqg_train_workspace_bytes(C.byref(self._cd), self.mode)
         if nbytes == 0:
             raise _cabi.MmqgError(self.lib.mmqg_last_error().decode())
-        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        # zeroed once: its first 8 bytes are the dropout call counter (see mmqg.h), the rest is scratch
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._greedy_ws = None
-        self.seed = 0
-        self.auto_seed = True
+        self.seed = 0          # base dropout seed; the library adds the number of forward calls made so far
 
     # -- batches -------------------------------------------------------------------------
     def to_device(self, batch: dict, non_blocking=False) -> dict:
@@ -118,8 +118,6 @@ class TrainEngine:
         reducer.on_phase(0)
         self.backward_events(batch, reducer.events)
         reducer.after_backward()
-        if self.dropout_p > 0 and self.auto_seed:
-            self.seed += 1
         return loss
 
     def step(self, batch, grad_scale=1.0, on_phase=None):
@@ -134,8 +132,6 @@ class TrainEngine:
             for ph in (1, 2, 3):
                 self.backward(batch, ph)
                 on_phase(ph)
-        if self.dropout_p > 0 and self.auto_seed:
-            self.seed += 1                   # fresh masks next step (a captured CUDA graph replays one seed)
         return loss
 
     # -- optimiser -------------------------------------------------
@@ -160,10 +156,20 @@ class TrainEngine:
             self.flat_params.numel(), lo, hi, float(lr), float(betas[0]), float(betas[1]), float(eps),
             a["state"].data_ptr(), _stream_ptr()))
 
+    def dropout_calls(self) -> int:
+        """Forward calls with dropout made on this workspace (the device counter the masks depend on)."""
+        return int(self.ws[:8].view(torch.int64).item())
+
+    def reset_dropout_calls(self, value=0):
+        self.ws[:8].view(torch.int64).fill_(int(value))
+
     def dropout_masks(self, seed=None):
-        """The multiplicative inter-layer dropout masks (0 or 1/(1-p)) a step with `seed` applies:
-        {"text": (L-1,T_t,B,H), "dec": (L-1,T_q,B,H)} -- what tests feed the oracle."""
-        d, seed = self.d, self.seed if seed is None else seed
+        """The multiplicative inter-layer dropout masks (0 or 1/(1-p)) of the NEXT step (or of an
+        explicit effective `seed`): {"text": (L-1,T_t,B,H), "dec": (L-1,T_q,B,H)} -- what tests feed
+        the oracle.  Effective seed of a step = self.seed + number of forward calls up to and
+        including it, counted on the device so that a replayed CUDA graph draws fresh masks too."""
+        d = self.d
+        seed = self.seed + self.dropout_calls() + 1 if seed is None else seed
         out = {}
         for key, sid0, T in (("text", 10, d.T_t), ("dec", 20, d.T_q)):
             m = torch.empty(max(d.L - 1, 0), T, d.B, d.H, dtype=torch.float32, device=self.device)

@@ -60,8 +60,8 @@ def test_bf16_dropout_step_matches_oracle_with_same_masks(eng_mod, cfg, chunks, 
     params = make_params(d, seed=51)
     batch = make_batch(d, seed=52)
     eng = eng_mod.TrainEngine(d, params, mode="bf16", dropout_p=0.2)
-    eng.seed, eng.auto_seed = 1234, False
-    masks = {k: v.cpu() for k, v in eng.dropout_masks().items()}
+    eng.seed = 1234
+    masks = {k: v.cpu() for k, v in eng.dropout_masks().items()}          # masks of the next step
     keep = torch.cat([m.flatten() for m in masks.values()])
     assert set(keep.unique().tolist()) <= {0.0, 1.25}
     assert abs(float((keep > 0).float().mean()) - 0.8) < 0.02
@@ -74,12 +74,35 @@ def test_bf16_dropout_step_matches_oracle_with_same_masks(eng_mod, cfg, chunks, 
     worst = max(errs.items(), key=lambda kv: kv[1])
     print("bf16+dropout worst grad rel err", worst, "loss", loss, float(loss_ref), "no-drop", float(loss_nodrop))
     assert worst[1] < GRAD_TOL, errs
-    # a different seed draws different masks -> a different loss; the same seed repeats
-    again = float(eng.step(eng.to_device(batch)))
-    assert abs(again - loss) < 1e-4 * abs(loss)
-    eng.seed = 99
+    # the next step draws fresh masks (device-side call counter) -> a different loss; rewinding the
+    # counter repeats the first step exactly
+    assert eng.dropout_calls() == 1
     other = float(eng.step(eng.to_device(batch)))
     assert other != loss
+    eng.reset_dropout_calls(0)
+    again = float(eng.step(eng.to_device(batch)))
+    assert abs(again - loss) < 1e-4 * abs(loss)
+
+
+def test_bf16_dropout_fresh_masks_under_graph_replay(eng_mod):
+    """A captured step replays with a new mask every time (the call counter lives on the device)."""
+    d = Dims(B=8, T_t=9, T_v=3, T_q=4, V=300, E=52, H=64, L=2, H_a=24, H_v=64, F_v=40, TM=12, AM=5)
+    eng = eng_mod.TrainEngine(d, make_params(d, seed=81), mode="bf16", dropout_p=0.5)
+    batch = eng.to_device(make_batch(d, seed=82))
+    eager = []
+    for _ in range(4):
+        eager.append(float(eng.step(batch)))
+    eng.reset_dropout_calls(1)                 # the capture below does not execute; replays are calls 2, 3, 4
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        eng.step(batch)
+    got = []
+    for _ in range(3):
+        g.replay()
+        got.append(float(eng.loss))
+    assert got == pytest.approx(eager[1:], rel=1e-5), (got, eager)
+    assert len(set(round(x, 5) for x in got)) == 3
 
 
 def test_fp32_mode_rejects_dropout(eng_mod):
