@@ -128,7 +128,8 @@ def run_reference(args, d, rank, world):
     """--impl reference: the CPU path timed on the host cores, same metric/config keys."""
     if rank != 0:
         return
-    per_step = max(1, min(8, args.cpu_samples // 4))
+    # bounded sample: about 200 samples in total (~100 s at ~2 samples/s on 16 cores), whatever K is
+    per_step = max(1, min(8, 200 // max(1, args.steps)))
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_samples_per_s(d, 1, dropout_p=args.dropout)
     t_total, n_total = 0.0, 0
