@@ -297,12 +297,19 @@ static int pack_weights_rest(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w,
 // Priorities: the serial chains (persistent recurrent kernels, decoder step loops) are latency-bound
 // and own the critical path, the hoisted products are throughput work that only has to finish by
 // the end of the step -- so the chain streams (s[0..NS-3] and `chain`, onto which the work of the
-// caller's stream is moved for the duration of a call) get the highest stream priority and the
+// caller's stream is moved for the duration of a call) get a high stream priority and the
 // auxiliary streams s[NS-2] (loss head) and s[NS-1] (hoisted products) the lowest: when SMs free up,
-// waiting chain CTAs are placed first.  MMQG_PRIO=0 creates all streams alike.
+// waiting chain CTAs are placed first.  The short products BETWEEN the chunks of the pipelined text
+// encoder (input projection of the next layer / input gradient for the layer below) go to the
+// streams g[l] with the very highest priority: two persistent kernels occupy 128 of the 148 SMs
+// with ~200 KB of shared memory each, so such a product can only run where a persistent kernel has
+// just exited, and it must win those SMs against the next waiting persistent kernel -- otherwise it
+// crawls on the 20 spare SMs for 50-100 us while the layer that needs it idles (measured with
+// tools/ktrace.py).  MMQG_PRIO=0 creates all streams alike.
 struct AuxStream {
-  static constexpr int NS = 4, NE = 96;
+  static constexpr int NS = 4, NE = 160;
   cudaStream_t s[NS] = {};
+  cudaStream_t g[NS] = {};
   cudaStream_t chain = nullptr;
   cudaEvent_t ev[NE] = {};
   bool ready = false, prio = false;
@@ -312,9 +319,15 @@ struct AuxStream {
     prio = !(e && e[0] == '0');
     int lo = 0, hi = 0;
     MMQG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least (numerically largest), hi = greatest
-    for (int i = 0; i < NS; ++i)
-      MMQG_CUDA(cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, prio ? (i >= NS - 2 ? lo : hi) : lo));
-    MMQG_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, hi));
+    // pipeline stages of the text encoder: the LATER a stage, the higher its priority (a ready chunk
+    // of a downstream layer must not wait behind the head layer running ahead): chain = stage 0,
+    // s[0] = stage 1, s[1] = stage 2.  Only two persistent kernels fit on the SMs at a time.
+    auto clampp = [&](int p) { return p < hi ? hi : (p > lo ? lo : p); };
+    for (int i = 0; i < NS; ++i) {
+      MMQG_CUDA(cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, prio ? (i >= NS - 2 ? lo : clampp(hi + 2 - i)) : lo));
+      MMQG_CUDA(cudaStreamCreateWithPriority(&g[i], cudaStreamNonBlocking, prio ? hi : lo));
+    }
+    MMQG_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, prio ? clampp(hi + 3) : lo));
     for (auto& e2 : ev) MMQG_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
     ready = true;
     return 0;
@@ -338,9 +351,16 @@ struct AuxStream {
 };
 static AuxStream g_aux;
 static constexpr int kMaxChunks = 8;
-// event slots: [0,8) misc, [16,48) forward done(l,c), [48,80) backward done(l,c)
+// event slots: [0,16) misc, [16,48) forward done(l,c), [48,80) backward done(l,c),
+// [96,128) / [128,160) hand-over between a layer stream and its product stream g[l]
 static cudaEvent_t ev_fwd(int l, int c) { return g_aux.ev[16 + l * kMaxChunks + c]; }
 static cudaEvent_t ev_bwd(int l, int c) { return g_aux.ev[48 + l * kMaxChunks + c]; }
+static cudaEvent_t ev_gf(int l, int c) { return g_aux.ev[96 + l * kMaxChunks + c]; }
+static cudaEvent_t ev_gb(int l, int c) { return g_aux.ev[128 + l * kMaxChunks + c]; }
+static bool split_products() {
+  static const bool on = []() { const char* e = getenv("MMQG_GSTREAMS"); return !(e && e[0] == '0'); }();
+  return on && g_aux.prio;
+}
 
 // Number of time chunks the text-encoder layers are pipelined over (1 = layer after layer).
 // Layer l can run chunk c as soon as layer l-1 has finished chunk c, so with the layers on
@@ -375,6 +395,7 @@ static int video_forward16(const mmqg_dims& d, const mmqg_batch& bt, Ws16& w, cu
                   w.acts_v + (size_t)t * B * Gv, Gv).bias(w.bsum_vid).run(st));
     MMQG_CUDA(cudaMemsetAsync(w.hs_v, 0, sizeof(b16) * (size_t)B * Hv, st));
     MMQG_CUDA(cudaMemsetAsync(w.cs_v, 0, sizeof(float) * (size_t)B * Hv, st));
+    tl_ktag = 900;
     MMQG_TRY(rec_fwd(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags_v, d.T_v, B, Hv, st));
   } else
   for (int t = 0; t < d.T_v; ++t) {
@@ -401,9 +422,11 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
     MMQG_TRY(g_aux.init());
     const int CL = (d.T_t + NC - 1) / NC;
     MMQG_TRY(Tc(w.x0, w.Ep, false, w.wt_ih[0], w.Ep, false, d.T_t * B, G, w.Ep, w.acts_text[0], G).bias(w.bsum_text[0]).run(st));
+    const int n_mt = (B + 127) / 128;
     for (int l = 0; l < d.L; ++l) {
       MMQG_CUDA(cudaMemsetAsync(w.hs_text[l], 0, sizeof(b16) * (size_t)B * H, st));
       MMQG_CUDA(cudaMemsetAsync(w.cs_text[l], 0, sizeof(float) * (size_t)B * H, st));
+      MMQG_CUDA(cudaMemsetAsync(w.flags_t[l], 0, sizeof(uint32_t) * (size_t)(d.T_t + 1) * n_mt, st));
     }
     MMQG_CUDA(cudaEventRecord(g_aux.ev[0], st));
     for (int l = 1; l < d.L; ++l) MMQG_CUDA(cudaStreamWaitEvent(g_aux.s[l - 1], g_aux.ev[0], 0));
@@ -412,18 +435,28 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
       for (int l = 0; l < d.L; ++l) {
         cudaStream_t s = l == 0 ? st : g_aux.s[l - 1];
         if (l > 0) {
-          MMQG_CUDA(cudaStreamWaitEvent(s, ev_fwd(l - 1, c), 0));
+          // input projection of this chunk on the layer's product stream (highest priority), then hand over
+          cudaStream_t gs = split_products() ? g_aux.g[l] : s;
+          MMQG_CUDA(cudaStreamWaitEvent(gs, ev_fwd(l - 1, c), 0));
           const b16* X = g_drop_p > 0.f ? w.xdrop_text[l - 1] + (size_t)t0 * B * H : w.hs_text[l - 1] + (size_t)(t0 + 1) * B * H;
           MMQG_TRY(Tc(X, H, false, w.wt_ih[l], H, false, nT * B, G, H, w.acts_text[l] + (size_t)t0 * B * G, G)
-                       .bias(w.bsum_text[l]).run(s));
+                       .bias(w.bsum_text[l]).run(gs));
+          if (gs != s) {
+            MMQG_CUDA(cudaEventRecord(ev_gf(l, c), gs));
+            MMQG_CUDA(cudaStreamWaitEvent(s, ev_gf(l, c), 0));
+          }
         }
+        tl_ktag = l * 16 + c;
+        DropSpec dr;           // the kernel writes the dropped copy of its h_t itself (no extra launch between chunks)
+        if (g_drop_p > 0.f && l + 1 < d.L) {
+          dr.out = w.xdrop_text[l] + (size_t)t0 * B * H; dr.ld = H; dr.seed = g_drop_seed; dr.ctr = g_drop_ctr;
+          dr.sid = kSidText + l; dr.base = (unsigned long long)t0 * B * H; dr.p = g_drop_p;
+        }
+        // arrival counters: one region per chunk of the layer's array, zeroed once above
         MMQG_TRY(lstm_seq_fwd_persist(w.acts_text[l] + (size_t)t0 * B * G, w.cs_text[l] + (size_t)t0 * B * H,
                                       w.hs_text[l] + (size_t)t0 * B * H, w.wtp_f[l],
                                       nullptr, l == d.L - 1 ? w.m_txt16 + (size_t)t0 * H : nullptr, (long long)d.TM * H,
-                                      w.flags_t[l], nT, B, H, c > 0 ? 1 : 0, s));
-        if (g_drop_p > 0.f && l + 1 < d.L)
-          MMQG_TRY(dropout_bf16(w.hs_text[l] + (size_t)(t0 + 1) * B * H, w.xdrop_text[l] + (size_t)t0 * B * H, (long long)nT * B * H,
-                                g_drop_seed, g_drop_ctr, kSidText + l, (unsigned long long)t0 * B * H, g_drop_p, s));
+                                      w.flags_t[l] + (size_t)t0 * n_mt, nT, B, H, c > 0 ? 1 : 0, s, dr, false));
         MMQG_CUDA(cudaEventRecord(ev_fwd(l, c), s));
       }
     }
@@ -716,6 +749,7 @@ struct Bwd16 {
     const int Hv = d.H_v, Gv = 4 * d.H_v;
     const long long pv = (long long)B * Hv;
     if (persist_video(d)) {
+      tl_ktag = 900;
       MMQG_TRY(rec_bwd(w.acts_v, w.cs_v, w.dg_v, w.wvp_b, w.dm_vid, Hv, (long long)d.AM * Hv, nullptr, nullptr, w.flags_v,
                        d.T_v, B, Hv, st));
     } else {
@@ -801,7 +835,9 @@ struct Bwd16 {
   // hoisted weight gradients of a finished layer go to `hoist`.
   int text_pipelined(int NC, cudaStream_t st, cudaStream_t hoist) {
     const int CL = (d.T_t + NC - 1) / NC;
-    auto S = [&](int l) { return l == L - 1 ? st : g_aux.s[l]; };
+    auto S = [&](int l) { return l == L - 1 ? st : g_aux.s[L - 2 - l]; };      // stage k of the reverse pipeline on s[k-1]
+    const int n_mt = (B + 127) / 128;
+    for (int l = 0; l < L; ++l) MMQG_CUDA(cudaMemsetAsync(w.flags_t[l], 0, sizeof(uint32_t) * (size_t)(d.T_t + 1) * n_mt, st));
     MMQG_CUDA(cudaEventRecord(g_aux.ev[1], st));
     for (int l = 0; l < L - 1; ++l) MMQG_CUDA(cudaStreamWaitEvent(S(l), g_aux.ev[1], 0));
     for (int c = NC - 1; c >= 0; --c) {
@@ -810,30 +846,38 @@ struct Bwd16 {
       for (int l = L - 1; l >= 0; --l) {
         cudaStream_t s = S(l);
         const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
+        DropSpec dr;
         if (l < L - 1) {
           MMQG_CUDA(cudaStreamWaitEvent(s, ev_bwd(l + 1, c), 0));
-          if (g_drop_p > 0.f)
-            MMQG_TRY(dropout_scale_f32(w.dx_text + (size_t)t0 * B * H, 1, 0, (long long)nT * B * H, g_drop_seed, g_drop_ctr, kSidText + l,
-                                       (unsigned long long)t0 * B * H, g_drop_p, s));
+          if (g_drop_p > 0.f) {      // dx_text is d/d(dropped h_l): the kernel applies this layer's output mask to it
+            dr.seed = g_drop_seed; dr.ctr = g_drop_ctr; dr.sid = kSidText + l; dr.base = (unsigned long long)t0 * B * H; dr.p = g_drop_p;
+          }
         }
         if (tail)   // d loss / d h_final of this layer (decoder initial state, + step-0 attention query on top)
           MMQG_TRY(sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, w.dh_last_l[l],
                                 B * H, s));
         const float* ext = l == L - 1 ? w.dm_txt + (size_t)t0 * H : w.dx_text + (size_t)t0 * B * H;
         const long long ts = l == L - 1 ? H : (long long)B * H, ld = l == L - 1 ? (long long)d.TM * H : H;
+        tl_ktag = l * 16 + c;
         MMQG_TRY(lstm_seq_bwd_persist(w.acts_text[l] + (size_t)t0 * B * G, w.cs_text[l] + (size_t)t0 * B * H,
                                       w.dg_text[l] + (size_t)t0 * B * G, w.wtp_b[l], ext, ts, ld, tail ? w.dh_last_l[l] : nullptr,
-                                      w.dc[l], w.flags_t[l], nT, B, H, tail ? 0 : 1, w.dc[l], s));
+                                      w.dc[l], w.flags_t[l] + (size_t)t0 * n_mt, nT, B, H, tail ? 0 : 1, w.dc[l], s, dr, false));
+        // input gradient of this chunk (what the layer below waits for) on the product stream
         float* dx = l == 0 ? w.dx_emb + (size_t)t0 * B * E : w.dx_text + (size_t)t0 * B * H;
-        MMQG_TRY(Tc(w.dg_text[l] + (size_t)t0 * B * G, G, false, w.wt_ih[l], Ip, true, nT * B, I, G, dx, I).run(s));
-        MMQG_CUDA(cudaEventRecord(ev_bwd(l, c), s));
+        cudaStream_t gs = split_products() ? g_aux.g[l] : s;
+        if (gs != s) {
+          MMQG_CUDA(cudaEventRecord(ev_gb(l, c), s));
+          MMQG_CUDA(cudaStreamWaitEvent(gs, ev_gb(l, c), 0));
+        }
+        MMQG_TRY(Tc(w.dg_text[l] + (size_t)t0 * B * G, G, false, w.wt_ih[l], Ip, true, nT * B, I, G, dx, I).run(gs));
+        MMQG_CUDA(cudaEventRecord(ev_bwd(l, c), gs));
         if (c == 0) {
           MMQG_CUDA(cudaStreamWaitEvent(hoist, ev_bwd(l, 0), 0));
           MMQG_TRY(text_hoisted(l, hoist));
         }
       }
     }
-    for (int l = 0; l < L - 1; ++l) MMQG_CUDA(cudaStreamWaitEvent(st, ev_bwd(l, 0), 0));   // join the layer streams
+    for (int l = 0; l < L; ++l) MMQG_CUDA(cudaStreamWaitEvent(st, ev_bwd(l, 0), 0));   // join the layer / product streams
     return 0;
   }
 

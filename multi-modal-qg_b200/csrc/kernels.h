@@ -91,12 +91,15 @@ int dropout_mask(float* out, long long n, unsigned long long seed, int sid, floa
 // persistent recurrent-cell kernels (lstm_persist.cu)
 bool lstm_persist_ok(int B, int H);
 int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st);
+extern thread_local int tl_ktag;      // debug: tag of the next persistent recurrent launch (lstm_persist.cu)
 int sum_partials(const float* a, int na, const float* b, int nb, long long stride, float* y, int n, cudaStream_t st);
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,
-                         uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st);
+                         uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st, DropSpec dr = DropSpec(),
+                         bool zero_flags = true);
 int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
-                         int T, int B, int H, int has_next, float* dc_out, cudaStream_t st);
+                         int T, int B, int H, int has_next, float* dc_out, cudaStream_t st, DropSpec dr = DropSpec(),
+                         bool zero_flags = true);
 // cluster variant (lstm_cluster.cu): cluster barrier + TMA multicast instead of global flags
 bool lstm_cluster_ok(int B, int H);
 int pack_whh_cluster(const float* w_hh, void* fwd_packed, int H, cudaStream_t st);

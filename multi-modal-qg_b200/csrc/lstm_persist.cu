@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "dropout.cuh"
 
 namespace mmqg {
 
@@ -106,6 +107,15 @@ __device__ __forceinline__ void row_bf16_to_global(uint32_t* stg, int lane, cons
   }
 }
 
+// kernel timeline record: buf[0] = atomic slot counter, then (tag, start, end) triples
+__device__ __forceinline__ int ktrace_begin(long long* buf, int tag) {
+  const int slot = (int)atomicAdd(reinterpret_cast<unsigned long long*>(buf), 1ull);
+  buf[1 + 3 * slot] = tag;
+  buf[2 + 3 * slot] = gtime();
+  return slot;
+}
+__device__ __forceinline__ void ktrace_end(long long* buf, int slot) { buf[3 + 3 * slot] = gtime(); }
+
 struct LstmFwdP {
   float* gates;        // (T*B, 4H) fp32: in = x W_ih^T + b (hoisted), out = activated gates i,f,g,o
   float* cs;           // ((T+1)*B, H) fp32; slab t+1 receives c_t (slab 0 is not read: c_{-1} = 0)
@@ -117,6 +127,8 @@ struct LstmFwdP {
   int T, B, H, n_mt, n_slices, KB;
   int load_c0;         // 1: c_{-1} is read from slab 0 of cs (continuing a sequence chunk), 0: zeros
   long long* trace;    // debug: per-step clock64 stamps of CTA (0,0), 8 per step (nullable)
+  long long* ktrace; int ktag;   // debug: kernel-level timeline (see mmqg_debug_ktrace)
+  DropSpec dr;         // dr.out: optional dropped bf16 copy of h_t, (T*B, H) rows t*B+b (input of the next layer)
 };
 
 __global__ void __launch_bounds__(160, 1)
@@ -192,6 +204,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     const int rows_valid = max(0, min(32, B - m0w));
     const int j0 = slice * 16;
     float* stg = reinterpret_cast<float*>(sA + p.KB * 16384) + warp * STG_WARP;
+    const bool kt = p.ktrace && row == 0 && slice == 0 && mt == 0;
+    const int kslot = kt ? ktrace_begin(p.ktrace, p.ktag) : 0;
     float c[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) c[u] = 0.f;
@@ -270,9 +284,24 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         if (p.mem16)
           row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.mem16 + (size_t)m0w * p.mem_ld + (size_t)t * H + j0,
                              (size_t)p.mem_ld, rows_valid);
+        if (p.dr.out) {       // inter-layer dropout: the next layer reads this copy
+          const float ik = 1.0f / (1.0f - p.dr.p);
+          const unsigned long long sd = p.dr.seed + (p.dr.ctr ? *p.dr.ctr : 0ull);
+          const unsigned long long e0 = p.dr.base + ((unsigned long long)t * B + m) * H + j0;
+          uint32_t dp[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(hv[2 * v] * drop_scale(sd, p.dr.sid, e0 + 2 * v, p.dr.p, ik),
+                                                      hv[2 * v + 1] * drop_scale(sd, p.dr.sid, e0 + 2 * v + 1, p.dr.p, ik));
+            dp[v] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, dp, reinterpret_cast<bf16*>(p.dr.out) + ((size_t)t * B + m0w) * p.dr.ld + j0,
+                             (size_t)p.dr.ld, rows_valid);
+        }
       }
       (void)valid;
     }
+    if (kt) ktrace_end(p.ktrace, kslot);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -295,6 +324,8 @@ struct LstmBwdP {
   int T, B, H, n_mt, n_slices, NKB;   // NKB = 4H/64
   int has_next;         // 1: dg slab T (first step of the following chunk) exists and feeds step T-1
   float* dc_out;        // (B,H) receives d loss / d c_{-1} at the end (nullable)
+  long long* ktrace; int ktag;
+  DropSpec dr;          // dr.p > 0: dh_ext is the gradient w.r.t. the DROPPED h_t -> multiplied by the mask here
 };
 
 static constexpr int BWD_STAGES = 6;     // 144 KB in flight: the streaming rate is ring bytes / TMA round trip
@@ -378,6 +409,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     const int rows_valid = max(0, min(32, B - m0w));
     const int j0 = slice * 16;
     float* stg = reinterpret_cast<float*>(sA + BWD_STAGES * 16384) + warp * STG_WARP;
+    const bool kt = p.ktrace && row == 0 && slice == 0 && mt == 0;
+    const int kslot = kt ? ktrace_begin(p.ktrace, p.ktag) : 0;
     float dc[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) dc[u] = (p.dc_last && valid) ? p.dc_last[(size_t)m * H + j0 + u] : 0.f;
@@ -402,6 +435,13 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       coop_to_row(stg, lane, cn4, cn);
       coop_to_row(stg, lane, cp4, cp);
       coop_to_row(stg, lane, ex4, ex);
+      if (p.dr.p > 0.f) {     // ext is d/d(dropped h_t): back through this layer's output mask
+        const float ik = 1.0f / (1.0f - p.dr.p);
+        const unsigned long long sd = p.dr.seed + (p.dr.ctr ? *p.dr.ctr : 0ull);
+        const unsigned long long e0 = p.dr.base + ((unsigned long long)t * B + m) * H + j0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) ex[u] *= drop_scale(sd, p.dr.sid, e0 + u, p.dr.p, ik);
+      }
       float dh[16];
       if (t == T - 1 && !p.has_next) {
 #pragma unroll
@@ -452,6 +492,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       row_to_coop(stg, lane, dc, tmp);
       coop_stg(p.dc_out + (size_t)m0w * H + j0, H, rows_valid, lane, tmp);
     }
+    if (kt) ktrace_end(p.ktrace, kslot);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -493,6 +534,8 @@ __global__ void sum_partials_kernel(const float* __restrict__ a, int na, const f
 
 // ---- host -----------------------------------------------------------------------------------
 static long long* g_lstm_trace = nullptr;   // debug hook, see mmqg_debug_lstm_trace()
+static long long* g_ktrace = nullptr;       // debug hook, see mmqg_debug_ktrace()
+thread_local int tl_ktag = 0;               // tag of the next persistent launch (set by the engine)
 
 static int num_sms() {
   static int n = 0;
@@ -548,9 +591,9 @@ static int launch_coop(Kern kern, dim3 grid, int threads, size_t smem, const CUt
 
 // gates: (T*B,4H) fp32 pre-gates -> activated gates.  wp_fwd: pack_whh forward layout.  hs slab 0 must be zeros.
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,
-                         uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st) {
+                         uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st, DropSpec dr, bool zero_flags) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
-  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, reinterpret_cast<bf16*>(mem16), mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace};
+  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, reinterpret_cast<bf16*>(mem16), mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace, g_ktrace, tl_ktag, dr};
   CUtensorMap tmW, tmH;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_fwd, 4 * (uint64_t)H, H, H, 64, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmH, hs, (uint64_t)(T + 1) * B, H, H, 128, 64));
@@ -560,7 +603,7 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
     MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 16384) + 4 * STG_WARP * sizeof(float) + 1024));
     attr = true;
   }
-  MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(T + 1) * p.n_mt, st));
+  if (zero_flags) MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(T + 1) * p.n_mt, st));
   const double fl = 2.0 * T * B * 4.0 * H * H;
   MMQG_PROBE(KC_LSTM_PERSIST, fl, 0);
   MMQG_TRY(launch_coop(lstm_seq_fwd_kernel, dim3(p.n_slices, p.n_mt), 160, smem, tmW, tmH, p, st));
@@ -570,10 +613,10 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
 
 int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
-                         int T, int B, int H, int has_next, float* dc_out, cudaStream_t st) {
+                         int T, int B, int H, int has_next, float* dc_out, cudaStream_t st, DropSpec dr, bool zero_flags) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_bwd_persist: shape B=%d H=%d not supported", B, H);
   LstmBwdP p{acts, cs, reinterpret_cast<bf16*>(dg), dh_ext, ext_ts, ext_ld, dh_last, dc_last, flags,
-             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64, has_next, dc_out};
+             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64, has_next, dc_out, g_ktrace, 1000 + tl_ktag, dr};
   CUtensorMap tmW, tmG;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_bwd, H, 4 * (uint64_t)H, 4 * (uint64_t)H, 16, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmG, dg, (uint64_t)(T + (has_next ? 1 : 0)) * B, 4 * (uint64_t)H, 4 * (uint64_t)H, 128, 64));
@@ -583,7 +626,7 @@ int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const voi
     MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 2048 + BWD_STAGES * 16384 + 4 * STG_WARP * (int)sizeof(float) + 1024));
     attr = true;
   }
-  MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)T * p.n_mt, st));
+  if (zero_flags) MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)T * p.n_mt, st));
   const double fl = 2.0 * (T - 1) * B * 4.0 * H * H;
   MMQG_PROBE(KC_LSTM_PERSIST, fl, 0);
   MMQG_TRY(launch_coop(lstm_seq_bwd_kernel, dim3(p.n_slices, p.n_mt), 192, smem, tmW, tmG, p, st));
@@ -596,3 +639,8 @@ int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const voi
 // Debug hook (not part of the product path): device buffer of 8*T int64 that the next forward
 // persistent launches fill with clock64() stamps of CTA (0,0); pass NULL to switch off.
 extern "C" void mmqg_debug_lstm_trace(void* dev_buf) { mmqg::g_lstm_trace = reinterpret_cast<long long*>(dev_buf); }
+
+// Debug hook: device buffer of int64 (slot counter, then (tag, start ns, end ns) per persistent
+// launch; tag = layer*16 + chunk, +1000 for the backward kernels, 900 = video).  NULL switches off.
+extern "C" void mmqg_debug_ktrace(void* dev_buf) { mmqg::g_ktrace = reinterpret_cast<long long*>(dev_buf); }
+

@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "dropout.cuh"
 
 namespace mmqg {
 
@@ -46,15 +47,6 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
 
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// same counter-based mask as pointwise_bf16.cu (drop_scale)
-__device__ __forceinline__ float drop_scale(unsigned long long seed, int sid, unsigned long long idx, float p, float inv_keep) {
-  unsigned long long z = seed + (unsigned long long)sid * 0x9E3779B97F4A7C15ull + idx * 0xD1342543DE82EF95ull;
-  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
-  z ^= z >> 27; z *= 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.f;
-}
 
 __global__ void __launch_bounds__(320, 1)
 lstm_step_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,

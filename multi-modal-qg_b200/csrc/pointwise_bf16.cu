@@ -3,6 +3,7 @@
 // bf16 (h sequences, gate gradients, gathered embeddings, dlogits, packed weights).
 #include <cuda_bf16.h>
 #include "kernels.h"
+#include "dropout.cuh"
 
 namespace mmqg {
 
@@ -36,14 +37,6 @@ __global__ void embedding_gather_bf16_kernel(const float* __restrict__ emb, cons
 // the seed and chunked application equals whole-tensor application.  Not bit-compatible with
 // ATen's Philox stream (SURVEY section 7 "Hard parts"): validated against the oracle run with the
 // exported mask (mmqg_dropout_mask) and statistically.
-__device__ __forceinline__ float drop_scale(unsigned long long seed, int sid, unsigned long long idx, float p, float inv_keep) {
-  unsigned long long z = seed + (unsigned long long)sid * 0x9E3779B97F4A7C15ull + idx * 0xD1342543DE82EF95ull;
-  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
-  z ^= z >> 27; z *= 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.f;
-}
 
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 
