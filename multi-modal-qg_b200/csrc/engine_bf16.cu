@@ -813,7 +813,7 @@ struct Bwd16 {
     // few microseconds -- these products share the SMs with the latency-bound BPTT kernels, which
     // can only start once 64 SMs are free -- and reduce the partial tiles afterwards.
     static const bool splitw_env = []() { const char* e = getenv("MMQG_SPLITW"); return !(e && e[0] == '0'); }();
-    const bool splitw = splitw_env && (long long)d.T_t * B >= 64ll * 64 * kSplitW;
+    const bool splitw = splitw_env && (long long)d.T_t * B >= 16ll * 64 * kSplitW;      // >= 16 k-blocks per slice
     if (splitw) {
       MMQG_TRY(Tc(dG, G, true, X, Ip, true, G, I, d.T_t * B, w.dw_part, I).split(kSplitW, (long long)G * I).run(st));
       MMQG_TRY(reduce_partials(w.dw_part, kSplitW, (long long)G * I, Gd.text_w_ih[l], I, G, I, st));

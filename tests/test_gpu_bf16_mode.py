@@ -113,6 +113,23 @@ def test_fp32_mode_rejects_dropout(eng_mod):
         eng.step(eng.to_device(make_batch(d)))
 
 
+def test_bf16_long_sequence_split_weight_gradients(eng_mod):
+    """T_t*B large enough for the split-K + reduce path of the text encoder's hoisted weight gradients."""
+    from oracle import mmqg_oracle as O
+    d = Dims(B=128, T_t=96, T_v=2, T_q=3, V=300, E=52, H=64, L=2, H_a=24, H_v=64, F_v=40, TM=100, AM=4)
+    params = make_params(d, seed=91)
+    batch = make_batch(d, seed=92)
+    loss_ref, grads_ref = O.loss_and_grads(round_params_bf16(params), batch, d.L, d.TM, d.AM, torch.float64)
+    eng = eng_mod.TrainEngine(d, params, mode="bf16")
+    loss = float(eng.step(eng.to_device(batch)))
+    torch.cuda.synchronize()
+    assert abs(loss - float(loss_ref)) < LOSS_TOL * abs(float(loss_ref))
+    errs = {k: rel(eng.grads[k], g) for k, g in grads_ref.items()}
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print("long-sequence worst grad rel err", worst)
+    assert worst[1] < GRAD_TOL, errs
+
+
 def test_bf16_close_to_fp32_engine(eng_mod):
     d = Dims(B=16, T_t=12, T_v=4, T_q=5, V=2000, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101)
     params = make_params(d, seed=43)
