@@ -151,7 +151,10 @@ size_t mmqg_greedy_workspace_bytes(const mmqg_dims* d, int max_len, int mode);
 
 /* Greedy decode (reference train.py:101-110, evaluate.py:70-80): encoder pass, then
  * max_len decoder steps feeding back argmax(logits) (lowest index on ties).
- * tokens_out: device int64 (B,max_len).  d->T_q is ignored. */
+ * tokens_out: device int64 (B,max_len).  d->T_q is ignored.  MMQG_MODE_FP32 reproduces the
+ * reference's tokens exactly (fp32-accurate logits); MMQG_MODE_BF16 runs the tensor-core path
+ * (about 6x faster) and can leave the fp32 token path where the top-2 logit margin is below
+ * bf16 resolution. */
 int mmqg_greedy_decode(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,
                        void* workspace, size_t workspace_bytes, int64_t* tokens_out, int max_len,
                        int mode, void* stream);

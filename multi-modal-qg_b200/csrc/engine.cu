@@ -239,7 +239,7 @@ size_t mmqg_train_workspace_bytes(const mmqg_dims* d, int mode) {
 
 size_t mmqg_greedy_workspace_bytes(const mmqg_dims* d, int max_len, int mode) {
   if (check_dims(d) != 0 || max_len <= 0) return 0;
-  (void)mode;
+  if (mode == MMQG_MODE_BF16) return check_dims_bf16(*d) == 0 ? greedy_workspace_bytes_bf16(*d, max_len) : 0;
   return carve(*d, max_len, nullptr).bytes;
 }
 
@@ -504,7 +504,9 @@ int mmqg_greedy_decode(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   MMQG_TRY(check_tensors(d, params, "params"));
   MMQG_REQUIRE(batch && batch->context && batch->frames && batch->audio, "batch: null pointer");
   MMQG_REQUIRE(workspace && tokens_out && max_len > 0, "greedy: bad args");
-  MMQG_REQUIRE(mode == MMQG_MODE_FP32, "mode %d not available in this build of the decode path", mode);
+  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
+  if (mode == MMQG_MODE_BF16)
+    return greedy_decode_bf16(d, *params, *batch, workspace, workspace_bytes, tokens_out, max_len, as_stream(stream));
   Ws w = carve(d, max_len, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);

@@ -637,6 +637,75 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   return 0;
 }
 
+// ---- greedy decode on the tensor-core path (reference train.py:81-110, evaluate.py:45-80) ------------
+// Encoder as in training (no dropout), then max_len decoder steps feeding back argmax(logits)
+// (lowest index on ties).  bf16 operands: tokens can leave the fp32 oracle's path at near-ties --
+// the fp32 mode carries the token-exact claim, this mode the throughput.
+int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace, size_t workspace_bytes,
+                       int64_t* tokens_out, int max_len, cudaStream_t user) {
+  MMQG_TRY(check_dims_bf16(d));
+  Ws16 w = carve16(d, max_len, workspace);
+  if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
+  g_drop_p = 0.f;
+  g_drop_seed = 0;
+  g_drop_ctr = w.seed_ctr;
+  cudaStream_t st;
+  MMQG_TRY(g_aux.enter(user, &st));
+  const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, Sp = w.Sp, Ep = w.Ep;
+  cudaStream_t ax = g_aux.s[AuxStream::NS - 1];
+  MMQG_TRY(build_indices(bt.context, nullptr, w.idx_ctx, nullptr, nullptr, B, d.T_t, 0, st));
+  MMQG_CUDA(cudaEventRecord(g_aux.ev[8], st));
+  MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[8], 0));
+  MMQG_TRY(pack_weights_rest(d, P, w, ax));
+  MMQG_TRY(video_forward16(d, bt, w, ax));
+  MMQG_CUDA(cudaEventRecord(g_aux.ev[9], ax));
+  MMQG_TRY(pack_weights_text(d, P, w, st));
+  MMQG_TRY(text_forward16(d, P, w, st));
+  MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[9], 0));
+  AttnShape as = attn_shape16(d, w);
+  as.ldctx16 = C;
+  MMQG_TRY(fill_i64(w.idx_cur, B, 1, st));                      // <start>, train.py:84
+  PdlScope pdl_scope(pdl_enabled());
+  for (int t = 0; t < max_len; ++t) {
+    StepGemmScope step_scope;
+    b16* e_t = w.e_dec + (size_t)t * B * Ep;
+    {
+      PdlScope no_pdl(false);
+      MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_cur, e_t, Ep, B, d.E, Ep, d.V, st));
+    }
+    const b16* htop_prev = w.hs_dec[d.L - 1] + (size_t)t * B * H;
+    float* sc = w.attn_all + (size_t)t * B * Sp;
+    b16* ctx = w.ctx16 + (size_t)t * B * C;
+    MMQG_TRY(Tc(e_t, Ep, false, w.wa_e, Ep, false, B, Sp, Ep, sc, Sp).second(htop_prev, H, w.wa_h, H, H).bias(w.attn_b_cat).run(st));
+    as.ctx16 = ctx;
+    MMQG_TRY(attn_fwd(sc, Sp, w.m_txt, w.m_aud, w.m_vid, w.ctx_tmp, C, as, st));
+    for (int l = 0; l < d.L; ++l) {
+      float* acts = w.acts_dec[l] + (size_t)t * B * G;
+      const b16* hprev = w.hs_dec[l] + (size_t)t * B * H;
+      if (l == 0) {
+        MMQG_TRY(Tc(e_t, Ep, false, w.wd_e, Ep, false, B, G, Ep, acts, G).bias(w.bsum_dec[0]).run(st));
+        MMQG_TRY(Tc(ctx, C, false, w.wd_cat[0] + H, H + C, false, B, G, C, acts, G).second(hprev, H, w.wd_cat[0], H + C, H)
+                     .accumulate(true).run(st));
+      } else {
+        MMQG_TRY(Tc(w.hs_dec[l - 1] + (size_t)(t + 1) * B * H, H, false, w.wd_cat[l] + H, 2 * H, false, B, G, H, acts, G)
+                     .second(hprev, H, w.wd_cat[l], 2 * H, H).bias(w.bsum_dec[l]).run(st));
+      }
+      MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
+                                       w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st));
+    }
+    const b16* htop = w.hs_dec[d.L - 1] + (size_t)(t + 1) * B * H;
+    PdlScope no_pdl(false);
+    for (int r0 = 0; r0 < B; r0 += w.Rc) {
+      const int rc = B - r0 < w.Rc ? B - r0 : w.Rc;
+      MMQG_TRY(Tc(htop + (size_t)r0 * H, H, false, w.wo, H, false, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(st));
+      MMQG_TRY(argmax_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, st));
+    }
+  }
+  return g_aux.leave(user, st);
+}
+
+size_t greedy_workspace_bytes_bf16(const mmqg_dims& d, int max_len) { return carve16(d, max_len, nullptr).bytes; }
+
 // ---- backward -----------------------------------------------------------------------------
 struct Bwd16 {
   const mmqg_dims& d; const mmqg_tensors& P; const mmqg_batch& bt; Ws16& w; mmqg_tensors& Gd;

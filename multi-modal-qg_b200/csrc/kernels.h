@@ -113,6 +113,9 @@ int check_dims_bf16(const mmqg_dims& d);
 int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                        size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
                        float dropout_p, unsigned long long seed, cudaStream_t st);
+int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace, size_t workspace_bytes,
+                       int64_t* tokens_out, int max_len, cudaStream_t st);
+size_t greedy_workspace_bytes_bf16(const mmqg_dims& d, int max_len);
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                         size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
                         cudaStream_t st, cudaEvent_t const* ready = nullptr);

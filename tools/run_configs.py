@@ -35,3 +35,11 @@ if "5" in which:
     ms = timed(lambda: eng.greedy(db, 30), 3)
     toks = eng.greedy(db, 30)
     print(f"cfg5 greedy fp32: {ms:.2f} ms per batch of {d.B}  {d.B / ms * 1e3:.0f} samples/s  distinct sequences {len({tuple(r) for r in toks.tolist()})}", flush=True)
+    e16 = TrainEngine(d, params, mode="bf16"); db16 = e16.to_device(batch)
+    ms16 = timed(lambda: e16.greedy(db16, 30), 5)
+    t16 = e16.greedy(db16, 30)
+    same = (t16 == toks)
+    first_diff = torch.where(same.all(1), torch.full((d.B,), 30, device=same.device), (~same).float().argmax(1))
+    print(f"cfg5 greedy bf16: {ms16:.2f} ms per batch of {d.B}  {d.B / ms16 * 1e3:.0f} samples/s  rows identical to fp32 "
+          f"{int(same.all(1).sum())}/{d.B}, tokens identical {float(same.float().mean()):.3f}, mean first difference at step "
+          f"{float(first_diff.float().mean()):.1f}", flush=True)
