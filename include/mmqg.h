@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MMQG_ABI_VERSION 1
+#define MMQG_ABI_VERSION 2
 #define MMQG_MAX_LAYERS 4
 
 typedef enum {
@@ -82,6 +82,16 @@ typedef struct {
   const int64_t* target;     /* (B,T_q)      question + <end>     train.py:174-175 */
   const float* frames;       /* (B,T_v,F_v)  frame features       encoder.py:69    */
   const float* audio;        /* (B,T_v,H_a)  VGGish features      encoder.py:122   */
+  /* Optional per-sample lengths (device int32 (B), or NULL = every sample uses the full T):
+   * sample b is context[b,:ctx_len[b]], target[b,:tgt_len[b]], frames/audio[b,:n_frames[b]],
+   * 1 <= len <= T; what lies beyond is ignored.  Same result as running the reference's
+   * per-sample loop (train.py:153-177) on each sample with its own lengths: encoder states
+   * start from zero at the sample's first real token, memory rows beyond the length are the
+   * zero padding of train.py:155-160, the loss sums over the sample's own target steps.
+   * Train path in MMQG_MODE_BF16 with the persistent recurrent kernels only. */
+  const int* ctx_len;
+  const int* tgt_len;
+  const int* n_frames;
 } mmqg_batch;
 
 int mmqg_abi_version(void);

@@ -258,6 +258,7 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
     return train_forward_bf16(d, *params, *batch, workspace, workspace_bytes, loss_out, want_grads, grads, grad_scale,
                               dropout_p, seed, as_stream(stream));
   MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: the fp32 parity mode runs without dropout (use the bf16 mode)", dropout_p);
+  MMQG_REQUIRE(!batch->ctx_len && !batch->tgt_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
   Ws w = carve(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
@@ -353,6 +354,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   if (mode == MMQG_MODE_BF16)
     return train_backward_bf16(d, *params, *batch, workspace, workspace_bytes, *grads, phase, dropout_p, seed, as_stream(stream));
   MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: the fp32 parity mode runs without dropout (use the bf16 mode)", dropout_p);
+  MMQG_REQUIRE(!batch->ctx_len && !batch->tgt_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
   Ws w = carve(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
@@ -507,6 +509,7 @@ int mmqg_greedy_decode(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
   if (mode == MMQG_MODE_BF16)
     return greedy_decode_bf16(d, *params, *batch, workspace, workspace_bytes, tokens_out, max_len, as_stream(stream));
+  MMQG_REQUIRE(!batch->ctx_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
   Ws w = carve(d, max_len, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);

@@ -52,6 +52,8 @@ struct Ws16 {
   b16 *xdrop_text[MMQG_MAX_LAYERS], *hdrop_dec[MMQG_MAX_LAYERS];   // dropped layer outputs (inputs of the next layer)
   b16 *m_txt16, *m_vid16;     // bf16 attention memories (what the attention kernels read in this mode)
   uint32_t *flags, *flags_v, *flags_t[MMQG_MAX_LAYERS];
+  int *shift_t, *shift_v;             // variable lengths: first real time step of every sample (text / video)
+  float* row_w;                       // ... and the 0/1 weight of every (target step, sample) loss row
   float *dh_last, *dh_last_l[MMQG_MAX_LAYERS], *dx_emb;
   int Sp, Ep, Vp, Rc;
   size_t bytes;
@@ -135,6 +137,7 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   }
   w.dx_emb = c.take<float>(Rt * d.E);
   for (int l = 0; l + 1 < d.L; ++l) { w.xdrop_text[l] = c.take<b16>(Rt * H); w.hdrop_dec[l] = c.take<b16>(R * H); }
+  w.shift_t = c.take<int>(B); w.shift_v = c.take<int>(B); w.row_w = c.take<float>(R);
   w.m_txt16 = c.take<b16>(B * d.TM * H);
   w.m_vid16 = c.take<b16>(B * d.AM * Hv);
   w.bytes = align_up(c.off, 256);
@@ -199,6 +202,18 @@ static thread_local float g_drop_p = 0.f;
 static thread_local unsigned long long g_drop_seed = 0;
 static thread_local const unsigned long long* g_drop_ctr = nullptr;
 static const int kSidText = 10, kSidDec = 20;
+// variable-length batch of the current call (mmqg_batch.ctx_len / tgt_len / n_frames): off = all null
+struct LenState { bool on = false; const int* shift_t = nullptr; const int* shift_v = nullptr; const float* row_w = nullptr; };
+static thread_local LenState g_len;
+static LenSpec len_text(int t_base, bool mem) { LenSpec l; if (g_len.on) { l.shift = g_len.shift_t; l.t_base = t_base; l.mem_shift = mem ? 1 : 0; } return l; }
+static LenSpec len_video() { LenSpec l; if (g_len.on) { l.shift = g_len.shift_v; l.mem_shift = 1; } return l; }
+static int set_len_state(const mmqg_dims& d, const mmqg_batch& bt, const Ws16& w) {
+  g_len = LenState();
+  if (!(bt.ctx_len || bt.tgt_len || bt.n_frames)) return 0;
+  g_len.on = true; g_len.shift_t = w.shift_t; g_len.shift_v = w.shift_v; g_len.row_w = w.row_w;
+  (void)d;
+  return 0;
+}
 
 // The encoders run on the persistent recurrent kernels when the shape allows it (lstm_persist.cu);
 // MMQG_PERSIST=0 forces the one-GEMM-plus-pointwise-launch-per-step path (for A/B comparison).
@@ -238,14 +253,21 @@ static int pack_rec(const float* w_hh, void* fwd, void* bwd, int B, int H, cudaS
   return pack_whh(w_hh, fwd, bwd, H, st);
 }
 static int rec_fwd(float* gates, float* cs, void* hs, const void* wp, float* mem, long long mem_ld, uint32_t* flags, int T, int B,
-                   int H, cudaStream_t st) {
-  if (persist_kind(B, H) == 2) return lstm_seq_fwd_cluster(gates, cs, hs, wp, mem, mem_ld, T, B, H, st);
-  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, nullptr, mem_ld, flags, T, B, H, 0, st);
+                   int H, cudaStream_t st, LenSpec len = LenSpec()) {
+  if (persist_kind(B, H) == 2) {
+    MMQG_REQUIRE(!len.shift, "variable-length batches are not supported by the cluster kernels (unset MMQG_CLUSTER)");
+    return lstm_seq_fwd_cluster(gates, cs, hs, wp, mem, mem_ld, T, B, H, st);
+  }
+  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, nullptr, mem_ld, flags, T, B, H, 0, st, DropSpec(), true, len);
 }
 static int rec_bwd(const float* acts, const float* cs, void* dg, const void* wp, const float* ext, long long ts, long long ld,
-                   const float* dh_last, const float* dc_last, uint32_t* flags, int T, int B, int H, cudaStream_t st) {
-  if (persist_kind(B, H) == 2) return lstm_seq_bwd_cluster(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, T, B, H, st);
-  return lstm_seq_bwd_persist(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, flags, T, B, H, 0, nullptr, st);
+                   const float* dh_last, const float* dc_last, uint32_t* flags, int T, int B, int H, cudaStream_t st,
+                   LenSpec len = LenSpec()) {
+  if (persist_kind(B, H) == 2) {
+    MMQG_REQUIRE(!len.shift, "variable-length batches are not supported by the cluster kernels (unset MMQG_CLUSTER)");
+    return lstm_seq_bwd_cluster(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, T, B, H, st);
+  }
+  return lstm_seq_bwd_persist(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, flags, T, B, H, 0, nullptr, st, DropSpec(), true, len);
 }
 
 // fp32 parameters -> packed bf16 caches + summed biases + concatenated attention bias.
@@ -382,26 +404,29 @@ static int text_chunks(const mmqg_dims& d) {
 // audio pass-through + video LSTM -> zero-padded attention memories (train.py:155-157)
 static int video_forward16(const mmqg_dims& d, const mmqg_batch& bt, Ws16& w, cudaStream_t st) {
   const int B = d.B, Hv = d.H_v, Gv = 4 * d.H_v;
-  MMQG_CUDA(cudaMemcpy2DAsync(w.m_aud, sizeof(float) * (size_t)d.AM * d.H_a, bt.audio,
-                              sizeof(float) * (size_t)d.T_v * d.H_a, sizeof(float) * (size_t)d.T_v * d.H_a, B,
-                              cudaMemcpyDeviceToDevice, st));
-  // video LSTM (encoder.py:69)
-  MMQG_TRY(cvt_f32_bf16_2d(bt.frames, d.F_v, w.frames16, d.F_v, (long long)B * d.T_v, d.F_v, d.F_v, st));
+  if (g_len.on) {
+    MMQG_REQUIRE(persist_video(d), "variable-length batches need the persistent recurrent kernels (B=%d H_v=%d)", B, Hv);
+    MMQG_TRY(audio_pad(bt.audio, w.m_aud, bt.n_frames, B, d.T_v, d.AM, d.H_a, st));
+    MMQG_CUDA(cudaMemsetAsync(w.m_vid, 0, sizeof(float) * (size_t)B * d.AM * Hv, st));      // rows >= n_frames stay zero
+  } else {
+    MMQG_CUDA(cudaMemcpy2DAsync(w.m_aud, sizeof(float) * (size_t)d.AM * d.H_a, bt.audio,
+                                sizeof(float) * (size_t)d.T_v * d.H_a, sizeof(float) * (size_t)d.T_v * d.H_a, B,
+                                cudaMemcpyDeviceToDevice, st));
+  }
+  // video LSTM (encoder.py:69): frames to time-major bf16 (right-aligned when lengths vary), ONE input
+  // projection over all T_v*B rows, then one persistent launch for the T_v recurrent steps
+  MMQG_TRY(frames_to_time_major_bf16(bt.frames, w.frames16, g_len.on ? g_len.shift_v : nullptr, B, d.T_v, d.F_v, st));
   if (persist_video(d)) {
-    // hoisted input projection (frames are batch-major: one product per frame index), then ONE
-    // persistent launch for all T_v recurrent steps
-    for (int t = 0; t < d.T_v; ++t)
-      MMQG_TRY(Tc(w.frames16 + (size_t)t * d.F_v, d.T_v * d.F_v, false, w.wv_ih, d.F_v, false, B, Gv, d.F_v,
-                  w.acts_v + (size_t)t * B * Gv, Gv).bias(w.bsum_vid).run(st));
+    MMQG_TRY(Tc(w.frames16, d.F_v, false, w.wv_ih, d.F_v, false, d.T_v * B, Gv, d.F_v, w.acts_v, Gv).bias(w.bsum_vid).run(st));
     MMQG_CUDA(cudaMemsetAsync(w.hs_v, 0, sizeof(b16) * (size_t)B * Hv, st));
     MMQG_CUDA(cudaMemsetAsync(w.cs_v, 0, sizeof(float) * (size_t)B * Hv, st));
     tl_ktag = 900;
-    MMQG_TRY(rec_fwd(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags_v, d.T_v, B, Hv, st));
+    MMQG_TRY(rec_fwd(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags_v, d.T_v, B, Hv, st, len_video()));
   } else
   for (int t = 0; t < d.T_v; ++t) {
     StepGemmScope step_scope;
     float* acts = w.acts_v + (size_t)t * B * Gv;
-    Tc g(w.frames16 + (size_t)t * d.F_v, d.T_v * d.F_v, false, w.wv_ih, d.F_v, false, B, Gv, d.F_v, acts, Gv);
+    Tc g(w.frames16 + (size_t)t * B * d.F_v, d.F_v, false, w.wv_ih, d.F_v, false, B, Gv, d.F_v, acts, Gv);
     g.bias(w.bsum_vid);
     if (t > 0) g.second(w.hs_v + (size_t)t * B * Hv, Hv, w.wv_hh, Hv, Hv);
     MMQG_TRY(g.run(st));
@@ -417,6 +442,11 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
   const int B = d.B, H = d.H, G = 4 * d.H;
   MMQG_TRY(embedding_gather_bf16(P.emb, w.idx_ctx, w.x0, w.Ep, d.T_t * B, d.E, w.Ep, d.V, st));
   const int NC = text_chunks(d);
+  if (g_len.on) {     // memory rows beyond a sample's length are the zero padding of train.py:160
+    MMQG_REQUIRE(persist_text(d), "variable-length batches need the persistent recurrent kernels (B=%d H=%d)", B, H);
+    if (NC > 1) MMQG_CUDA(cudaMemsetAsync(w.m_txt16, 0, sizeof(b16) * (size_t)B * d.TM * H, st));
+    else MMQG_CUDA(cudaMemsetAsync(w.m_txt, 0, sizeof(float) * (size_t)B * d.TM * H, st));
+  }
   if (NC > 1) {
     // layers pipelined over NC time chunks, one stream per layer
     MMQG_TRY(g_aux.init());
@@ -456,7 +486,7 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
         MMQG_TRY(lstm_seq_fwd_persist(w.acts_text[l] + (size_t)t0 * B * G, w.cs_text[l] + (size_t)t0 * B * H,
                                       w.hs_text[l] + (size_t)t0 * B * H, w.wtp_f[l],
                                       nullptr, l == d.L - 1 ? w.m_txt16 + (size_t)t0 * H : nullptr, (long long)d.TM * H,
-                                      w.flags_t[l] + (size_t)t0 * n_mt, nT, B, H, c > 0 ? 1 : 0, s, dr, false));
+                                      w.flags_t[l] + (size_t)t0 * n_mt, nT, B, H, c > 0 ? 1 : 0, s, dr, false, len_text(t0, l == d.L - 1)));
         MMQG_CUDA(cudaEventRecord(ev_fwd(l, c), s));
       }
     }
@@ -473,7 +503,7 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
       MMQG_CUDA(cudaMemsetAsync(w.hs_text[l], 0, sizeof(b16) * (size_t)B * H, st));
       MMQG_CUDA(cudaMemsetAsync(w.cs_text[l], 0, sizeof(float) * (size_t)B * H, st));
       MMQG_TRY(rec_fwd(w.acts_text[l], w.cs_text[l], w.hs_text[l], w.wtp_f[l], l == d.L - 1 ? w.m_txt : nullptr,
-                       (long long)d.TM * H, w.flags, d.T_t, B, H, st));
+                       (long long)d.TM * H, w.flags, d.T_t, B, H, st, len_text(0, l == d.L - 1)));
       continue;
     }
     for (int t = 0; t < d.T_t; ++t) {
@@ -522,11 +552,13 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, R = d.T_q * B, Sp = w.Sp, Ep = w.Ep;
 
   g_drop_ctr = w.seed_ctr;
+  MMQG_TRY(set_len_state(d, bt, w));
   mark(0, st);
   if (dropout_p > 0.f) MMQG_TRY(bump_counter(w.seed_ctr, st));     // this call's masks: seed + (calls so far)
   MMQG_TRY(g_aux.init());
   cudaStream_t ax = g_aux.s[AuxStream::NS - 1], lh = g_aux.s[AuxStream::NS - 2];
-  MMQG_TRY(build_indices(bt.context, bt.target, w.idx_ctx, w.idx_dec, w.tgt_tm, B, d.T_t, d.T_q, st));
+  if (g_len.on) MMQG_TRY(prep_lengths(bt.ctx_len, bt.tgt_len, bt.n_frames, w.shift_t, w.shift_v, w.row_w, B, d.T_t, d.T_v, d.T_q, st));
+  MMQG_TRY(build_indices(bt.context, bt.target, w.idx_ctx, w.idx_dec, w.tgt_tm, B, d.T_t, d.T_q, st, g_len.on ? w.shift_t : nullptr));
   // fork: everything the text encoder does not need -- the other weight packs, the video LSTM
   // and the decoder's hoisted embedding-column products over all teacher-forced steps -- runs on
   // an auxiliary stream beside the text encoder and is joined in front of the decoder loop
@@ -557,7 +589,7 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
       const int rc = r0 + n - q0 < w.Rc ? r0 + n - q0 : w.Rc;
       MMQG_TRY(Tc(htop + (size_t)q0 * H, H, false, w.wo, H, false, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(s));
       MMQG_TRY(nll_rows_bf16(w.logits, d.V, w.tgt_tm + q0, w.nll + q0, rc, d.V, dscale, want_grads ? w.dlogits16 : nullptr,
-                             w.Vp, s));
+                             w.Vp, s, g_len.on ? w.row_w + q0 : nullptr));
       if (want_grads) {
         MMQG_TRY(Tc(w.dlogits16, w.Vp, false, w.wo, H, true, rc, H, d.V, w.dhtop + (size_t)q0 * H, H).run(s));
         MMQG_TRY(Tc(w.dlogits16, w.Vp, true, htop + (size_t)q0 * H, H, true, d.V, H, rc, grads->out_w, H).accumulate(!first).run(s));
@@ -649,11 +681,13 @@ int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
   g_drop_p = 0.f;
   g_drop_seed = 0;
   g_drop_ctr = w.seed_ctr;
+  MMQG_TRY(set_len_state(d, bt, w));
   cudaStream_t st;
   MMQG_TRY(g_aux.enter(user, &st));
   const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, Sp = w.Sp, Ep = w.Ep;
   cudaStream_t ax = g_aux.s[AuxStream::NS - 1];
-  MMQG_TRY(build_indices(bt.context, nullptr, w.idx_ctx, nullptr, nullptr, B, d.T_t, 0, st));
+  if (g_len.on) MMQG_TRY(prep_lengths(bt.ctx_len, nullptr, bt.n_frames, w.shift_t, w.shift_v, w.row_w, B, d.T_t, d.T_v, 0, st));
+  MMQG_TRY(build_indices(bt.context, nullptr, w.idx_ctx, nullptr, nullptr, B, d.T_t, 0, st, g_len.on ? w.shift_t : nullptr));
   MMQG_CUDA(cudaEventRecord(g_aux.ev[8], st));
   MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[8], 0));
   MMQG_TRY(pack_weights_rest(d, P, w, ax));
@@ -820,7 +854,7 @@ struct Bwd16 {
     if (persist_video(d)) {
       tl_ktag = 900;
       MMQG_TRY(rec_bwd(w.acts_v, w.cs_v, w.dg_v, w.wvp_b, w.dm_vid, Hv, (long long)d.AM * Hv, nullptr, nullptr, w.flags_v,
-                       d.T_v, B, Hv, st));
+                       d.T_v, B, Hv, st, len_video()));
     } else {
       for (int t = d.T_v - 1; t >= 0; --t) {
         StepGemmScope step_scope;
@@ -837,9 +871,7 @@ struct Bwd16 {
       MMQG_TRY(Tc(w.dg_v + (size_t)B * Gv, Gv, true, w.hs_v + (size_t)B * Hv, Hv, true, Gv, Hv, (d.T_v - 1) * B, Gd.vid_w_hh, Hv).run(st));
     else
       MMQG_CUDA(cudaMemsetAsync(Gd.vid_w_hh, 0, sizeof(float) * (size_t)Gv * Hv, st));
-    for (int t = 0; t < d.T_v; ++t)
-      MMQG_TRY(Tc(w.dg_v + (size_t)t * B * Gv, Gv, true, w.frames16 + (size_t)t * d.F_v, d.T_v * d.F_v, true, Gv, d.F_v, B,
-                  Gd.vid_w_ih, d.F_v).accumulate(t > 0).run(st));
+    MMQG_TRY(Tc(w.dg_v, Gv, true, w.frames16, d.F_v, true, Gv, d.F_v, d.T_v * B, Gd.vid_w_ih, d.F_v).run(st));
     return colsum_bf16(w.dg_v, Gv, Gd.vid_b_ih, Gd.vid_b_hh, d.T_v * B, Gv, 0.f, st);
   }
 
@@ -855,7 +887,7 @@ struct Bwd16 {
       const float* ext = l == L - 1 ? w.dm_txt : w.dx_text;
       const long long ts = l == L - 1 ? H : (long long)B * H, ld = l == L - 1 ? (long long)d.TM * H : H;
       MMQG_TRY(rec_bwd(w.acts_text[l], w.cs_text[l], w.dg_text[l], w.wtp_b[l], ext, ts, ld, w.dh_last, w.dc[l], w.flags,
-                       d.T_t, B, H, st));
+                       d.T_t, B, H, st, len_text(0, l == L - 1)));
     } else {
       for (int t = d.T_t - 1; t >= 0; --t) {
         StepGemmScope step_scope;
@@ -930,7 +962,8 @@ struct Bwd16 {
         tl_ktag = l * 16 + c;
         MMQG_TRY(lstm_seq_bwd_persist(w.acts_text[l] + (size_t)t0 * B * G, w.cs_text[l] + (size_t)t0 * B * H,
                                       w.dg_text[l] + (size_t)t0 * B * G, w.wtp_b[l], ext, ts, ld, tail ? w.dh_last_l[l] : nullptr,
-                                      w.dc[l], w.flags_t[l] + (size_t)t0 * n_mt, nT, B, H, tail ? 0 : 1, w.dc[l], s, dr, false));
+                                      w.dc[l], w.flags_t[l] + (size_t)t0 * n_mt, nT, B, H, tail ? 0 : 1, w.dc[l], s, dr, false,
+                                      len_text(t0, l == L - 1)));
         // input gradient of this chunk (what the layer below waits for) on the product stream
         float* dx = l == 0 ? w.dx_emb + (size_t)t0 * B * E : w.dx_text + (size_t)t0 * B * H;
         cudaStream_t gs = split_products() ? g_aux.g[l] : s;
@@ -977,6 +1010,7 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   Ws16 w = carve16(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   g_drop_ctr = w.seed_ctr;      // unchanged since the forward of this step: the same masks
+  MMQG_TRY(set_len_state(d, bt, w));      // shift arrays were filled by the forward of this step
   Bwd16 b(d, P, bt, w, Gd);
   if (phase == 1) {
     MMQG_TRY(b.dec_loop(st));

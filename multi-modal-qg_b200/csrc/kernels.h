@@ -22,7 +22,7 @@ int argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_str
 int colsum(const float* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
 int add2(const float* a, const float* b, float* y, int n, cudaStream_t st);
 int build_indices(const int64_t* ctx, const int64_t* tgt, int64_t* idx_ctx, int64_t* idx_dec, int64_t* tgt_tm, int B,
-                  int T_t, int T_q, cudaStream_t st);
+                  int T_t, int T_q, cudaStream_t st, const int* shift_t = nullptr);
 int sum_scale(const float* x, int n, float scale, float* out, cudaStream_t st);
 int fill_i64(int64_t* p, int n, int64_t v, cudaStream_t st);
 
@@ -87,19 +87,33 @@ int bump_counter(unsigned long long* ctr, cudaStream_t st);
 int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, const unsigned long long* ctr, int sid, unsigned long long base,
                       float p, cudaStream_t st);
 int reduce_partials(const float* part, int n_part, long long stride, float* out, int ldo, long long rows, int N, cudaStream_t st);
+// variable-length batches (mmqg_batch.ctx_len / tgt_len / n_frames), pointwise_bf16.cu
+int prep_lengths(const int* ctx_len, const int* tgt_len, const int* n_frames, int* shift_t, int* shift_v, float* row_w, int B,
+                 int T_t, int T_v, int T_q, cudaStream_t st);
+int frames_to_time_major_bf16(const float* frames, void* out, const int* shift_v, int B, int T_v, int F, cudaStream_t st);
+int audio_pad(const float* audio, float* m_aud, const int* n_frames, int B, int T_v, int AM, int H_a, cudaStream_t st);
 int dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, cudaStream_t st);
 // persistent recurrent-cell kernels (lstm_persist.cu)
 bool lstm_persist_ok(int B, int H);
 int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st);
+// Variable-length batches in the persistent recurrent kernels: sample (row) m is right-aligned in time,
+// its steps t_base + t < shift[m] are masked (state held at zero, no gradient); with mem_shift the
+// batch-major memory output (forward) / external gradient input (backward) is indexed by the
+// sample's own position t_base + t - shift[m] instead of the time step.
+struct LenSpec {
+  const int* shift = nullptr;
+  int t_base = 0;
+  int mem_shift = 0;
+};
 extern thread_local int tl_ktag;      // debug: tag of the next persistent recurrent launch (lstm_persist.cu)
 int sum_partials(const float* a, int na, const float* b, int nb, long long stride, float* y, int n, cudaStream_t st);
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,
                          uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st, DropSpec dr = DropSpec(),
-                         bool zero_flags = true);
+                         bool zero_flags = true, LenSpec len = LenSpec());
 int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
                          int T, int B, int H, int has_next, float* dc_out, cudaStream_t st, DropSpec dr = DropSpec(),
-                         bool zero_flags = true);
+                         bool zero_flags = true, LenSpec len = LenSpec());
 // cluster variant (lstm_cluster.cu): cluster barrier + TMA multicast instead of global flags
 bool lstm_cluster_ok(int B, int H);
 int pack_whh_cluster(const float* w_hh, void* fwd_packed, int H, cudaStream_t st);
@@ -120,7 +134,7 @@ int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_ba
                         size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
                         cudaStream_t st, cudaEvent_t const* ready = nullptr);
 int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* nll, int R, int V, float scale,
-                  void* dlogits, int lddl, cudaStream_t st);
+                  void* dlogits, int lddl, cudaStream_t st, const float* row_w = nullptr);
 int attn_fwd(float* scores, int lds, const float* M_txt, const float* M_aud, const float* M_vid, float* ctx,
              int ldctx, const AttnShape& s, cudaStream_t st);
 int attn_bwd(const float* attn, float* ds_out, int lds, const float* dctx, int lddctx, const float* M_txt,

@@ -116,6 +116,43 @@ __device__ __forceinline__ int ktrace_begin(long long* buf, int tag) {
 }
 __device__ __forceinline__ void ktrace_end(long long* buf, int slot) { buf[3 + 3 * slot] = gtime(); }
 
+// ---- per-row shifted variants for variable-length batches: row r of the warp belongs to a sample whose
+// shift `sh` lives in lane r; element rows are addressed by (time - shift), masked rows are skipped / zero.
+__device__ __forceinline__ void coop_ldg_shift(const float* base, size_t row_stride, int rows_valid, int lane, float4 (&v)[4], int sh,
+                                               int tg, long long ts) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    const int shr = __shfl_sync(0xffffffffu, sh, r);
+    v[i] = (r < rows_valid && tg >= shr)
+               ? *reinterpret_cast<const float4*>(base + (size_t)r * row_stride - (long long)shr * ts + 4 * (lane & 3))
+               : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void coop_stg_shift(float* base, size_t row_stride, int rows_valid, int lane, const float4 (&v)[4], int sh,
+                                               int tg, long long ts) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    const int shr = __shfl_sync(0xffffffffu, sh, r);
+    if (r < rows_valid && tg >= shr) *reinterpret_cast<float4*>(base + (size_t)r * row_stride - (long long)shr * ts + 4 * (lane & 3)) = v[i];
+  }
+}
+__device__ __forceinline__ void row_bf16_to_global_shift(uint32_t* stg, int lane, const uint32_t (&w8)[8], bf16* base, size_t row_stride,
+                                                         int rows_valid, int sh, int tg, long long ts) {
+  __syncwarp();
+  *reinterpret_cast<uint4*>(stg + lane * 12) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+  *reinterpret_cast<uint4*>(stg + lane * 12 + 4) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = 16 * i + (lane >> 1), hsel = lane & 1;
+    const int shr = __shfl_sync(0xffffffffu, sh, r);
+    const uint4 x = *reinterpret_cast<const uint4*>(stg + r * 12 + 4 * hsel);
+    if (r < rows_valid && tg >= shr) *reinterpret_cast<uint4*>(base + (size_t)r * row_stride - (long long)shr * ts + 8 * hsel) = x;
+  }
+}
+
 struct LstmFwdP {
   float* gates;        // (T*B, 4H) fp32: in = x W_ih^T + b (hoisted), out = activated gates i,f,g,o
   float* cs;           // ((T+1)*B, H) fp32; slab t+1 receives c_t (slab 0 is not read: c_{-1} = 0)
@@ -129,6 +166,7 @@ struct LstmFwdP {
   long long* trace;    // debug: per-step clock64 stamps of CTA (0,0), 8 per step (nullable)
   long long* ktrace; int ktag;   // debug: kernel-level timeline (see mmqg_debug_ktrace)
   DropSpec dr;         // dr.out: optional dropped bf16 copy of h_t, (T*B, H) rows t*B+b (input of the next layer)
+  LenSpec len;
 };
 
 __global__ void __launch_bounds__(160, 1)
@@ -206,6 +244,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     float* stg = reinterpret_cast<float*>(sA + p.KB * 16384) + warp * STG_WARP;
     const bool kt = p.ktrace && row == 0 && slice == 0 && mt == 0;
     const int kslot = kt ? ktrace_begin(p.ktrace, p.ktag) : 0;
+    const int sh = (p.len.shift && valid) ? p.len.shift[m] : 0;       // variable lengths: first real step of this row
     float c[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) c[u] = 0.f;
@@ -249,6 +288,11 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         hv[u] = og * tanh_fast(c[u]);
         acc[u] = ig; acc[16 + u] = fg; acc[32 + u] = gg; acc[48 + u] = og;
       }
+      const int tg = p.len.t_base + t;
+      if (tg < sh) {          // before the sample's first token: the state stays at its zero initial value
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { c[u] = 0.f; hv[u] = 0.f; }
+      }
       // h_t first: it is the only thing the other CTAs are waiting for
       uint32_t hp[8];
 #pragma unroll
@@ -277,13 +321,20 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         }
         row_to_coop(stg, lane, c, tmp);
         coop_stg(p.cs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid, lane, tmp);
+        const bool shifted = p.len.shift && p.len.mem_shift;      // memory row = the sample's own position
         if (p.mem) {
           row_to_coop(stg, lane, hv, tmp);
-          coop_stg(p.mem + (size_t)m0w * p.mem_ld + (size_t)t * H + j0, (size_t)p.mem_ld, rows_valid, lane, tmp);
+          if (shifted) coop_stg_shift(p.mem + (size_t)m0w * p.mem_ld + (size_t)t * H + j0, (size_t)p.mem_ld, rows_valid, lane, tmp, sh, tg, H);
+          else coop_stg(p.mem + (size_t)m0w * p.mem_ld + (size_t)t * H + j0, (size_t)p.mem_ld, rows_valid, lane, tmp);
         }
-        if (p.mem16)
-          row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.mem16 + (size_t)m0w * p.mem_ld + (size_t)t * H + j0,
-                             (size_t)p.mem_ld, rows_valid);
+        if (p.mem16) {
+          if (shifted)
+            row_bf16_to_global_shift(reinterpret_cast<uint32_t*>(stg), lane, hp, p.mem16 + (size_t)m0w * p.mem_ld + (size_t)t * H + j0,
+                                     (size_t)p.mem_ld, rows_valid, sh, tg, H);
+          else
+            row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.mem16 + (size_t)m0w * p.mem_ld + (size_t)t * H + j0,
+                               (size_t)p.mem_ld, rows_valid);
+        }
         if (p.dr.out) {       // inter-layer dropout: the next layer reads this copy
           const float ik = 1.0f / (1.0f - p.dr.p);
           const unsigned long long sd = p.dr.seed + (p.dr.ctr ? *p.dr.ctr : 0ull);
@@ -326,6 +377,7 @@ struct LstmBwdP {
   float* dc_out;        // (B,H) receives d loss / d c_{-1} at the end (nullable)
   long long* ktrace; int ktag;
   DropSpec dr;          // dr.p > 0: dh_ext is the gradient w.r.t. the DROPPED h_t -> multiplied by the mask here
+  LenSpec len;
 };
 
 static constexpr int BWD_STAGES = 6;     // 144 KB in flight: the streaming rate is ring bytes / TMA round trip
@@ -411,6 +463,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     float* stg = reinterpret_cast<float*>(sA + BWD_STAGES * 16384) + warp * STG_WARP;
     const bool kt = p.ktrace && row == 0 && slice == 0 && mt == 0;
     const int kslot = kt ? ktrace_begin(p.ktrace, p.ktag) : 0;
+    const int sh = (p.len.shift && valid) ? p.len.shift[m] : 0;
     float dc[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) dc[u] = (p.dc_last && valid) ? p.dc_last[(size_t)m * H + j0 + u] : 0.f;
@@ -424,7 +477,10 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       for (int g = 0; g < 4; ++g) coop_ldg(abase + g * H, G, rows_valid, lane, a4[g]);
       coop_ldg(p.cs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid, lane, cn4);
       coop_ldg(p.cs + ((size_t)t * B + m0w) * H + j0, H, rows_valid, lane, cp4);
-      if (p.dh_ext) coop_ldg(p.dh_ext + (size_t)t * p.ext_ts + (size_t)m0w * p.ext_ld + j0, (size_t)p.ext_ld, rows_valid, lane, ex4);
+      const int tg = p.len.t_base + t;
+      if (p.dh_ext && p.len.shift && p.len.mem_shift)
+        coop_ldg_shift(p.dh_ext + (size_t)t * p.ext_ts + (size_t)m0w * p.ext_ld + j0, (size_t)p.ext_ld, rows_valid, lane, ex4, sh, tg, p.ext_ts);
+      else if (p.dh_ext) coop_ldg(p.dh_ext + (size_t)t * p.ext_ts + (size_t)m0w * p.ext_ld + j0, (size_t)p.ext_ld, rows_valid, lane, ex4);
       else {
 #pragma unroll
         for (int i2 = 0; i2 < 4; ++i2) ex4[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -468,6 +524,12 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           dgv[32 + u] = dct * ig * (1.f - gg * gg);
           dgv[48 + u] = d * tc_ * og * (1.f - og);
           dc[u] = dct * fg;
+        }
+        if (tg < sh) {        // masked step: no gradient reaches the weights or anything earlier
+#pragma unroll
+          for (int u = 0; u < 64; ++u) dgv[u] = 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) dc[u] = 0.f;
         }
         bf16* dbase = p.dg + ((size_t)t * B + m0w) * G + j0;
 #pragma unroll
@@ -591,9 +653,9 @@ static int launch_coop(Kern kern, dim3 grid, int threads, size_t smem, const CUt
 
 // gates: (T*B,4H) fp32 pre-gates -> activated gates.  wp_fwd: pack_whh forward layout.  hs slab 0 must be zeros.
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,
-                         uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st, DropSpec dr, bool zero_flags) {
+                         uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st, DropSpec dr, bool zero_flags, LenSpec len) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
-  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, reinterpret_cast<bf16*>(mem16), mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace, g_ktrace, tl_ktag, dr};
+  LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, reinterpret_cast<bf16*>(mem16), mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace, g_ktrace, tl_ktag, dr, len};
   CUtensorMap tmW, tmH;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_fwd, 4 * (uint64_t)H, H, H, 64, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmH, hs, (uint64_t)(T + 1) * B, H, H, 128, 64));
@@ -613,10 +675,10 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
 
 int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
-                         int T, int B, int H, int has_next, float* dc_out, cudaStream_t st, DropSpec dr, bool zero_flags) {
+                         int T, int B, int H, int has_next, float* dc_out, cudaStream_t st, DropSpec dr, bool zero_flags, LenSpec len) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_bwd_persist: shape B=%d H=%d not supported", B, H);
   LstmBwdP p{acts, cs, reinterpret_cast<bf16*>(dg), dh_ext, ext_ts, ext_ld, dh_last, dc_last, flags,
-             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64, has_next, dc_out, g_ktrace, 1000 + tl_ktag, dr};
+             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64, has_next, dc_out, g_ktrace, 1000 + tl_ktag, dr, len};
   CUtensorMap tmW, tmG;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_bwd, H, 4 * (uint64_t)H, 4 * (uint64_t)H, 16, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmG, dg, (uint64_t)(T + (has_next ? 1 : 0)) * B, 4 * (uint64_t)H, 4 * (uint64_t)H, 128, 64));

@@ -204,11 +204,15 @@ __global__ void add2_kernel(const float* __restrict__ a, const float* __restrict
 //   idx_ctx(t*B+b) = context(b,t);  idx_dec(t*B+b) = t==0 ? <start> : target(b,t-1);  tgt_tm(t*B+b) = target(b,t)
 __global__ void build_indices_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict__ tgt,
                                      int64_t* __restrict__ idx_ctx, int64_t* __restrict__ idx_dec,
-                                     int64_t* __restrict__ tgt_tm, int B, int T_t, int T_q) {
+                                     int64_t* __restrict__ tgt_tm, int B, int T_t, int T_q,
+                                     const int* __restrict__ shift_t) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * T_t) {
     int t = i / B, b = i % B;
-    idx_ctx[i] = ctx[(size_t)b * T_t + t];
+    // variable lengths: sample b is right-aligned in time (its first token sits at t = shift_t[b]);
+    // the steps before it are masked in the recurrent kernels, any valid index will do there
+    const int sh = shift_t ? shift_t[b] : 0;
+    idx_ctx[i] = t >= sh ? ctx[(size_t)b * T_t + t - sh] : 0;
   }
   if (tgt && i < B * T_q) {
     int t = i / B, b = i % B;
@@ -304,9 +308,9 @@ int add2(const float* a, const float* b, float* y, int n, cudaStream_t st) {
 }
 
 int build_indices(const int64_t* ctx, const int64_t* tgt, int64_t* idx_ctx, int64_t* idx_dec, int64_t* tgt_tm, int B,
-                  int T_t, int T_q, cudaStream_t st) {
+                  int T_t, int T_q, cudaStream_t st, const int* shift_t) {
   int n = B * (T_t > T_q ? T_t : T_q);
-  build_indices_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ctx, tgt, idx_ctx, idx_dec, tgt_tm, B, T_t, T_q);
+  build_indices_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ctx, tgt, idx_ctx, idx_dec, tgt_tm, B, T_t, T_q, shift_t);
   MMQG_LAUNCH_CHECK();
   return 0;
 }

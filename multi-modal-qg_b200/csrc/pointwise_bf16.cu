@@ -159,7 +159,7 @@ __device__ __forceinline__ float wsum_(float v) {
 __global__ void __launch_bounds__(256) nll_rows_bf16_kernel(const float* __restrict__ logits, int ldl,
                                                             const int64_t* __restrict__ targets,
                                                             float* __restrict__ nll, int R, int V, float scale,
-                                                            bf16* __restrict__ dl, int lddl) {
+                                                            bf16* __restrict__ dl, int lddl, const float* __restrict__ row_w) {
   __shared__ float sh[8];
   const int r = blockIdx.x, tid = threadIdx.x;
   const float* x = logits + (size_t)r * ldl;
@@ -181,11 +181,77 @@ __global__ void __launch_bounds__(256) nll_rows_bf16_kernel(const float* __restr
   const float lse = m + logf(s);
   long long t = targets[r];
   t = t < 0 ? 0 : (t >= V ? V - 1 : t);
-  if (tid == 0) nll[r] = lse - x[t];
+  const float wr = row_w ? row_w[r] : 1.f;      // 0 for target steps beyond the sample's length
+  if (tid == 0) nll[r] = wr * (lse - x[t]);
   if (dl) {
     bf16* d = dl + (size_t)r * lddl;
-    for (int v = tid; v < V; v += 256) d[v] = __float2bfloat16_rn(scale * (expf(x[v] - lse) - (v == t ? 1.f : 0.f)));
+    const float sc = scale * wr;
+    for (int v = tid; v < V; v += 256) d[v] = __float2bfloat16_rn(sc * (expf(x[v] - lse) - (v == t ? 1.f : 0.f)));
   }
+}
+
+// ---- variable-length batches (mmqg_batch.ctx_len / tgt_len / n_frames) -----------------------------
+// Sequences are RIGHT-aligned in time inside the fixed (T, B) layout: sample b's first real step is
+// t = shift[b] = T - len[b], so every sample's final state sits at t = T-1 (what the decoder takes
+// over) and the masked steps before it simply hold the zero initial state.
+__global__ void prep_lengths_kernel(const int* __restrict__ ctx_len, const int* __restrict__ tgt_len, const int* __restrict__ n_frames,
+                                    int* __restrict__ shift_t, int* __restrict__ shift_v, float* __restrict__ row_w, int B, int T_t,
+                                    int T_v, int T_q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    const int cl = ctx_len ? min(max(ctx_len[i], 1), T_t) : T_t;
+    const int nf = n_frames ? min(max(n_frames[i], 1), T_v) : T_v;
+    shift_t[i] = T_t - cl;
+    shift_v[i] = T_v - nf;
+  }
+  if (i < B * T_q) {
+    const int t = i / B, b = i % B;
+    const int tl = tgt_len ? min(max(tgt_len[b], 1), T_q) : T_q;
+    row_w[i] = t < tl ? 1.f : 0.f;
+  }
+}
+int prep_lengths(const int* ctx_len, const int* tgt_len, const int* n_frames, int* shift_t, int* shift_v, float* row_w, int B,
+                 int T_t, int T_v, int T_q, cudaStream_t st) {
+  const int n = B * (T_q > 1 ? T_q : 1);
+  prep_lengths_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx_len, tgt_len, n_frames, shift_t, shift_v, row_w, B, T_t, T_v, T_q);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+// frames (B, T_v, F) fp32 batch-major -> (T_v*B, F) bf16 time-major, right-aligned by shift_v (zeros before)
+__global__ void frames_tm_kernel(const float* __restrict__ frames, bf16* __restrict__ out, const int* __restrict__ shift_v, int B,
+                                 int T_v, int F) {
+  const int row = blockIdx.x;                 // t*B + b
+  const int t = row / B, b = row % B;
+  const int sh = shift_v ? shift_v[b] : 0;
+  bf16* dst = out + (size_t)row * F;
+  if (t < sh) {
+    for (int f = threadIdx.x; f < F; f += blockDim.x) dst[f] = __float2bfloat16_rn(0.f);
+  } else {
+    const float* src = frames + ((size_t)b * T_v + (t - sh)) * F;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) dst[f] = __float2bfloat16_rn(src[f]);
+  }
+}
+int frames_to_time_major_bf16(const float* frames, void* out, const int* shift_v, int B, int T_v, int F, cudaStream_t st) {
+  frames_tm_kernel<<<B * T_v, 256, 0, st>>>(frames, reinterpret_cast<bf16*>(out), shift_v, B, T_v, F);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+// audio (B, T_v, H_a) -> zero-padded memory (B, AM, H_a); rows >= n_frames[b] are zero (train.py:156)
+__global__ void audio_pad_kernel(const float* __restrict__ audio, float* __restrict__ m_aud, const int* __restrict__ n_frames, int B,
+                                 int T_v, int AM, int H_a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * AM * H_a) return;
+  const int h = (int)(i % H_a);
+  const int k = (int)((i / H_a) % AM);
+  const int b = (int)(i / ((long long)H_a * AM));
+  const int nf = n_frames ? min(max(n_frames[b], 1), T_v) : T_v;
+  m_aud[i] = k < nf ? audio[((size_t)b * T_v + k) * H_a + h] : 0.f;
+}
+int audio_pad(const float* audio, float* m_aud, const int* n_frames, int B, int T_v, int AM, int H_a, cudaStream_t st) {
+  const long long n = (long long)B * AM * H_a;
+  audio_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(audio, m_aud, n_frames, B, T_v, AM, H_a);
+  MMQG_LAUNCH_CHECK();
+  return 0;
 }
 
 __global__ void bump_counter_kernel(unsigned long long* ctr) { *ctr += 1ull; }
@@ -335,10 +401,10 @@ int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, f
 }
 
 int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* nll, int R, int V, float scale,
-                  void* dlogits, int lddl, cudaStream_t st) {
+                  void* dlogits, int lddl, cudaStream_t st, const float* row_w) {
   MMQG_REQUIRE(logits && targets && nll && R > 0 && V > 0, "nll_rows_bf16: bad args");
   MMQG_PROBE(KC_LOSS, 0, 4.0 * R * V + (dlogits ? 2.0 * R * V : 0));
-  nll_rows_bf16_kernel<<<R, 256, 0, st>>>(logits, ldl, targets, nll, R, V, scale, reinterpret_cast<bf16*>(dlogits), lddl);
+  nll_rows_bf16_kernel<<<R, 256, 0, st>>>(logits, ldl, targets, nll, R, V, scale, reinterpret_cast<bf16*>(dlogits), lddl, row_w);
   MMQG_LAUNCH_CHECK();
   return 0;
 }

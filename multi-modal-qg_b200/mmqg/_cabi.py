@@ -29,7 +29,8 @@ class MmqgTensors(C.Structure):
 
 
 class MmqgBatch(C.Structure):
-    _fields_ = [("context", _fp), ("target", _fp), ("frames", _fp), ("audio", _fp)]
+    _fields_ = [("context", _fp), ("target", _fp), ("frames", _fp), ("audio", _fp),
+                ("ctx_len", _fp), ("tgt_len", _fp), ("n_frames", _fp)]
 
 
 class MmqgGemmArgs(C.Structure):
@@ -102,7 +103,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.mmqg_abi_version() != 1:
+        if L.mmqg_abi_version() != 2:
             raise MmqgError("libmmqg.so ABI version mismatch")
         _lib = L
     return _lib

@@ -69,10 +69,12 @@ class TrainEngine:
         self.seed = 0          # base dropout seed; the library adds the number of forward calls made so far
 
     # -- batches -------------------------------------------------------------------------
+    LENGTH_KEYS = ("ctx_len", "tgt_len", "n_frames")
+
     def to_device(self, batch: dict, non_blocking=False) -> dict:
         out = {}
         for k, v in batch.items():
-            want = torch.int64 if k in ("context", "target") else torch.float32
+            want = torch.int64 if k in ("context", "target") else (torch.int32 if k in self.LENGTH_KEYS else torch.float32)
             out[k] = v.to(self.device, want, non_blocking=non_blocking).contiguous()
         return out
 
@@ -83,8 +85,13 @@ class TrainEngine:
         for k, v in b.items():
             assert v.is_cuda and v.is_contiguous(), k
         tgt = b.get("target")
+        lens = []
+        for k in self.LENGTH_KEYS:                       # optional per-sample lengths, int32 (B)
+            v = b.get(k)
+            assert v is None or (v.dtype == torch.int32 and tuple(v.shape) == (d.B,)), k
+            lens.append(0 if v is None else v.data_ptr())
         return _cabi.MmqgBatch(b["context"].data_ptr(), 0 if tgt is None else tgt.data_ptr(),
-                               b["frames"].data_ptr(), b["audio"].data_ptr())
+                               b["frames"].data_ptr(), b["audio"].data_ptr(), *lens)
 
     # -- train step ----------------------------------------------------------------------
     def forward(self, batch, want_grads=True, grad_scale=1.0):

@@ -141,13 +141,33 @@ def teacher_forced_loss(p, batch, L, TM, AM, return_steps=False, drop=None):
     return loss
 
 
+def teacher_forced_loss_varlen(p, batch, L, TM, AM):
+    """Batch with per-sample lengths (batch["ctx_len"], ["tgt_len"], ["n_frames"], each (B) or absent):
+    literally the reference's per-sample loop (train.py:153-177) on every sample cut to its own
+    lengths; loss = mean over samples of the per-sample summed cross entropy."""
+    B = batch["context"].shape[0]
+    total = 0
+    for b in range(B):
+        cl = int(batch["ctx_len"][b]) if "ctx_len" in batch else batch["context"].shape[1]
+        tl = int(batch["tgt_len"][b]) if "tgt_len" in batch else batch["target"].shape[1]
+        nf = int(batch["n_frames"][b]) if "n_frames" in batch else batch["frames"].shape[1]
+        one = {"context": batch["context"][b:b + 1, :cl], "target": batch["target"][b:b + 1, :tl],
+               "frames": batch["frames"][b:b + 1, :nf], "audio": batch["audio"][b:b + 1, :nf]}
+        total = total + teacher_forced_loss(p, one, L, TM, AM)
+    return total / B
+
+
 def loss_and_grads(params, batch, L, TM, AM, dtype=torch.float64, drop=None):
     """Loss and d loss / d every parameter, computed in `dtype` on the CPU."""
     p = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in params.items()}
     b = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in batch.items()}
     if drop is not None:
         drop = {k: v.to(dtype) for k, v in drop.items()}
-    loss = teacher_forced_loss(p, b, L, TM, AM, drop=drop)
+    if any(k in b for k in ("ctx_len", "tgt_len", "n_frames")):
+        assert drop is None, "variable lengths and dropout masks are not combined in the oracle"
+        loss = teacher_forced_loss_varlen(p, b, L, TM, AM)
+    else:
+        loss = teacher_forced_loss(p, b, L, TM, AM, drop=drop)
     names = list(p)
     grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
     g = {n: (torch.zeros_like(p[n]) if gr is None else gr).detach() for n, gr in zip(names, grads)}

@@ -26,13 +26,13 @@ def test_header_symbols_all_exported(cabi):
     for name in declared:
         assert hasattr(L, name), f"{name} declared in mmqg.h but not exported"
     assert declared == set(cabi.SYMBOLS), declared ^ set(cabi.SYMBOLS)
-    assert L.mmqg_abi_version() == 1
+    assert L.mmqg_abi_version() == 2
 
 
 def test_struct_layouts(cabi):
     assert C.sizeof(cabi.MmqgDims) == 13 * 4
     assert C.sizeof(cabi.MmqgTensors) == 8 * (1 + 4 * 4 + 4 + 6 + 4 * 4 + 2)
-    assert C.sizeof(cabi.MmqgBatch) == 32
+    assert C.sizeof(cabi.MmqgBatch) == 56      # 4 tensors + 3 optional length arrays
 
 
 def test_workspace_and_validation_without_gpu(cabi):

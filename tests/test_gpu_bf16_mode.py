@@ -197,3 +197,55 @@ def test_bf16_greedy_decode_follows_oracle_until_a_near_tie(eng_mod):
             assert float(margins[b, int(diff[0])]) < 0.5, (b, toks[b], ref[b], margins[b])
     assert exact_rows >= d.B // 2, exact_rows
     assert toks.min() >= 0 and toks.max() < d.V
+
+
+@pytest.mark.parametrize("T_t,chunks", [(12, "1"), (33, "3")])
+def test_bf16_variable_lengths_match_per_sample_oracle(eng_mod, T_t, chunks, monkeypatch):
+    """mmqg_batch.ctx_len / tgt_len / n_frames: the batched step must equal the reference's per-sample
+    loop with every sample cut to its own lengths (oracle teacher_forced_loss_varlen), on both the
+    one-launch-per-layer and the chunk-pipelined schedule.  Same bf16 tolerances."""
+    from oracle import mmqg_oracle as O
+    monkeypatch.setenv("MMQG_CHUNKS", chunks)
+    d = Dims(B=10, T_t=T_t, T_v=4, T_q=5, V=300, E=52, H=64, L=2, H_a=24, H_v=64, F_v=40, TM=T_t + 3, AM=6)
+    params = make_params(d, seed=101)
+    batch = make_batch(d, seed=102)
+    g = torch.Generator().manual_seed(5)
+    batch["ctx_len"] = torch.randint(1, T_t + 1, (d.B,), generator=g, dtype=torch.int32)
+    batch["tgt_len"] = torch.randint(1, d.T_q + 1, (d.B,), generator=g, dtype=torch.int32)
+    batch["n_frames"] = torch.randint(1, d.T_v + 1, (d.B,), generator=g, dtype=torch.int32)
+    batch["ctx_len"][0], batch["tgt_len"][0], batch["n_frames"][0] = T_t, d.T_q, d.T_v      # one full-length sample
+    batch["ctx_len"][1], batch["tgt_len"][1], batch["n_frames"][1] = 1, 1, 1                # and one minimal
+    loss_ref, grads_ref = O.loss_and_grads(round_params_bf16(params), batch, d.L, d.TM, d.AM, torch.float64)
+    loss_full, _ = O.loss_and_grads(round_params_bf16(params), {k: v for k, v in batch.items() if not k.endswith("len") and k != "n_frames"},
+                                    d.L, d.TM, d.AM, torch.float64)
+    eng = eng_mod.TrainEngine(d, params, mode="bf16")
+    loss = float(eng.step(eng.to_device(batch)))
+    torch.cuda.synchronize()
+    assert abs(float(loss_ref) - float(loss_full)) > 0.05 * abs(float(loss_full))       # the lengths matter
+    assert abs(loss - float(loss_ref)) < LOSS_TOL * abs(float(loss_ref)), (loss, float(loss_ref), float(loss_full))
+    errs = {k: rel(eng.grads[k], g) for k, g in grads_ref.items()}
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print("varlen worst grad rel err", worst)
+    assert worst[1] < GRAD_TOL, errs
+    # full lengths given explicitly == no lengths given
+    full = {k: v for k, v in batch.items()}
+    full["ctx_len"] = torch.full((d.B,), T_t, dtype=torch.int32)
+    full["tgt_len"] = torch.full((d.B,), d.T_q, dtype=torch.int32)
+    full["n_frames"] = torch.full((d.B,), d.T_v, dtype=torch.int32)
+    l_full = float(eng.step(eng.to_device(full)))
+    g_full = {k: v.clone() for k, v in eng.grads.items()}
+    plain = {k: v for k, v in batch.items() if k not in ("ctx_len", "tgt_len", "n_frames")}
+    l_plain = float(eng.step(eng.to_device(plain)))
+    assert abs(l_full - l_plain) < 1e-5 * abs(l_plain)
+    for k in g_full:
+        assert rel(g_full[k], eng.grads[k]) < 1e-4, k
+
+
+def test_fp32_mode_rejects_lengths(eng_mod):
+    from mmqg import _cabi
+    d = Dims(B=2, T_t=3, T_v=2, T_q=2, V=11, E=10, H=12, L=2, H_a=6, H_v=12, F_v=10, TM=4, AM=3)
+    eng = eng_mod.TrainEngine(d, make_params(d), mode="fp32")
+    b = make_batch(d)
+    b["ctx_len"] = torch.tensor([2, 3], dtype=torch.int32)
+    with pytest.raises(_cabi.MmqgError):
+        eng.step(eng.to_device(b))
