@@ -249,3 +249,30 @@ def test_fp32_mode_rejects_lengths(eng_mod):
     b["ctx_len"] = torch.tensor([2, 3], dtype=torch.int32)
     with pytest.raises(_cabi.MmqgError):
         eng.step(eng.to_device(b))
+
+
+def test_bf16_greedy_decode_with_lengths(eng_mod):
+    """Greedy decode honours ctx_len / n_frames: each row equals the oracle run on that sample alone,
+    cut to its own lengths (up to the first near-tie)."""
+    from oracle import mmqg_oracle as O
+    d = Dims(B=8, T_t=14, T_v=4, T_q=5, V=400, E=52, H=64, L=2, H_a=24, H_v=64, F_v=40, TM=16, AM=6)
+    params = make_params(d, seed=111, bias_scale=0.1, out_weight_scale=10.0)
+    batch = make_batch(d, seed=112)
+    g = torch.Generator().manual_seed(9)
+    batch["ctx_len"] = torch.randint(1, d.T_t + 1, (d.B,), generator=g, dtype=torch.int32)
+    batch["n_frames"] = torch.randint(1, d.T_v + 1, (d.B,), generator=g, dtype=torch.int32)
+    eng = eng_mod.TrainEngine(d, params, mode="bf16")
+    toks = eng.greedy(eng.to_device(batch), 6).cpu()
+    rp = round_params_bf16(params)
+    exact = 0
+    for b in range(d.B):
+        cl, nf = int(batch["ctx_len"][b]), int(batch["n_frames"][b])
+        one = {"context": batch["context"][b:b + 1, :cl], "target": batch["target"][b:b + 1],
+               "frames": batch["frames"][b:b + 1, :nf], "audio": batch["audio"][b:b + 1, :nf]}
+        ref, margins = O.greedy_decode(rp, one, d.L, d.TM, d.AM, 6, torch.float64, return_margins=True)
+        diff = (toks[b] != ref[0]).nonzero()
+        if diff.numel() == 0:
+            exact += 1
+        else:
+            assert float(margins[0, int(diff[0])]) < 0.5, (b, toks[b], ref[0], margins[0])
+    assert exact >= d.B // 2, exact
