@@ -146,6 +146,13 @@ int mmqg_train_backward(const mmqg_dims* d, const mmqg_tensors* params, const mm
                         void* workspace, size_t workspace_bytes, mmqg_tensors* grads,
                         int phase, float dropout_p, unsigned long long seed, int mode, void* stream);
 
+/* Same decode loop with the reference's 'sampling' strategy (evaluate.py:84-90): every step draws
+ * the next token from softmax(logits) instead of taking the arg-max ('topk' in the reference is
+ * topk(1), i.e. greedy).  Deterministic in (seed, step, row). */
+int mmqg_sample_decode(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,
+                       void* workspace, size_t workspace_bytes, int64_t* tokens_out, int max_len,
+                       unsigned long long seed, int mode, void* stream);
+
 /* The whole backward (as phase 0, with its internal overlap) for data-parallel callers:
  * ready_events[i] (a cudaEvent_t created by the caller, or NULL) is recorded at the point
  * where gradient group i+1 (1 decoder, 2 video, 3 text + embedding) is final -- on
@@ -268,6 +275,12 @@ int mmqg_nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_
                   int R, int V, float dlogits_scale, void* stream);
 /* tokens(r) = argmax_v logits(r,v), lowest index on ties (train.py:107-108). */
 int mmqg_argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int R, int V, void* stream);
+/* tokens(r) ~ softmax(logits(r,:)): the reference's 'sampling' strategy (evaluate.py:84-90,
+ * np.random.choice(V, p=softmax)) as an inverse-CDF draw with the uniform u(seed, step, r) that
+ * mmqg_sample_uniform returns (n = R entries of one step) -- for tests and other hosts. */
+int mmqg_sample_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int R, int V,
+                     unsigned long long seed, unsigned long long step, void* stream);
+int mmqg_sample_uniform(float* out, int n, unsigned long long seed, unsigned long long step, void* stream);
 /* out(n) = sum_m X(m,n)  (bias gradients). */
 int mmqg_colsum(const float* X, int ldx, float* out, int M, int N, float beta, void* stream);
 

@@ -499,8 +499,24 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   return 0;
 }
 
+static int decode_impl(const mmqg_dims* dp, const mmqg_tensors* params, const mmqg_batch* batch, void* workspace,
+                       size_t workspace_bytes, int64_t* tokens_out, int max_len, int mode, void* stream, int sample,
+                       unsigned long long seed);
+
 int mmqg_greedy_decode(const mmqg_dims* dp, const mmqg_tensors* params, const mmqg_batch* batch, void* workspace,
                        size_t workspace_bytes, int64_t* tokens_out, int max_len, int mode, void* stream) {
+  return decode_impl(dp, params, batch, workspace, workspace_bytes, tokens_out, max_len, mode, stream, 0, 0);
+}
+
+int mmqg_sample_decode(const mmqg_dims* dp, const mmqg_tensors* params, const mmqg_batch* batch, void* workspace,
+                       size_t workspace_bytes, int64_t* tokens_out, int max_len, unsigned long long seed, int mode,
+                       void* stream) {
+  return decode_impl(dp, params, batch, workspace, workspace_bytes, tokens_out, max_len, mode, stream, 1, seed);
+}
+
+static int decode_impl(const mmqg_dims* dp, const mmqg_tensors* params, const mmqg_batch* batch, void* workspace,
+                       size_t workspace_bytes, int64_t* tokens_out, int max_len, int mode, void* stream, int sample,
+                       unsigned long long seed) {
   MMQG_TRY(check_dims(dp));
   const mmqg_dims& d = *dp;
   MMQG_TRY(check_tensors(d, params, "params"));
@@ -508,7 +524,7 @@ int mmqg_greedy_decode(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   MMQG_REQUIRE(workspace && tokens_out && max_len > 0, "greedy: bad args");
   MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
   if (mode == MMQG_MODE_BF16)
-    return greedy_decode_bf16(d, *params, *batch, workspace, workspace_bytes, tokens_out, max_len, as_stream(stream));
+    return greedy_decode_bf16(d, *params, *batch, workspace, workspace_bytes, tokens_out, max_len, as_stream(stream), sample, seed);
   MMQG_REQUIRE(!batch->ctx_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
   Ws w = carve(d, max_len, workspace);
   if (w.bytes > workspace_bytes)
@@ -547,7 +563,11 @@ int mmqg_greedy_decode(const mmqg_dims* dp, const mmqg_tensors* params, const mm
     for (int r0 = 0; r0 < B; r0 += w.Rc) {
       const int rc = B - r0 < w.Rc ? B - r0 : w.Rc;
       MMQG_TRY(GemmCall(htop + (size_t)r0 * H, H, false, P.out_w, H, true, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(st));
-      MMQG_TRY(argmax_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, st));
+      if (sample)
+        MMQG_TRY(sample_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, seed,
+                             (unsigned long long)t, r0, B, st));
+      else
+        MMQG_TRY(argmax_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, st));
     }
   }
   return 0;

@@ -674,7 +674,7 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
 // (lowest index on ties).  bf16 operands: tokens can leave the fp32 oracle's path at near-ties --
 // the fp32 mode carries the token-exact claim, this mode the throughput.
 int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace, size_t workspace_bytes,
-                       int64_t* tokens_out, int max_len, cudaStream_t user) {
+                       int64_t* tokens_out, int max_len, cudaStream_t user, int sample, unsigned long long seed) {
   MMQG_TRY(check_dims_bf16(d));
   Ws16 w = carve16(d, max_len, workspace);
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
@@ -732,7 +732,11 @@ int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
     for (int r0 = 0; r0 < B; r0 += w.Rc) {
       const int rc = B - r0 < w.Rc ? B - r0 : w.Rc;
       MMQG_TRY(Tc(htop + (size_t)r0 * H, H, false, w.wo, H, false, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(st));
-      MMQG_TRY(argmax_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, st));
+      if (sample)
+        MMQG_TRY(sample_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, seed,
+                             (unsigned long long)t, r0, B, st));
+      else
+        MMQG_TRY(argmax_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, st));
     }
   }
   return g_aux.leave(user, st);

@@ -19,6 +19,8 @@ int nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_strid
              float scale, cudaStream_t st);
 int argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int64_t* tokens2, int R, int V,
                 cudaStream_t st);
+int sample_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int64_t* tokens2, int R, int V,
+                unsigned long long seed, unsigned long long step, int row0, int R_total, cudaStream_t st);
 int colsum(const float* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
 int add2(const float* a, const float* b, float* y, int n, cudaStream_t st);
 int build_indices(const int64_t* ctx, const int64_t* tgt, int64_t* idx_ctx, int64_t* idx_dec, int64_t* tgt_tm, int B,
@@ -128,7 +130,7 @@ int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
                        size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
                        float dropout_p, unsigned long long seed, cudaStream_t st);
 int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace, size_t workspace_bytes,
-                       int64_t* tokens_out, int max_len, cudaStream_t st);
+                       int64_t* tokens_out, int max_len, cudaStream_t st, int sample = 0, unsigned long long seed = 0);
 size_t greedy_workspace_bytes_bf16(const mmqg_dims& d, int max_len);
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                         size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,

@@ -173,6 +173,73 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
   }
 }
 
+// 'sampling' strategy of the reference (evaluate.py:84-90: np.random.choice(V, p=softmax(logits))):
+// tokens(r) = the smallest v with cumsum_softmax(r, v) > u(r), u from the counter-based generator
+// (seed, stream 30, index step*R_total + row) -- the inverse-CDF draw numpy makes, with our own uniforms.
+// One block per row: softmax statistics, then every thread owns a contiguous segment of the
+// vocabulary; a block scan of the segment masses finds the segment, a short serial scan the token.
+__device__ __forceinline__ float sample_uniform(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + 30ull * 0x9E3779B97F4A7C15ull + idx * 0xD1342543DE82EF95ull;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+__global__ void __launch_bounds__(256) sample_rows_kernel(const float* __restrict__ logits, int ldl, int64_t* __restrict__ tokens,
+                                                          long long tok_stride, int64_t* __restrict__ tokens2, int R, int V,
+                                                          unsigned long long seed, unsigned long long idx_base) {
+  __shared__ float sh[256];
+  __shared__ float s_m, s_target;
+  __shared__ int s_seg;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + (size_t)r * ldl;
+  const int seg = (V + 255) / 256, v0 = tid * seg, v1 = min(V, v0 + seg);
+  float m = -INFINITY;
+  for (int v = v0; v < v1; ++v) m = fmaxf(m, x[v]);
+  sh[tid] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) sh[tid] = fmaxf(sh[tid], sh[tid + o]);
+    __syncthreads();
+  }
+  if (tid == 0) s_m = sh[0];
+  __syncthreads();
+  m = s_m;
+  float mass = 0.f;
+  for (int v = v0; v < v1; ++v) mass += expf(x[v] - m);
+  __syncthreads();
+  sh[tid] = mass;
+  __syncthreads();
+  if (tid == 0) {      // serial scan of 256 segment masses: deterministic, and tiny next to the passes over V
+    float tot = 0.f;
+    for (int i = 0; i < 256; ++i) tot += sh[i];
+    const float target = sample_uniform(seed, idx_base + r) * tot;
+    float acc = 0.f;
+    int k = 0;
+    for (; k < 255; ++k) {
+      if (acc + sh[k] > target) break;
+      acc += sh[k];
+    }
+    s_seg = k;
+    s_target = target - acc;
+  }
+  __syncthreads();
+  if (tid == s_seg) {
+    float acc = 0.f;
+    int w = v1 > v0 ? v1 - 1 : 0;
+    for (int v = v0; v < v1; ++v) {
+      acc += expf(x[v] - m);
+      if (acc > s_target) { w = v; break; }
+    }
+    tokens[(size_t)r * tok_stride] = w;
+    if (tokens2) tokens2[r] = w;
+  }
+}
+__global__ void sample_uniform_kernel(float* out, int n, unsigned long long seed, unsigned long long base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sample_uniform(seed, base + i);
+}
+
 // out(n) = beta*out(n) + sum_m X(m,n).  Block = 32 columns x 8 row lanes.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out,
                                                      float* __restrict__ out2, int M, int N, float beta) {
@@ -294,6 +361,16 @@ int argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_str
   return 0;
 }
 
+int sample_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int64_t* tokens2, int R, int V,
+                unsigned long long seed, unsigned long long step, int row0, int R_total, cudaStream_t st) {
+  MMQG_REQUIRE(logits && tokens && R > 0 && V > 0, "sample_rows: bad args");
+  // the uniform of row r at step t is indexed t*R_total + row0 + r, whatever the row chunking
+  sample_rows_kernel<<<R, 256, 0, st>>>(logits, ldl, tokens, tok_stride, tokens2, R, V, seed,
+                                         step * (unsigned long long)R_total + (unsigned long long)row0);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
 int colsum(const float* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st) {
   MMQG_REQUIRE(X && out && M > 0 && N > 0, "colsum: bad args");
   colsum_kernel<<<ceil_div(N, 32), 256, 0, st>>>(X, ldx, out, out2, M, N, beta);
@@ -369,6 +446,17 @@ int mmqg_nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_
 }
 int mmqg_argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int R, int V, void* stream) {
   return argmax_rows(logits, ldl, tokens, tok_stride, nullptr, R, V, as_stream(stream));
+}
+int mmqg_sample_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int R, int V,
+                     unsigned long long seed, unsigned long long step, void* stream) {
+  return sample_rows(logits, ldl, tokens, tok_stride, nullptr, R, V, seed, step, 0, R, as_stream(stream));
+}
+int mmqg_sample_uniform(float* out, int n, unsigned long long seed, unsigned long long step, void* stream) {
+  if (!out || n <= 0) return set_err(MMQG_ERR_BAD_ARG, "sample_uniform: bad args");
+  cudaStream_t st = as_stream(stream);
+  sample_uniform_kernel<<<ceil_div(n, 256), 256, 0, st>>>(out, n, seed, step * (unsigned long long)n);
+  MMQG_LAUNCH_CHECK();
+  return 0;
 }
 int mmqg_colsum(const float* X, int ldx, float* out, int M, int N, float beta, void* stream) {
   return colsum(X, ldx, out, nullptr, M, N, beta, as_stream(stream));

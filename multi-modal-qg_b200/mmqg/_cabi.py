@@ -69,6 +69,9 @@ SYMBOLS = {
                                         _P(_fp), _f, _ull, _i, _fp]),
     "mmqg_greedy_workspace_bytes": (_sz, [_P(MmqgDims), _i, _i]),
     "mmqg_greedy_decode": (_i, [_P(MmqgDims), _P(MmqgTensors), _P(MmqgBatch), _fp, _sz, _fp, _i, _i, _fp]),
+    "mmqg_sample_decode": (_i, [_P(MmqgDims), _P(MmqgTensors), _P(MmqgBatch), _fp, _sz, _fp, _i, _ull, _i, _fp]),
+    "mmqg_sample_rows": (_i, [_fp, _i, _fp, _ll, _i, _i, _ull, _ull, _fp]),
+    "mmqg_sample_uniform": (_i, [_fp, _i, _ull, _ull, _fp]),
     "mmqg_dropout_mask": (_i, [_fp, _ll, _ull, _i, _f, _fp]),
     "mmqg_adam_step": (_i, [_fp, _fp, _fp, _fp, _ll, _ll, _ll, _f, _f, _f, _f, _fp, _fp]),
     "mmqg_gemm_f32": (_i, [_P(MmqgGemmArgs), _fp]),

@@ -187,7 +187,12 @@ class TrainEngine:
         return out
 
     # -- greedy decode ---------------------------------------------------------------------
-    def greedy(self, batch, max_len):
+    def greedy(self, batch, max_len, strategy="greedy", seed=0):
+        """Decode max_len tokens per sample (no early exit; callers cut at <end>).  strategy: "greedy"
+        (evaluate.py:71-80), "topk" (the reference's topk(1): the same tokens) or "sampling"
+        (evaluate.py:84-90: draw from softmax(logits), deterministic in `seed`)."""
+        if strategy not in ("greedy", "topk", "sampling"):
+            raise ValueError(f"unknown decode strategy {strategy!r}")
         cb = self._cbatch(batch)
         key = int(max_len)
         if self._greedy_ws is None or self._greedy_ws[0] != key:
@@ -198,9 +203,14 @@ class TrainEngine:
             self._greedy_ws = (key, ws)
         ws = self._greedy_ws[1]
         toks = torch.empty(self.d.B, key, dtype=torch.int64, device=self.device)
-        _cabi.check(self.lib.mmqg_greedy_decode(
-            C.byref(self._cd), C.byref(self._cp), C.byref(cb), ws.data_ptr(), ws.numel(), toks.data_ptr(), key,
-            self.mode, _stream_ptr()))
+        if strategy == "sampling":
+            _cabi.check(self.lib.mmqg_sample_decode(
+                C.byref(self._cd), C.byref(self._cp), C.byref(cb), ws.data_ptr(), ws.numel(), toks.data_ptr(), key,
+                int(seed), self.mode, _stream_ptr()))
+        else:
+            _cabi.check(self.lib.mmqg_greedy_decode(
+                C.byref(self._cd), C.byref(self._cp), C.byref(cb), ws.data_ptr(), ws.numel(), toks.data_ptr(), key,
+                self.mode, _stream_ptr()))
         return toks
 
 

@@ -185,6 +185,22 @@ def argmax_rows(logits):
     return tok
 
 
+def sample_rows(logits, seed=0, step=0):
+    """tokens(r) ~ softmax(logits(r,:)) -- the reference's 'sampling' strategy (evaluate.py:84-90)."""
+    _chk(logits)
+    R, V = logits.shape
+    tok = torch.empty(R, device=logits.device, dtype=torch.int64)
+    check(lib().mmqg_sample_rows(logits.data_ptr(), _ld(logits), tok.data_ptr(), 1, R, V, int(seed), int(step), _st()))
+    return tok
+
+
+def sample_uniform(n, seed=0, step=0, device="cuda"):
+    """The uniforms sample_rows(seed, step) uses for rows 0..n-1 (for tests)."""
+    out = torch.empty(n, device=device, dtype=torch.float32)
+    check(lib().mmqg_sample_uniform(out.data_ptr(), n, int(seed), int(step), _st()))
+    return out
+
+
 def colsum(X, out=None, beta=0.0):
     _chk(X, out)
     M, N = X.shape
