@@ -60,7 +60,9 @@ struct Ws16 {
 };
 
 static int vocab_chunk_rows16(int R, int V) {
-  long long rc = (16ll << 20) / (V > 0 ? V : 1);
+  // logits of one chunk of rows: MMQG_LH_ELEMS fp32 elements (default 32 Mi = 128 MB: measured best at cfg-2, larger products beat finer overlap)
+  static const long long budget = []() { const char* e = getenv("MMQG_LH_ELEMS"); long long v = e ? atoll(e) : (32ll << 20); return v < (1 << 16) ? (1ll << 16) : v; }();
+  long long rc = budget / (V > 0 ? V : 1);
   rc = rc / 128 * 128;
   if (rc < 128) rc = 128;
   if (rc > R) rc = R;
