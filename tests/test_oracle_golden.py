@@ -118,3 +118,33 @@ def test_oracle_dropout_masks_semantics():
     masks = [[drop["text"][l, t].double() for l in range(d.L - 1)] for t in range(d.T_t)]
     mem, _, _ = O.text_encode(p64, batch["context"], d.L, d.TM, masks)
     assert torch.allclose(mem[:, :d.T_t].transpose(0, 1), x, atol=1e-12)
+
+
+def test_oracle_variable_lengths_equal_the_per_sample_loop_of_stock_modules():
+    """teacher_forced_loss_varlen (what the batched CUDA path is held to) against the per-sample
+    loop over stock torch.nn modules (oracle/ref_loop.py, the train.py:153-177 call structure) with
+    every sample cut to its own lengths: loss and every gradient."""
+    import torch
+    from mmqg.dims import Dims
+    from mmqg.synth import make_batch, make_params
+    from oracle import mmqg_oracle as O
+    from oracle.ref_loop import RefModules
+    d = Dims(B=4, T_t=6, T_v=3, T_q=4, V=31, E=6, H=8, L=2, H_a=4, H_v=8, F_v=5, TM=7, AM=4)
+    params, batch = make_params(d, seed=13), make_batch(d, seed=14)
+    batch["ctx_len"] = torch.tensor([6, 1, 3, 4])
+    batch["tgt_len"] = torch.tensor([4, 2, 1, 3])
+    batch["n_frames"] = torch.tensor([3, 1, 2, 2])
+    loss, grads = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
+    ref = RefModules(params, d.L, 0.0, torch.float64)
+    ref.zero_grad()
+    total = 0.0
+    for b in range(d.B):
+        cl, tl, nf = int(batch["ctx_len"][b]), int(batch["tgt_len"][b]), int(batch["n_frames"][b])
+        l = ref.sample_loss(batch["context"][b, :cl], batch["frames"][b, :nf].double(), batch["audio"][b, :nf].double(),
+                            batch["target"][b, :tl]) / d.B
+        l.backward()
+        total += float(l.detach())
+    assert abs(float(loss) - total) < 1e-10 * abs(total)
+    for n, p in ref.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert O.rel_err(grads[n], g) < 1e-9, n
