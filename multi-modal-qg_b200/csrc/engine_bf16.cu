@@ -247,10 +247,12 @@ static int persist_kind(int B, int H) {
 }
 static bool persist_text(const mmqg_dims& d) { return persist_kind(d.B, d.H) != 0; }
 static bool persist_video(const mmqg_dims& d) { return persist_kind(d.B, d.H_v) != 0; }
+// packed W_hh of a persistent layer: the forward layout is needed at once, the backward (transposed)
+// layout only by the BPTT -- either may be null
 static int pack_rec(const float* w_hh, void* fwd, void* bwd, int B, int H, cudaStream_t st) {
   if (persist_kind(B, H) == 2) {
-    MMQG_TRY(pack_whh_cluster(w_hh, fwd, H, st));
-    return pack_whh(w_hh, nullptr, bwd, H, st);
+    if (fwd) MMQG_TRY(pack_whh_cluster(w_hh, fwd, H, st));
+    return bwd ? pack_whh(w_hh, nullptr, bwd, H, st) : 0;
   }
   return pack_whh(w_hh, fwd, bwd, H, st);
 }
@@ -280,11 +282,11 @@ static int pack_weights_text(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w,
   for (int l = 0; l < d.L; ++l) {
     const int I = l == 0 ? E : H, Ip = l == 0 ? Ep : H;
     MMQG_TRY(cvt_f32_bf16_2d(P.text_w_ih[l], I, w.wt_ih[l], Ip, G, I, Ip, st));
-    MMQG_TRY(cvt_f32_bf16_2d(P.text_w_hh[l], H, w.wt_hh[l], H, G, H, H, st));
+    if (!persist_text(d)) MMQG_TRY(cvt_f32_bf16_2d(P.text_w_hh[l], H, w.wt_hh[l], H, G, H, H, st));   // per-step path only
     MMQG_TRY(add2(P.text_b_ih[l], P.text_b_hh[l], w.bsum_text[l], G, st));
   }
-  if (persist_text(d))
-    for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_rec(P.text_w_hh[l], w.wtp_f[l], w.wtp_b[l], d.B, H, st));
+  if (persist_text(d))      // forward layout only: this sits in front of the text encoder on the critical path
+    for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_rec(P.text_w_hh[l], w.wtp_f[l], nullptr, d.B, H, st));
   return 0;
 }
 static int pack_weights_rest(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cudaStream_t st) {
@@ -311,6 +313,8 @@ static int pack_weights_rest(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w,
   }
   MMQG_TRY(cvt_f32_bf16_2d(P.out_w, H, w.wo, H, d.V, H, H, st));
   if (persist_video(d)) MMQG_TRY(pack_rec(P.vid_w_hh, w.wvp_f, w.wvp_b, d.B, Hv, st));
+  if (persist_text(d))      // BPTT layouts of the text layers: not needed before the backward pass
+    for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_rec(P.text_w_hh[l], nullptr, w.wtp_b[l], d.B, H, st));
   return 0;
 }
 
