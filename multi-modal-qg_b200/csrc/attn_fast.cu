@@ -226,7 +226,10 @@ __global__ void __launch_bounds__(512) attn_bwd_fast_kernel(const float* attn, f
 static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool attn_fast_ok(const AttnShape& s, const void* M_txt, const void* M_aud, const void* M_vid) {
-  return s.H % 8 == 0 && s.H_v % 8 == 0 && al16p(M_txt) && al16p(M_vid) && M_aud != nullptr;
+  // both kernels stage one sample in at most 48 KB of shared memory; larger shapes take the generic kernels
+  const int S = s.TM + 2 * s.AM, Hmax = s.H > s.H_v ? s.H : s.H_v, C = s.H + s.H_a + s.H_v;
+  const bool fits = (size_t)(S + 8 * Hmax) * sizeof(float) <= 48 * 1024 && (size_t)(2 * S + 4 + C) * sizeof(float) <= 48 * 1024;
+  return fits && s.H % 8 == 0 && s.H_v % 8 == 0 && al16p(M_txt) && al16p(M_vid) && M_aud != nullptr;
 }
 
 int attn_fwd_fast(float* scores, int lds, const void* M_txt, const float* M_aud, const void* M_vid, bool mem_bf16, float* ctx,
