@@ -129,7 +129,7 @@ def run_reference(args, d, rank, world):
     if rank != 0:
         return
     # bounded sample: about 200 samples in total (~100 s at ~2 samples/s on 16 cores), whatever K is
-    per_step = max(1, min(8, 200 // max(1, args.steps)))
+    per_step = max(1, min(8, args.cpu_samples, 200 // max(1, args.steps)))
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_samples_per_s(d, 1, dropout_p=args.dropout)
     t_total, n_total = 0.0, 0
