@@ -164,7 +164,50 @@ def run_case(name, d, seed, dtype=torch.float64):
           "min margin", float(fx["greedy_margins"].min()), os.path.getsize(path), "bytes")
 
 
+VARLEN = {"varlen_a": dict(dims=Dims(B=4, T_t=7, T_v=3, T_q=5, V=41, E=12, H=32, L=3, H_a=8, H_v=32, F_v=20, TM=9, AM=5),
+                           seed=21, ctx_len=[7, 1, 4, 5], tgt_len=[5, 2, 1, 4], n_frames=[3, 1, 2, 3])}
+
+
+def run_varlen_case(name, d, seed, ctx_len, tgt_len, n_frames, dtype=torch.float64):
+    """Per-sample lengths: the reference's loop on every sample cut to its own lengths (what a
+    batch-1 DataLoader hands train.py); loss = mean over samples, gradients of that mean."""
+    params = make_params(d, seed=seed)
+    batch = make_batch(d, seed=seed + 1000)
+    emb, video, text, dec = build_reference(d, params, dtype)
+    crit = torch.nn.CrossEntropyLoss()
+    for m in (emb, video, text, dec):
+        m.zero_grad()
+    losses = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for b in range(d.B):
+            cl, tl, nf = ctx_len[b], tgt_len[b], n_frames[b]
+            ctx, tgt = batch["context"][b, :cl], batch["target"][b, :tl]
+            fr, au = batch["frames"][b, :nf].to(dtype), batch["audio"][b, :nf].to(dtype)
+            n, pa, pv, hid, all_enc = encode_sample(d, video, text, ctx, fr, au)
+            assert n == nf
+            dec_input = torch.tensor([[1]])
+            loss = 0
+            for di in range(tl):
+                out, hid, *_ = dec(dec_input, n, cl, pa, pv, hid, all_enc)
+                loss = loss + crit(out, tgt[di].view(-1))
+                dec_input = tgt[di]
+            (loss / d.B).backward()
+            losses.append(loss.detach())
+    fx = {"dims": d.asdict(), "seed": seed, "dtype": str(dtype), "params": params, "batch": batch,
+          "ctx_len": torch.tensor(ctx_len, dtype=torch.int32), "tgt_len": torch.tensor(tgt_len, dtype=torch.int32),
+          "n_frames": torch.tensor(n_frames, dtype=torch.int32), "loss_per_sample": torch.stack(losses),
+          "loss": torch.stack(losses).mean(), "grads": named_grads(emb, video, text, dec)}
+    path = os.path.join(HERE, f"{name}.pt")
+    torch.save(fx, path)
+    print(name, "loss", float(fx["loss"]), os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    which = sys.argv[1:]
     for name, c in CASES.items():
-        run_case(name, c["dims"], c["seed"])
+        if not which or name in which:
+            run_case(name, c["dims"], c["seed"])
+    for name, c in VARLEN.items():
+        if not which or name in which:
+            run_varlen_case(name, c["dims"], c["seed"], c["ctx_len"], c["tgt_len"], c["n_frames"])

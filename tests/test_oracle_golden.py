@@ -148,3 +148,24 @@ def test_oracle_variable_lengths_equal_the_per_sample_loop_of_stock_modules():
     for n, p in ref.named_parameters():
         g = p.grad if p.grad is not None else torch.zeros_like(p)
         assert O.rel_err(grads[n], g) < 1e-9, n
+
+
+def test_oracle_variable_lengths_match_the_reference_fixture():
+    """tests/golden/varlen_a.pt was produced by the reference's own modules driven per sample with
+    every sample cut to its own lengths (make_golden.py run_varlen_case): the oracle's
+    variable-length path must reproduce its per-sample losses and every gradient."""
+    import torch
+    from conftest import load_golden
+    from mmqg.dims import Dims
+    from oracle import mmqg_oracle as O
+    fx = load_golden("varlen_a")
+    d = Dims(**fx["dims"])
+    batch = dict(fx["batch"])
+    batch["ctx_len"], batch["tgt_len"], batch["n_frames"] = fx["ctx_len"], fx["tgt_len"], fx["n_frames"]
+    loss, grads = O.loss_and_grads(fx["params"], batch, d.L, d.TM, d.AM, torch.float64)
+    assert abs(float(loss) - float(fx["loss"])) < 1e-9 * abs(float(fx["loss"]))
+    for k, g in fx["grads"].items():
+        assert O.rel_err(grads[k], g) < 1e-9, k
+    # and the lengths matter: the full-length loss of the same batch is different
+    full, _ = O.loss_and_grads(fx["params"], fx["batch"], d.L, d.TM, d.AM, torch.float64)
+    assert abs(float(full) - float(fx["loss"])) > 0.1
