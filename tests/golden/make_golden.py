@@ -202,9 +202,58 @@ def run_varlen_case(name, d, seed, ctx_len, tgt_len, n_frames, dtype=torch.float
     print(name, "loss", float(fx["loss"]), os.path.getsize(path), "bytes")
 
 
+def run_adam_case(name="adam_a", seed=31, n_iter=3, dtype=torch.float64):
+    """Three iterations of the reference's train loop INCLUDING its optimisers, wired exactly as
+    train.py:265-267 (Adam over av_enc / text_enc / dec .parameters(), lr 1e-4; the shared embedding
+    is a parameter of both the text encoder and the decoder) and stepped as train.py:149-181
+    (zero_grad, forward, backward, three .step() per sample).  Stored: the three samples, the
+    per-iteration losses and every parameter after the last iteration."""
+    d = Dims(B=1, T_t=6, T_v=3, T_q=4, V=37, E=12, H=32, L=3, H_a=8, H_v=32, F_v=20, TM=9, AM=5)
+    params = make_params(d, seed=seed)
+    emb, video, text, dec = build_reference(d, params, dtype)
+    opts = [torch.optim.Adam(video.parameters(), lr=1e-4), torch.optim.Adam(text.parameters(), lr=1e-4),
+            torch.optim.Adam(dec.parameters(), lr=1e-4)]
+    assert any(p is emb.weight for p in text.parameters()) and any(p is emb.weight for p in dec.parameters())
+    crit = torch.nn.CrossEntropyLoss()
+    batches, losses = [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for it in range(n_iter):
+            batch = make_batch(d, seed=seed + 100 + it)
+            batches.append(batch)
+            for o in opts:
+                o.zero_grad()
+            fr, au = batch["frames"][0].to(dtype), batch["audio"][0].to(dtype)
+            n, pa, pv, hid, all_enc = encode_sample(d, video, text, batch["context"][0], fr, au)
+            dec_input = torch.tensor([[1]])
+            loss = 0
+            for di in range(d.T_q):
+                out, hid, *_ = dec(dec_input, n, d.T_t, pa, pv, hid, all_enc)
+                loss = loss + crit(out, batch["target"][0][di].view(-1))
+                dec_input = batch["target"][0][di]
+            loss.backward()
+            for o in opts:
+                o.step()
+            losses.append(float(loss))
+    final = {"emb.weight": emb.weight.detach().clone()}
+    for n_, p_ in video.lstm.named_parameters():
+        final[f"video.lstm.{n_}"] = p_.detach().clone()
+    for n_, p_ in text.lstm.named_parameters():
+        final[f"text.lstm.{n_}"] = p_.detach().clone()
+    for n_, p_ in dec.named_parameters():
+        if not n_.startswith("emb_layer"):
+            final[f"dec.{n_}"] = p_.detach().clone()
+    fx = {"dims": d.asdict(), "seed": seed, "params": params, "batches": batches, "losses": torch.tensor(losses, dtype=torch.float64),
+          "final_params": final}
+    path = os.path.join(HERE, f"{name}.pt")
+    torch.save(fx, path)
+    print(name, "losses", losses, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     which = sys.argv[1:]
+    if not which or "adam_a" in which:
+        run_adam_case()
     for name, c in CASES.items():
         if not which or name in which:
             run_case(name, c["dims"], c["seed"])

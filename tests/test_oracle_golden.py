@@ -169,3 +169,34 @@ def test_oracle_variable_lengths_match_the_reference_fixture():
     # and the lengths matter: the full-length loss of the same batch is different
     full, _ = O.loss_and_grads(fx["params"], fx["batch"], d.L, d.TM, d.AM, torch.float64)
     assert abs(float(full) - float(fx["loss"])) > 0.1
+
+
+def test_oracle_adam_wiring_matches_the_reference_fixture():
+    """tests/golden/adam_a.pt: three iterations of the reference's own loop with its three Adam
+    optimisers (train.py:265-267, 149-181).  The oracle + torch.optim.Adam wired as tests/test_gpu_adam.py
+    wires it (the CUDA path's yardstick) must land on the same parameters -- in particular the
+    shared embedding, which two of the optimisers step."""
+    import torch
+    from conftest import load_golden
+    from mmqg.dims import Dims
+    from oracle import mmqg_oracle as O
+    fx = load_golden("adam_a")
+    d = Dims(**fx["dims"])
+    p = {k: v.detach().double().clone().requires_grad_(True) for k, v in fx["params"].items()}
+    emb = p["emb.weight"]
+    groups = ([v for k, v in p.items() if k.startswith("video.")], [emb] + [v for k, v in p.items() if k.startswith("text.")],
+              [emb] + [v for k, v in p.items() if k.startswith("dec.")])
+    opts = [torch.optim.Adam(g, lr=1e-4) for g in groups]
+    for it, b in enumerate(fx["batches"]):
+        bb = {k: (v.double() if v.is_floating_point() else v) for k, v in b.items()}
+        for o in opts:
+            o.zero_grad()
+        loss = O.teacher_forced_loss(p, bb, d.L, d.TM, d.AM)
+        loss.backward()
+        for o in opts:
+            o.step()
+        assert abs(float(loss) - float(fx["losses"][it])) < 1e-9 * abs(float(loss))
+    for k, v in fx["final_params"].items():
+        upd_ref = v.double() - fx["params"][k].double()
+        upd = p[k].detach() - fx["params"][k].double()
+        assert float((upd - upd_ref).norm()) <= 1e-7 * float(upd_ref.norm()) + 1e-15, k
