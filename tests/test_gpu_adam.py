@@ -93,3 +93,25 @@ def test_adam_graph_capture_advances_step_count():
     torch.cuda.synchronize()
     for k in e1.params:
         assert torch.allclose(e1.params[k], e2.params[k], rtol=0, atol=1e-7), k
+
+
+def test_adam_against_the_reference_fixture():
+    """tests/golden/adam_a.pt: three batch-1 iterations of the reference's own modules and its three
+    Adam optimisers (train.py:149-181, 265-267).  The fp32 engine + fused Adam must land on the same
+    parameters (accumulated update within 1e-3; losses within 1e-5)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from conftest import load_golden
+    from mmqg import engine
+    fx = load_golden("adam_a")
+    d = Dims(**fx["dims"])
+    eng = engine.TrainEngine(d, fx["params"], mode="fp32")
+    for it, b in enumerate(fx["batches"]):
+        loss = float(eng.step(eng.to_device(b)))
+        eng.adam_step(lr=1e-4)
+        assert abs(loss - float(fx["losses"][it])) < 1e-5 * abs(loss), (it, loss, float(fx["losses"][it]))
+    torch.cuda.synchronize()
+    for k, v in fx["final_params"].items():
+        ref = v.double() - fx["params"][k].double()
+        got = eng.params[k].double().cpu() - fx["params"][k].double()
+        assert float((got - ref).norm()) < 1e-3 * float(ref.norm()), k
