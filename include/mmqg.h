@@ -17,6 +17,8 @@
  *     and is ordered on it: there are no hidden synchronisations.  The bf16 train path forks
  *     library-owned auxiliary streams from `stream` and joins them back with events before
  *     the call returns, so callers (and CUDA-graph capture) see single-stream semantics.
+ *   - one process drives one GPU (the data-parallel layout of SURVEY.md section 8e): the helper
+ *     streams and events are per process, calls are not re-entrant across host threads.
  *   - return value: 0 = enqueued OK, otherwise an mmqg_status; mmqg_last_error()
  *     gives a thread-local message.
  *   - parameters are fp32 in PyTorch layout: LSTM weights (4H, in) row-major with gate
