@@ -376,6 +376,26 @@ struct AuxStream {
     MMQG_CUDA(cudaStreamWaitEvent(user, ev[13], 0));
     return 0;
   }
+  // Error path of an entry point: whatever was already enqueued on the internal streams is joined back
+  // onto the caller's stream (the header promises single-stream semantics, and an unjoined fork would
+  // invalidate a CUDA-graph capture with a confusing error).  Best effort: CUDA errors here are dropped,
+  // the caller returns the ORIGINAL status.  While capturing, only streams that joined the capture are touched.
+  void join_after_error(cudaStream_t user, cudaStream_t st) {
+    if (!ready) return;
+    cudaStreamCaptureStatus ucap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(user, &ucap);
+    auto join = [&](cudaStream_t s) {
+      if (!s || s == user) return;
+      cudaStreamCaptureStatus c = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &c);
+      if (ucap == cudaStreamCaptureStatusActive && c != cudaStreamCaptureStatusActive) return;
+      if (cudaEventRecord(ev[14], s) == cudaSuccess) cudaStreamWaitEvent(user, ev[14], 0);
+    };
+    for (int i = 0; i < NS; ++i) { join(s[i]); join(g[i]); }
+    join(chain);
+    (void)st;
+    cudaGetLastError();
+  }
 };
 static AuxStream g_aux;
 static constexpr int kMaxChunks = 8;
@@ -394,13 +414,11 @@ static bool split_products() {
 // Layer l can run chunk c as soon as layer l-1 has finished chunk c, so with the layers on
 // separate streams the serial chain shrinks from L*T_t to about (NC+L-1)/NC * T_t steps.
 static int text_chunks(const mmqg_dims& d) {
-  static int want = -1;
-  if (want < 0) {
-    const char* e = getenv("MMQG_CHUNKS");
-    want = e ? atoi(e) : 6;
-    if (want < 1) want = 1;
-    if (want > kMaxChunks) want = kMaxChunks;
-  }
+  // read on every call (tests switch schedules inside one process); getenv is noise next to a step's launches
+  const char* e = getenv("MMQG_CHUNKS");
+  int want = e ? atoi(e) : 6;
+  if (want < 1) want = 1;
+  if (want > kMaxChunks) want = kMaxChunks;
   if (persist_kind(d.B, d.H) != 1 || d.L < 2 || d.L > AuxStream::NS) return 1;
   int nc = want;
   while (nc > 1 && d.T_t / nc < 8) --nc;
@@ -541,9 +559,14 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
 int train_forward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                        size_t workspace_bytes, float* loss_out, int want_grads, mmqg_tensors* grads, float grad_scale,
                        float dropout_p, unsigned long long seed, cudaStream_t user) {
+  // validate before any work is moved onto the internal streams
+  MMQG_TRY(check_dims_bf16(d));
+  const size_t need = train_workspace_bytes_bf16(d, d.T_q);
+  if (need > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
   cudaStream_t st;
   MMQG_TRY(g_aux.enter(user, &st));
-  MMQG_TRY(train_forward_bf16_on(d, P, bt, workspace, workspace_bytes, loss_out, want_grads, grads, grad_scale, dropout_p, seed, st));
+  const int rc = train_forward_bf16_on(d, P, bt, workspace, workspace_bytes, loss_out, want_grads, grads, grad_scale, dropout_p, seed, st);
+  if (rc != 0) { g_aux.join_after_error(user, st); return rc; }
   return g_aux.leave(user, st);
 }
 
@@ -679,6 +702,9 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
 // Encoder as in training (no dropout), then max_len decoder steps feeding back argmax(logits)
 // (lowest index on ties).  bf16 operands: tokens can leave the fp32 oracle's path at near-ties --
 // the fp32 mode carries the token-exact claim, this mode the throughput.
+static int greedy_decode_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, Ws16& w, int64_t* tokens_out,
+                                 int max_len, cudaStream_t st, int sample, unsigned long long seed);
+
 int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace, size_t workspace_bytes,
                        int64_t* tokens_out, int max_len, cudaStream_t user, int sample, unsigned long long seed) {
   MMQG_TRY(check_dims_bf16(d));
@@ -690,6 +716,13 @@ int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
   MMQG_TRY(set_len_state(d, bt, w));
   cudaStream_t st;
   MMQG_TRY(g_aux.enter(user, &st));
+  const int rc = greedy_decode_bf16_on(d, P, bt, w, tokens_out, max_len, st, sample, seed);
+  if (rc != 0) { g_aux.join_after_error(user, st); return rc; }
+  return g_aux.leave(user, st);
+}
+
+static int greedy_decode_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, Ws16& w, int64_t* tokens_out,
+                                 int max_len, cudaStream_t st, int sample, unsigned long long seed) {
   const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, Sp = w.Sp, Ep = w.Ep;
   cudaStream_t ax = g_aux.s[AuxStream::NS - 1];
   if (g_len.on) MMQG_TRY(prep_lengths(bt.ctx_len, nullptr, bt.n_frames, w.shift_t, w.shift_v, w.row_w, B, d.T_t, d.T_v, 0, st));
@@ -745,7 +778,7 @@ int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
         MMQG_TRY(argmax_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, st));
     }
   }
-  return g_aux.leave(user, st);
+  return 0;
 }
 
 size_t greedy_workspace_bytes_bf16(const mmqg_dims& d, int max_len) { return carve16(d, max_len, nullptr).bytes; }
@@ -1005,9 +1038,13 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                         size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
                         cudaStream_t user, cudaEvent_t const* ready) {
+  MMQG_TRY(check_dims_bf16(d));
+  const size_t need = train_workspace_bytes_bf16(d, d.T_q);
+  if (need > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
   cudaStream_t st;
   MMQG_TRY(g_aux.enter(user, &st));
-  MMQG_TRY(train_backward_bf16_on(d, P, bt, workspace, workspace_bytes, Gd, phase, dropout_p, seed, st, ready));
+  const int rc = train_backward_bf16_on(d, P, bt, workspace, workspace_bytes, Gd, phase, dropout_p, seed, st, ready);
+  if (rc != 0) { g_aux.join_after_error(user, st); return rc; }
   return g_aux.leave(user, st);
 }
 
