@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MMQG_ABI_VERSION 2
+#define MMQG_ABI_VERSION 3
 #define MMQG_MAX_LAYERS 4
 
 typedef enum {
@@ -283,6 +283,32 @@ int mmqg_argmax_rows(const float* logits, int ldl, int64_t* tokens, long long to
 int mmqg_sample_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int R, int V,
                      unsigned long long seed, unsigned long long step, void* stream);
 int mmqg_sample_uniform(float* out, int n, unsigned long long seed, unsigned long long step, void* stream);
+/* ---- fused loss head (K4) and greedy arg-max (K6): SURVEY.md section 8b minimum export set ---- */
+
+/* Scratch for the three calls below for R rows, vocabulary V, hidden size H (multiple of 8). */
+size_t mmqg_vocab_workspace_bytes(int R, int V, int H);
+
+/* Vocabulary projection + log-softmax + NLL (decoder.py:106 out_layer, train.py:174 CrossEntropyLoss) without
+ * materialising the logits: h (R,H) and w (V,H) are bf16 row-major, bias fp32 (V); the logits tile
+ * h w^T + bias lives in tensor memory, its epilogue keeps per-row (max, sum exp, target logit).
+ * nll(r) = row_w(r) * (lse(r) - logit(r, targets(r)))   (row_w may be NULL = 1).
+ * lse (R) and row_scale (R) = grad_scale * row_w are what mmqg_vocab_nll_bwd needs (either may be NULL). */
+int mmqg_vocab_nll_fwd(const void* h_bf16, const void* w_bf16, const float* bias, const int64_t* targets, const float* row_w,
+                       int R, int V, int H, float grad_scale, void* workspace, size_t workspace_bytes, float* nll, float* lse,
+                       float* row_scale, void* stream);
+
+/* Backward: d logits(r,:) = row_scale(r) * (softmax(logits(r,:)) - onehot(targets(r))) is re-formed tile by tile
+ * (bf16, in L2-sized row chunks inside the workspace) and contracted: dH (R,H) = dZ w, dW (V,H) = dZ^T h,
+ * db (V) = column sums of dZ; all fp32.  accumulate != 0 adds into dW / db instead of overwriting them. */
+int mmqg_vocab_nll_bwd(const void* h_bf16, const void* w_bf16, const float* bias, const int64_t* targets, const float* lse,
+                       const float* row_scale, int R, int V, int H, void* workspace, size_t workspace_bytes, float* dH,
+                       float* dW, float* db, int accumulate, void* stream);
+
+/* Greedy step (train.py:106-108): tokens(r * tok_stride) = argmax_v (h w^T + bias)(r, v), lowest index on ties;
+ * the arg-max is taken in the projection's epilogue, logits are not stored. */
+int mmqg_decode_step_argmax(const void* h_bf16, const void* w_bf16, const float* bias, int R, int V, int H, void* workspace,
+                            size_t workspace_bytes, int64_t* tokens, long long tok_stride, void* stream);
+
 /* out(n) = sum_m X(m,n)  (bias gradients). */
 int mmqg_colsum(const float* X, int ldx, float* out, int M, int N, float beta, void* stream);
 

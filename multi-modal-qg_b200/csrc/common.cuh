@@ -49,16 +49,38 @@ struct PdlScope {
   ~PdlScope() { tl_pdl = prev; }
 };
 bool pdl_enabled();
+// L2 persistence window for the launches issued inside an L2WindowScope (the decoder's attention
+// steps re-read the same bf16 memories every step: decoder.py:81,87,95): accesses to [base, base+bytes)
+// are marked persisting, everything else streaming.  The set-aside is sized once (l2_window_reserve).
+extern thread_local const void* tl_l2win_base;
+extern thread_local size_t tl_l2win_bytes;
+struct L2WindowScope {
+  const void* pb; size_t pn;
+  L2WindowScope(const void* base, size_t bytes) : pb(tl_l2win_base), pn(tl_l2win_bytes) { tl_l2win_base = base; tl_l2win_bytes = bytes; }
+  ~L2WindowScope() { tl_l2win_base = pb; tl_l2win_bytes = pn; }
+};
+// Reserves a persisting-L2 set-aside of at least `bytes` (clamped to the device maximum); returns window_bytes
+// if a window of that size can be attached to a launch, else 0 (persistence unavailable, window too large).
+size_t l2_window_reserve(size_t bytes, size_t window_bytes);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   int n = 0;
   if (tl_pdl) {
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    n = 1;
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (tl_l2win_base && tl_l2win_bytes) {
+    at[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[n].val.accessPolicyWindow.base_ptr = const_cast<void*>(tl_l2win_base);
+    at[n].val.accessPolicyWindow.num_bytes = tl_l2win_bytes;
+    at[n].val.accessPolicyWindow.hitRatio = 1.0f;
+    at[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
   }
   cfg.attrs = at; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);

@@ -48,7 +48,7 @@ struct Ws {
   size_t bytes;
 };
 
-static int vocab_chunk_rows(int R, int V) {
+static int vocab_chunk_rows32(int R, int V) {
   long long rc = (16ll << 20) / (V > 0 ? V : 1);
   rc = rc / 64 * 64;
   if (rc < 64) rc = 64;
@@ -65,7 +65,7 @@ static Ws carve(const mmqg_dims& d, int T_q, void* base) {
   w.S_pad = (S + 3) / 4 * 4;
   const size_t Q = d.E + d.H, C = (size_t)d.H + d.H_a + d.H_v, X0 = d.E + C;
   const size_t R = (size_t)T_q * B;
-  w.Rc = vocab_chunk_rows((int)R, d.V);
+  w.Rc = vocab_chunk_rows32((int)R, d.V);
   w.idx_ctx = c.take<int64_t>((size_t)d.T_t * B);
   w.idx_dec = c.take<int64_t>(R);
   w.tgt_tm = c.take<int64_t>(R);

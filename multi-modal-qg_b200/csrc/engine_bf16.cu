@@ -55,13 +55,15 @@ struct Ws16 {
   int *shift_t, *shift_v;             // variable lengths: first real time step of every sample (text / video)
   float* row_w;                       // ... and the 0/1 weight of every (target step, sample) loss row
   float *dh_last, *dh_last_l[MMQG_MAX_LAYERS], *dx_emb;
-  int Sp, Ep, Vp, Rc;
+  // fused loss head (vocab_nll.cu): per-tile softmax partials, per-row lse / gradient scale / target logit, split-K scratch of dH
+  float *stat_a, *stat_b, *lse, *rscale, *tgt_logit, *dh_part;
+  int Sp, Ep, Vp, Rc, Rs;     // Rc: rows of one bf16 d-logits chunk; Rs: rows of the fp32 logits scratch of the sampling decode
   size_t bytes;
 };
 
-static int vocab_chunk_rows16(int R, int V) {
-  // logits of one chunk of rows: MMQG_LH_ELEMS fp32 elements (default 32 Mi = 128 MB: measured best at cfg-2, larger products beat finer overlap)
-  static const long long budget = []() { const char* e = getenv("MMQG_LH_ELEMS"); long long v = e ? atoll(e) : (32ll << 20); return v < (1 << 16) ? (1ll << 16) : v; }();
+static int sample_chunk_rows16(int R, int V) {
+  // fp32 logits of one chunk of rows for the 'sampling' decode strategy (the only consumer of materialised logits): 8 Mi elements
+  const long long budget = 8ll << 20;
   long long rc = budget / (V > 0 ? V : 1);
   rc = rc / 128 * 128;
   if (rc < 128) rc = 128;
@@ -80,7 +82,8 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.Vp = (d.V + 7) / 8 * 8;
   const size_t Sp = w.Sp, Ep = w.Ep, Q = d.E + d.H, C = (size_t)d.H + d.H_a + d.H_v;
   const size_t R = (size_t)T_q * B, Rt = (size_t)d.T_t * B, Rv = (size_t)d.T_v * B;
-  w.Rc = vocab_chunk_rows16((int)R, d.V);
+  w.Rc = vocab_chunk_rows((int)R, w.Vp);
+  w.Rs = sample_chunk_rows16((int)B, d.V);
   w.idx_ctx = c.take<int64_t>(Rt); w.idx_dec = c.take<int64_t>(R); w.tgt_tm = c.take<int64_t>(R);
   w.idx_cur = c.take<int64_t>(B);
   for (int l = 0; l < d.L; ++l) { w.bsum_text[l] = c.take<float>(G); w.bsum_dec[l] = c.take<float>(G); }
@@ -115,8 +118,14 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
     w.cs_dec[l] = c.take<float>((R + B) * H);
     w.dg_dec[l] = c.take<b16>(R * G);
   }
-  w.logits = c.take<float>((size_t)w.Rc * d.V);
+  w.logits = c.take<float>((size_t)w.Rs * d.V);
   w.dlogits16 = c.take<b16>((size_t)w.Rc * w.Vp);
+  {
+    const size_t rows = R > B ? R : B, ns = vocab_stat_floats((int)rows, d.V);
+    w.stat_a = c.take<float>(ns); w.stat_b = c.take<float>(ns);
+    w.lse = c.take<float>(rows); w.rscale = c.take<float>(rows); w.tgt_logit = c.take<float>(rows);
+    w.dh_part = c.take<float>((size_t)16 * w.Rc * H);
+  }
   w.nll = c.take<float>(R); w.dhtop = c.take<float>(R * H);
   for (int l = 0; l < d.L; ++l) { w.dh_rec[l] = c.take<float>(kSplitB * B * H); w.dc[l] = c.take<float>(B * H); }
   w.dx_above = c.take<float>(kSplitB * B * H); w.dq_h = c.take<float>(kSplitB * B * H);
@@ -178,6 +187,17 @@ static AttnShape attn_shape16(const mmqg_dims& d, const Ws16& w) {
   a.m_txt16 = w.m_txt16;
   a.m_vid16 = w.m_vid16;
   return a;
+}
+
+// Persisting-L2 window over the bf16 attention memories (m_txt16 and m_vid16 are adjacent in the workspace):
+// the set-aside is sized to the bytes the decoder really touches (T_t and T_v rows per sample).
+static size_t attn_l2_window(const mmqg_dims& d, const Ws16& w) {
+  static const bool on = []() { const char* e = getenv("MMQG_L2WIN"); return e && e[0] == '1'; }();
+  if (!on || !w.m_txt16 || !w.m_vid16) return 0;
+  const size_t span = (size_t)(reinterpret_cast<const char*>(w.m_vid16) - reinterpret_cast<const char*>(w.m_txt16)) +
+                      sizeof(b16) * (size_t)d.B * d.AM * d.H_v;
+  const size_t touched = sizeof(b16) * (size_t)d.B * ((size_t)d.T_t * d.H + (size_t)d.T_v * d.H_v);
+  return l2_window_reserve(touched + (touched >> 2), span);
 }
 
 // Debug hook (tools/sections.py; not used by the product path): CUDA events at the section
@@ -607,33 +627,30 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   mark(3, st);
   AttnShape as = attn_shape16(d, w);
   as.ldctx16 = C;
-  // loss head over rows [r0, r0+n) of h_top (row = t*B + b), in chunks of at most Rc rows: logits
-  // (fp32, chunk only) -> NLL (+ bf16 dlogits -> dH, dW_out, db_out); full-vocabulary logits are
-  // never stored (decoder.py:106, train.py:174).
+  // loss head over rows [r0, r0+n) of h_top (row = t*B + b): fused vocabulary projection + log-softmax + NLL
+  // and its backward (vocab_nll.cu); logits are never stored (decoder.py:106, train.py:174).
   const b16* htop = w.hs_dec[d.L - 1] + (size_t)B * H;
   const float dscale = want_grads ? grad_scale / (float)B : 0.f;
   auto loss_head = [&](int r0, int n, bool first, cudaStream_t s) -> int {
     PdlScope no_pdl(false);
-    for (int q0 = r0; q0 < r0 + n; q0 += w.Rc, first = false) {
-      const int rc = r0 + n - q0 < w.Rc ? r0 + n - q0 : w.Rc;
-      MMQG_TRY(Tc(htop + (size_t)q0 * H, H, false, w.wo, H, false, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(s));
-      MMQG_TRY(nll_rows_bf16(w.logits, d.V, w.tgt_tm + q0, w.nll + q0, rc, d.V, dscale, want_grads ? w.dlogits16 : nullptr,
-                             w.Vp, s, g_len.on ? w.row_w + q0 : nullptr));
-      if (want_grads) {
-        MMQG_TRY(Tc(w.dlogits16, w.Vp, false, w.wo, H, true, rc, H, d.V, w.dhtop + (size_t)q0 * H, H).run(s));
-        MMQG_TRY(Tc(w.dlogits16, w.Vp, true, htop + (size_t)q0 * H, H, true, d.V, H, rc, grads->out_w, H).accumulate(!first).run(s));
-        MMQG_TRY(colsum_bf16(w.dlogits16, w.Vp, grads->out_b, nullptr, rc, d.V, first ? 0.f : 1.f, s));
-      }
-    }
+    // forward: logits tiles live in tensor memory only; per-row (max, sum exp, target logit) -> lse, NLL
+    MMQG_TRY(vocab_nll_fwd(htop + (size_t)r0 * H, H, w.wo, H, P.out_b, w.tgt_tm + r0, g_len.on ? w.row_w + r0 : nullptr, n, d.V, H, dscale,
+                           w.nll + r0, w.lse + r0, w.rscale + r0, w.stat_a, w.stat_b, w.tgt_logit + r0, s));
+    // backward: tiles recomputed, bf16 d-logits in L2-sized row chunks -> dH, dW_out (+=), db_out (+=)
+    if (want_grads)
+      MMQG_TRY(vocab_nll_bwd(htop + (size_t)r0 * H, H, w.wo, H, P.out_b, w.tgt_tm + r0, w.lse + r0, w.rscale + r0, n, d.V, H, w.dlogits16,
+                             w.Vp, w.Rc, w.dh_part, w.dhtop + (size_t)r0 * H, H, grads->out_w, grads->out_b, !first, s));
     return 0;
   };
   // The loss head of the steps already decoded runs on its own stream under the remaining
   // (latency-bound, 64-CTA) decoder steps: groups of `lh_steps` whole steps, at most Rc rows.
   static const bool lh_env = []() { const char* e = getenv("MMQG_LOSS_OVERLAP"); return !(e && e[0] == '0'); }();
-  const int lh_steps = w.Rc / B;
+  static const int lh_group_env = []() { const char* e = getenv("MMQG_LH_STEPS"); return e ? atoi(e) : 0; }();
+  const int lh_steps = lh_group_env > 0 ? lh_group_env : (w.Rc / B > 1 ? w.Rc / B : 1);      // whole steps per loss-head group
   const bool lh_overlap = lh_env && lh_steps >= 1 && d.T_q > 1;
   int lh_done = 0;      // steps whose loss head has been issued
   PdlScope pdl_scope(pdl_enabled());      // the dependent launches below overlap prologue and tail
+  L2WindowScope l2_scope(w.m_txt16, attn_l2_window(d, w));     // attention memories stay in L2 across the T_q steps
   // MMQG_STEP_FUSE: 0 = product + cell kernel, 1 = one fused launch (lstm_step_tc.cu), 2 = split-K product + summing cell kernel
   static const int step_mode_env = []() { const char* e = getenv("MMQG_STEP_FUSE"); return e ? atoi(e) : 2; }();
   const int step_mode = step_mode_env;
@@ -768,14 +785,16 @@ static int greedy_decode_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
     }
     const b16* htop = w.hs_dec[d.L - 1] + (size_t)(t + 1) * B * H;
     PdlScope no_pdl(false);
-    for (int r0 = 0; r0 < B; r0 += w.Rc) {
-      const int rc = B - r0 < w.Rc ? B - r0 : w.Rc;
+    if (!sample) {     // vocabulary projection with the arg-max in its epilogue: no logits in memory (train.py:106-108)
+      MMQG_TRY(vocab_argmax(htop, H, w.wo, H, P.out_b, B, d.V, H, w.stat_a, reinterpret_cast<int*>(w.stat_b), tokens_out + t, max_len,
+                            w.idx_cur, st));
+      continue;
+    }
+    for (int r0 = 0; r0 < B; r0 += w.Rs) {
+      const int rc = B - r0 < w.Rs ? B - r0 : w.Rs;
       MMQG_TRY(Tc(htop + (size_t)r0 * H, H, false, w.wo, H, false, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(st));
-      if (sample)
-        MMQG_TRY(sample_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, seed,
-                             (unsigned long long)t, r0, B, st));
-      else
-        MMQG_TRY(argmax_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, st));
+      MMQG_TRY(sample_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, seed,
+                           (unsigned long long)t, r0, B, st));
     }
   }
   return 0;
@@ -801,6 +820,7 @@ struct Bwd16 {
     MMQG_CUDA(cudaMemsetAsync(w.ds_all, 0, sizeof(float) * (size_t)R * Sp, st));
     MMQG_CUDA(cudaMemsetAsync(w.ds16, 0, sizeof(b16) * (size_t)R * Sp, st));
     PdlScope pdl_scope(pdl_enabled());
+    L2WindowScope l2_scope(w.m_txt16, attn_l2_window(d, w));
     for (int t = d.T_q - 1; t >= 0; --t) {
       StepGemmScope step_scope;
       const bool last = t == d.T_q - 1;

@@ -206,7 +206,7 @@ int gemm_bf16(const mmqg_gemm_bf16_args& g, cudaStream_t st) {
   } else {
     ta2 = ta; tb2 = tb;
   }
-  TcGemmP p;
+  TcGemmP p{};
   p.M = g.M; p.N = g.N; p.nk1 = ceil_div(g.K, TBK); p.nk2 = g.K2 > 0 ? ceil_div(g.K2, TBK) : 0;
   p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_bf16;
   p.Cin = g.Cin; p.ldcin = g.ldcin; p.beta = g.beta; p.alpha = g.alpha; p.bias = g.bias;

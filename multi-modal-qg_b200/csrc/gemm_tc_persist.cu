@@ -25,7 +25,132 @@ static constexpr int PA_BYTES = PBM * PBK * 2, PB_BYTES = PBN * PBK * 2;
 static constexpr int PSTG_FLOATS = 4 * EPI_STG_FLOATS;
 static constexpr int PSMEM = PSTAGES * (PA_BYTES + PB_BYTES) + PSTG_FLOATS * 4 + 1024;
 
-template <bool A_MN, bool B_MN>
+// ---- fused vocabulary epilogues (decoder.py:106 + train.py:174 / train.py:107-108) --------------------------
+// One epilogue warp owns 32 rows of the 128 x 256 logits tile; tcgen05.ld hands every thread ONE row, so the
+// row-wise softmax statistics / arg-max / d logits are plain register arithmetic, 32 columns at a time.
+//   VE_STATS  : per (tile, row) running max m and s = sum exp(x - m) over the tile's columns, plus the target
+//               column's logit; a tiny merge kernel turns the tiles_n partials of a row into lse and the NLL.
+//   VE_DLOGITS: recomputes the tile and stores row_scale * (exp(x - lse) - onehot) as bf16 (coalesced through a
+//               per-warp shared-memory transpose): the operand of the dH / dW_out products.
+//   VE_ARGMAX : per (tile, row) maximum and its lowest column (greedy decode); merged the same way.
+// x = acc + bias; columns >= N get bias = -inf, i.e. probability 0.
+template <int MODE>
+__device__ __forceinline__ void vocab_epilogue(uint32_t taddr, float* stg, const TcGemmP& p, int m0w, int n0, int tile_n, int lane,
+                                               uint64_t* release_bar) {
+  using namespace tc;
+  const int row = m0w + lane;
+  const bool rvalid = row < p.M;
+  // bias of the tile's 256 columns -> this warp's staging area (broadcast reads below)
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + 32 * i + lane;
+    stg[32 * i + lane] = n < p.N ? (p.bias ? p.bias[n] : 0.f) : -INFINITY;
+  }
+  __syncwarp();
+  long long tgt = -1;
+  if (MODE != VE_ARGMAX && rvalid && p.targets) {
+    tgt = p.targets[row];
+    tgt = tgt < 0 ? 0 : (tgt >= p.N ? p.N - 1 : tgt);
+  }
+  if (MODE == VE_STATS || MODE == VE_ARGMAX) {
+    float m = -INFINITY, ssum = 0.f, tl = 0.f;
+    int bi = 0x7fffffff;
+    bool has_t = false;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+      if (c == 7 && release_bar) {
+        tc_fence_before_sync();
+        mbar_arrive(release_bar);
+      }
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] += stg[32 * c + j];
+        cm = fmaxf(cm, v[j]);
+      }
+      if (MODE == VE_STATS) {
+        const float mn = fmaxf(m, cm);
+        float acc = 0.f;
+        if (mn > -INFINITY) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += __expf(v[j] - mn);
+          ssum = ssum * __expf(m - mn) + acc;      // m = -inf on the first chunk: exp(-inf) = 0, ssum is 0 anyway
+        }
+        m = mn;
+        const long long offl = tgt - (n0 + 32 * c);
+        const int off = (offl >= 0 && offl < 32) ? (int)offl : -1;      // branch-free select keeps v[] in registers
+        has_t = has_t || off >= 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tl = (j == off) ? v[j] : tl;
+      } else {
+        if (cm > m) {        // strict: an equal maximum in a later chunk keeps the earlier (lower) column
+          m = cm;
+          int k = 31;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) k = min(k, v[j] == cm ? j : 31);
+          bi = n0 + 32 * c + k;
+        }
+      }
+    }
+    if (rvalid) {
+      const size_t o = (size_t)tile_n * p.M + row;
+      p.stat_a[o] = m;
+      if (MODE == VE_STATS) {
+        p.stat_b[o] = ssum;
+        if (has_t) p.tgt_logit[row] = tl;
+      } else {
+        p.stat_i[o] = bi;
+      }
+    }
+  } else {      // VE_DLOGITS
+    const float lse = rvalid ? p.lse[row] : 0.f;
+    const float rs = rvalid ? p.row_scale[row] : 0.f;
+    __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C);
+    uint32_t* stw = reinterpret_cast<uint32_t*>(stg + 256);        // 32 rows x 20 words behind the bias tile
+    const int rows = min(32, p.M - m0w);
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+      if (c == 7 && release_bar) {
+        tc_fence_before_sync();
+        mbar_arrive(release_bar);
+      }
+      const long long off = tgt - (n0 + 32 * c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pr = __expf(v[j] + stg[32 * c + j] - lse);
+        v[j] = rs * (pr - ((long long)j == off ? 1.f : 0.f));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * q4 + 2 * e], v[8 * q4 + 2 * e + 1]);
+          w[e] = *reinterpret_cast<uint32_t*>(&t2);
+        }
+        *reinterpret_cast<uint4*>(stw + lane * 20 + 4 * q4) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      __syncwarp();
+      const int nb = n0 + 32 * c + 8 * (lane & 3);       // first of this lane's 8 columns
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + (lane >> 2);
+        const uint4 x = *reinterpret_cast<const uint4*>(stw + r * 20 + 4 * (lane & 3));
+        if (r < rows && nb < p.ldc) *reinterpret_cast<uint4*>(C + (size_t)(m0w + r) * p.ldc + nb) = x;
+      }
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN, int EPI = VE_NONE>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, TcGemmP p) {
@@ -120,8 +245,12 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int m0 = (tile / tiles_n) * PBM, n0 = (tile % tiles_n) * PBN;
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after_sync();
-      epilogue_block<PBN / 32>(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * PBN, stg, out, m0 + 32 * q, n0, lane,
-                               &acc_empty[buf]);
+      if (EPI == VE_NONE)
+        epilogue_block<PBN / 32>(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * PBN, stg, out, m0 + 32 * q, n0, lane,
+                                 &acc_empty[buf]);
+      else
+        vocab_epilogue<EPI>(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * PBN, stg, p, m0 + 32 * q, n0, tile % tiles_n, lane,
+                            &acc_empty[buf]);
     }
     tc_fence_before_sync();
   }
@@ -149,6 +278,32 @@ static int launch_persist(const CUtensorMap& a, const CUtensorMap& b, const CUte
   gemm_tc_persist_kernel<A_MN, B_MN><<<grid, 192, PSMEM, st>>>(a, b, a2, b2, p);
   MMQG_LAUNCH_CHECK();
   return 0;
+}
+
+template <int EPI>
+static int launch_vocab(const CUtensorMap& a, const CUtensorMap& b, const TcGemmP& p, cudaStream_t st) {
+  static bool attr = false;
+  static int sms = 0;
+  if (!attr) {
+    MMQG_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<false, false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM));
+    int dev = 0;
+    MMQG_CUDA(cudaGetDevice(&dev));
+    MMQG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr = true;
+  }
+  const int n_tiles = ceil_div(p.M, PBM) * ceil_div(p.N, PBN);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  gemm_tc_persist_kernel<false, false, EPI><<<grid, 192, PSMEM, st>>>(a, b, a, b, p);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+// X (M,K) K-major  x  W (N,K) K-major with one of the fused vocabulary epilogues
+int gemm_tc_vocab_launch(const CUtensorMap& a, const CUtensorMap& b, const TcGemmP& p, int mode, cudaStream_t st) {
+  if (mode == VE_STATS) return launch_vocab<VE_STATS>(a, b, p, st);
+  if (mode == VE_DLOGITS) return launch_vocab<VE_DLOGITS>(a, b, p, st);
+  if (mode == VE_ARGMAX) return launch_vocab<VE_ARGMAX>(a, b, p, st);
+  return set_err(MMQG_ERR_BAD_ARG, "gemm_tc_vocab_launch: mode %d", mode);
 }
 
 int gemm_tc_persist_launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2,

@@ -135,6 +135,19 @@ size_t greedy_workspace_bytes_bf16(const mmqg_dims& d, int max_len);
 int train_backward_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_batch& bt, void* workspace,
                         size_t workspace_bytes, mmqg_tensors& Gd, int phase, float dropout_p, unsigned long long seed,
                         cudaStream_t st, cudaEvent_t const* ready = nullptr);
+// fused vocabulary projection + log-softmax + NLL, backward, greedy arg-max (vocab_nll.cu)
+size_t vocab_stat_floats(int R, int V);
+int vocab_chunk_rows(int R, int Vp);
+int vocab_nll_fwd(const void* X, int ldx, const void* W, int ldw, const float* bias, const int64_t* targets, const float* row_w, int R,
+                  int V, int H, float dscale, float* nll, float* lse, float* row_scale, float* stat_a, float* stat_b, float* tgt_logit,
+                  cudaStream_t st);
+int vocab_dlogits(const void* X, int ldx, const void* W, int ldw, const float* bias, const int64_t* targets, const float* lse,
+                  const float* row_scale, int R, int V, int H, void* dlogits, int lddl, cudaStream_t st);
+int vocab_nll_bwd(const void* X, int ldx, const void* W, int ldw, const float* bias, const int64_t* targets, const float* lse,
+                  const float* row_scale, int R, int V, int H, void* dl, int Vp, int rc_rows, float* part, float* dH, int lddh, float* dW,
+                  float* db, bool accumulate, cudaStream_t st);
+int vocab_argmax(const void* X, int ldx, const void* W, int ldw, const float* bias, int R, int V, int H, float* stat_a, int* stat_i,
+                 int64_t* tokens, long long tok_stride, int64_t* tokens2, cudaStream_t st);
 int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* nll, int R, int V, float scale,
                   void* dlogits, int lddl, cudaStream_t st, const float* row_w = nullptr);
 int attn_fwd(float* scores, int lds, const float* M_txt, const float* M_aud, const float* M_vid, float* ctx,

@@ -564,6 +564,308 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BPTT kernel, split-K over a 4-CTA cluster (round 2).
+//
+// lstm_seq_bwd_kernel above gives every CTA the output slice D[128 x 16] = dG_{t+1}[128 x 4H] . W_hh[:, 16 units]:
+// each CTA streams the WHOLE 512 KB dG tile of its m-tile every step, and at ~100 GB/s of L2->SM ingest
+// per SM that is 5 of the step's 9.7 us (profiles/r01_ncu_full_prof_r1d: tensor pipe 5.7 %).
+// Here the 4 CTAs of a cluster own 64 hidden units together and split the K = 4H reduction by GATE:
+// CTA rank r keeps W_hh[gate r rows, 64 units]^T (64 x H bf16, 64 KB at H=512) resident, streams only the
+// gate-r quarter of dG_{t+1} (128 x H bf16 = 128 KB per step) and forms the partial product
+// P_r[128 x 64] in TMEM.  The partials are exchanged through distributed shared memory: every thread
+// (= batch row) stores the 16-column blocks that belong to the three peer CTAs straight into their
+// exchange buffers with st.async, which reports the bytes to the receiving warp's mbarrier (complete_tx):
+// no fence and no separate arrive; after its own barrier completes (3 peers x 32 rows x 64 B) the thread sums
+// the four partials of its 16 units and continues with the pointwise cell gradient exactly like the
+// kernel above.  Exchange buffers are double-buffered by step parity: a peer can only write buffer b
+// again after it has received this CTA's partial of the step in between, which this CTA sends after it
+// has consumed buffer b -- no "buffer free" message is needed.
+// Cross-cluster hand-over of dG_t is unchanged (global memory + one arrival counter per (t, m-tile)).
+struct LstmBwd4Smem {
+  static constexpr int STAGES = 6;
+  static constexpr int XROW = 64;                   // bytes per exchanged row (16 fp32)
+  static constexpr int XSRC = 128 * XROW;           // one source CTA's block: 128 rows
+  static constexpr int XBUF = 3 * XSRC;             // three peers
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// asynchronous remote store that reports its 16 bytes to an mbarrier in the destination CTA (complete_tx)
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t cluster_bar, float a, float b, float c, float d) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%2, %3, %4, %5}, [%1];"
+               ::"r"(cluster_addr), "r"(cluster_bar), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(192, 1)
+lstm_seq_bwd4_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, LstmBwdP p) {
+  constexpr int STAGES = LstmBwd4Smem::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int KB = p.H / 64;                    // 64-wide k-blocks of one gate
+  uint8_t* sW = smem;                         // KB x (64 rows x 128 B): W_hh[gate r, 64 units]^T, resident
+  uint8_t* sA = sW + KB * 8192;               // STAGES x (128 rows x 128 B): streamed quarter of dG_{t+1}
+  uint8_t* sX = sA + STAGES * 16384;          // 2 x 3 x (128 rows x 64 B): partials received from the peers
+  float* stg_base = reinterpret_cast<float*>(sX + 2 * LstmBwd4Smem::XBUF);
+  __shared__ uint64_t w_full, full[STAGES], empty[STAGES], mma_done, tmem_free, xfull[2][4];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x, mt = blockIdx.y;
+  const int rank = (int)cluster_ctarank();    // == slice & 3: gate (K quarter) of this CTA
+  const int unit0 = (slice >> 2) * 64;        // first hidden unit of the cluster
+  const int H = p.H, B = p.B, G = 4 * p.H, T = p.T;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&w_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&mma_done, 1);
+    mbar_init(&tmem_free, 128);
+    for (int b2 = 0; b2 < 2; ++b2)            // one per (buffer, epilogue warp): completes on 3 peers x 32 rows x 64 bytes
+      for (int w2 = 0; w2 < 4; ++w2) mbar_init(&xfull[b2][w2], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 5) tmem_alloc(&tmem_slot, 64);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  cluster_sync_all();                         // peers' mbarriers exist before anyone arrives on them
+  const uint32_t tmem_base = tmem_slot;
+  const int t_first = T - 1 - (p.has_next ? 0 : 1);     // first step that has a matrix product
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_expect_tx(&w_full, KB * 8192);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, &w_full, rank * H + kb * 64, unit0);
+      int i = 0;
+      for (int t = t_first; t >= 0; --t) {          // step t consumes dG_{t+1}
+        if (t + 1 < T) {                            // slab T comes from an earlier launch: already complete
+          const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
+          while (ld_relaxed_gpu(f) < (uint32_t)p.n_slices) {
+          }
+          fence_acq_rel_gpu();
+          fence_proxy_async();
+        }
+        for (int kb = 0; kb < KB; ++kb, ++i) {
+          const int s = i % STAGES, ph = (i / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], 16384);
+          tma_load_2d(sA + s * 16384, &tmG, &full[s], rank * H + kb * 64, (t + 1) * B + mt * 128);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(&w_full, 0);
+      int i = 0, it = 0;
+      for (int t = t_first; t >= 0; --t, ++it) {
+        if (it > 0) mbar_wait(&tmem_free, (it - 1) & 1);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < KB; ++kb, ++i) {
+          const int s = i % STAGES, ph = (i / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + s * 16384), b_addr = smem_u32(sW + kb * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, umma_smem_desc(a_addr + k * 32, 16, 1024), umma_smem_desc(b_addr + k * 32, 16, 1024),
+                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&mma_done);
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const int m0w = mt * 128 + warp * 32;
+    const int m = m0w + lane;
+    const bool valid = m < B;
+    const int rows_valid = max(0, min(32, B - m0w));
+    const int j0 = slice * 16;                 // == unit0 + 16 * rank
+    float* stg = stg_base + warp * STG_WARP;
+    const bool kt = p.ktrace && row == 0 && slice == 0 && mt == 0;
+    const int kslot = kt ? ktrace_begin(p.ktrace, p.ktag) : 0;
+    const int sh = (p.len.shift && valid) ? p.len.shift[m] : 0;
+    // exchange addressing: row `row` of source s lives at sX + buf*XBUF + slot(s)*XSRC + row*64, its four 16-byte
+    // chunks XOR-swizzled with (row >> 1) & 3 so that neither the remote stores nor the local loads conflict
+    const uint32_t xrow_off = (uint32_t)row * LstmBwd4Smem::XROW;
+    const uint32_t swz = (uint32_t)(row >> 1) & 3u;
+    uint32_t peer_x[4], peer_bar[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int my_slot_at_peer = rank < rr ? rank : rank - 1;      // slot index of source `rank` inside peer rr
+      peer_x[rr] = mapa_u32(smem_u32(sX) + my_slot_at_peer * LstmBwd4Smem::XSRC + xrow_off, (uint32_t)rr);
+      peer_bar[0][rr] = mapa_u32(smem_u32(&xfull[0][warp]), (uint32_t)rr);
+      peer_bar[1][rr] = mapa_u32(smem_u32(&xfull[1][warp]), (uint32_t)rr);
+    }
+    float dc[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) dc[u] = (p.dc_last && valid) ? p.dc_last[(size_t)m * H + j0 + u] : 0.f;
+    int it = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      float4 a4[4][4], cn4[4], cp4[4], ex4[4];
+      const float* abase = p.acts + ((size_t)t * B + m0w) * G + j0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) coop_ldg(abase + g * H, G, rows_valid, lane, a4[g]);
+      coop_ldg(p.cs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid, lane, cn4);
+      coop_ldg(p.cs + ((size_t)t * B + m0w) * H + j0, H, rows_valid, lane, cp4);
+      const int tg = p.len.t_base + t;
+      if (p.dh_ext && p.len.shift && p.len.mem_shift)
+        coop_ldg_shift(p.dh_ext + (size_t)t * p.ext_ts + (size_t)m0w * p.ext_ld + j0, (size_t)p.ext_ld, rows_valid, lane, ex4, sh, tg, p.ext_ts);
+      else if (p.dh_ext) coop_ldg(p.dh_ext + (size_t)t * p.ext_ts + (size_t)m0w * p.ext_ld + j0, (size_t)p.ext_ld, rows_valid, lane, ex4);
+      else {
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) ex4[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float a[64], cn[16], cp[16], ex[16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) coop_to_row(stg, lane, a4[g], a + g * 16);
+      coop_to_row(stg, lane, cn4, cn);
+      coop_to_row(stg, lane, cp4, cp);
+      coop_to_row(stg, lane, ex4, ex);
+      if (p.dr.p > 0.f) {     // ext is d/d(dropped h_t): back through this layer's output mask
+        const float ik = 1.0f / (1.0f - p.dr.p);
+        const unsigned long long sd = p.dr.seed + (p.dr.ctr ? *p.dr.ctr : 0ull);
+        const unsigned long long e0 = p.dr.base + ((unsigned long long)t * B + m) * H + j0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) ex[u] *= drop_scale(sd, p.dr.sid, e0 + u, p.dr.p, ik);
+      }
+      float dh[16];
+      if (t == T - 1 && !p.has_next) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) dh[u] = (p.dh_last && valid) ? p.dh_last[(size_t)m * H + j0 + u] : 0.f;
+      } else {
+        const int xb = it & 1;
+        mbar_wait(&mma_done, it & 1);
+        tc_fence_after_sync();
+        float part[64];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + q * 16, part + q * 16);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&tmem_free);
+        // this warp's receive barrier for the step: 3 peers x 32 rows x 64 bytes will be reported to it
+        if (lane == 0) mbar_expect_tx(&xfull[xb][warp], 3 * 32 * LstmBwd4Smem::XROW);
+        // send: columns [16 rr, 16 rr + 16) of this CTA's partial belong to peer rr (same warp index there);
+        // every 16-byte store reports itself to that warp's barrier -- no fence, no separate arrive
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          if (rr == rank) continue;
+          const uint32_t dst = peer_x[rr] + (uint32_t)xb * LstmBwd4Smem::XBUF;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            st_async_v4(dst + (((uint32_t)c ^ swz) << 4), peer_bar[xb][rr], part[16 * rr + 4 * c], part[16 * rr + 4 * c + 1],
+                        part[16 * rr + 4 * c + 2], part[16 * rr + 4 * c + 3]);
+        }
+        // receive the three peers' partials of this warp's 32 rows
+        mbar_wait_cluster(&xfull[xb][warp], (uint32_t)(it >> 1) & 1u);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) dh[u] = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)        // own partial without a trip through shared memory
+          if (rr == rank) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) dh[u] = part[16 * rr + u];
+          }
+        const uint8_t* xin = sX + xb * LstmBwd4Smem::XBUF + xrow_off;
+#pragma unroll
+        for (int sl = 0; sl < 3; ++sl) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(xin + sl * LstmBwd4Smem::XSRC + (((uint32_t)c ^ swz) << 4));
+            dh[4 * c] += v.x; dh[4 * c + 1] += v.y; dh[4 * c + 2] += v.z; dh[4 * c + 3] += v.w;
+          }
+        }
+        ++it;
+      }
+      {
+        float dgv[64];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float ig = a[u], fg = a[16 + u], gg = a[32 + u], og = a[48 + u];
+          const float d = dh[u] + ex[u];
+          const float tc_ = tanh_fast(cn[u]);
+          const float dct = dc[u] + d * og * (1.f - tc_ * tc_);
+          dgv[u] = dct * gg * ig * (1.f - ig);
+          dgv[16 + u] = dct * cp[u] * fg * (1.f - fg);
+          dgv[32 + u] = dct * ig * (1.f - gg * gg);
+          dgv[48 + u] = d * tc_ * og * (1.f - og);
+          dc[u] = dct * fg;
+        }
+        if (tg < sh) {        // masked step: no gradient reaches the weights or anything earlier
+#pragma unroll
+          for (int u = 0; u < 64; ++u) dgv[u] = 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) dc[u] = 0.f;
+        }
+        bf16* dbase = p.dg + ((size_t)t * B + m0w) * G + j0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w8[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(dgv[g * 16 + 2 * v], dgv[g * 16 + 2 * v + 1]);
+            w8[v] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, w8, dbase + g * H, G, rows_valid);
+        }
+      }
+      epi_bar_sync();
+      if (row == 0) {
+        __threadfence();
+        red_relaxed_gpu_add(p.flags + (size_t)t * p.n_mt + mt, 1u);
+      }
+    }
+    if (p.dc_out) {
+      float4 tmp[4];
+      row_to_coop(stg, lane, dc, tmp);
+      coop_stg(p.dc_out + (size_t)m0w * H + j0, H, rows_valid, lane, tmp);
+    }
+    if (kt) ktrace_end(p.ktrace, kslot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                         // no CTA leaves while a peer may still store into its exchange buffers
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
 // gate-slice packing of W_hh for the forward kernel: row (s*64 + g*16 + u) = W_hh[g*H + s*16 + u, :]
 __global__ void pack_whh_fwd_kernel(const float* __restrict__ w, bf16* __restrict__ out, int H) {
   const int r = blockIdx.x;                 // packed row
@@ -673,12 +975,89 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
   return 0;
 }
 
+// Launch with a (4,1,1) cluster AND the cooperative attribute: the clusters of one launch still wait on
+// each other through the global arrival counters, so the whole grid must be co-resident.
+template <typename Kern, typename P>
+static cudaError_t launch_coop_cluster4(Kern kern, dim3 grid, int threads, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1,
+                                        const P& p, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 4;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kern, m0, m1, p);
+}
+
+static size_t bwd4_smem_bytes(int H) {
+  return (size_t)(H / 64) * 8192 + LstmBwd4Smem::STAGES * 16384 + 2 * LstmBwd4Smem::XBUF + 4 * STG_WARP * sizeof(float) + 1024;
+}
+
+// 1 = split-K cluster kernel usable on this device for hidden size H, 0 = not (fall back to lstm_seq_bwd_kernel).
+// Decided once per H by an occupancy query with the exact launch attributes; MMQG_BWD4=0 forces the old kernel.
+static int g_bwd4_state[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};      // index H/64
+static int bwd4_state(int H) {
+  int* state = g_bwd4_state;
+  const int idx = H / 64;
+  if (H % 64 != 0 || idx < 1 || idx > 8) return 0;
+  if (state[idx] >= 0) return state[idx];
+  const char* e = getenv("MMQG_BWD4");
+  if (e && e[0] == '0') return state[idx] = 0;
+  const size_t smem = bwd4_smem_bytes(H);
+  if (cudaFuncSetAttribute(lstm_seq_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd4_smem_bytes(512)) != cudaSuccess) {
+    cudaGetLastError();
+    return state[idx] = 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(H / 16, 1);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&n_clusters, lstm_seq_bwd4_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return state[idx] = 0;
+  }
+  return state[idx] = n_clusters >= 1 ? 1 : 0;
+}
+
 int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext,
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
                          int T, int B, int H, int has_next, float* dc_out, cudaStream_t st, DropSpec dr, bool zero_flags, LenSpec len) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_bwd_persist: shape B=%d H=%d not supported", B, H);
   LstmBwdP p{acts, cs, reinterpret_cast<bf16*>(dg), dh_ext, ext_ts, ext_ld, dh_last, dc_last, flags,
              T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64, has_next, dc_out, g_ktrace, 1000 + tl_ktag, dr, len};
+  if (bwd4_state(H) == 1) {
+    CUtensorMap tmW4, tmG4;
+    MMQG_TRY(make_tmap_bf16_2d(&tmW4, wp_bwd, H, 4 * (uint64_t)H, 4 * (uint64_t)H, 64, 64));
+    MMQG_TRY(make_tmap_bf16_2d(&tmG4, dg, (uint64_t)(T + (has_next ? 1 : 0)) * B, 4 * (uint64_t)H, 4 * (uint64_t)H, 128, 64));
+    if (zero_flags) MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)T * p.n_mt, st));
+    const double fl4 = 2.0 * (T - 1) * B * 4.0 * H * H;
+    MMQG_PROBE(KC_LSTM_PERSIST, fl4, 0);
+    const cudaError_t le = launch_coop_cluster4(lstm_seq_bwd4_kernel, dim3(p.n_slices, p.n_mt), 192, bwd4_smem_bytes(H), tmW4, tmG4, p, st);
+    if (le == cudaSuccess) {
+      MMQG_LAUNCH_CHECK();
+      return 0;
+    }
+    // the driver refused the cooperative cluster launch: say so once and use the single-CTA-slice kernel from now on
+    fprintf(stderr, "libmmqg: cooperative (4,1,1)-cluster launch of lstm_seq_bwd4_kernel failed (%s); falling back to lstm_seq_bwd_kernel\n",
+            cudaGetErrorString(le));
+    cudaGetLastError();
+    probe_close(st);
+    g_bwd4_state[H / 64] = 0;
+  }
   CUtensorMap tmW, tmG;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_bwd, H, 4 * (uint64_t)H, 4 * (uint64_t)H, 16, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmG, dg, (uint64_t)(T + (has_next ? 1 : 0)) * B, 4 * (uint64_t)H, 4 * (uint64_t)H, 128, 64));

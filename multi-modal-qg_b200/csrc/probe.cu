@@ -12,6 +12,36 @@ namespace mmqg {
 thread_local int tl_gemm_class = KC_GEMM_SEQ;
 thread_local int tl_pdl = 0;
 
+thread_local const void* tl_l2win_base = nullptr;
+thread_local size_t tl_l2win_bytes = 0;
+
+size_t l2_window_reserve(size_t bytes, size_t window_bytes) {
+  static long long max_window = -1, reserved = 0, max_persist = 0;
+  if (max_window < 0) {
+    const char* e = getenv("MMQG_L2WIN");
+    int dev = 0, mw = 0, mp = 0;
+    cudaGetDevice(&dev);
+    if ((e && e[0] == '0') || cudaDeviceGetAttribute(&mw, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&mp, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess) {
+      cudaGetLastError();
+      mw = mp = 0;
+    }
+    max_window = mw;
+    max_persist = mp;
+  }
+  if (max_window <= 0 || max_persist <= 0) return 0;
+  long long want = (long long)bytes < max_persist ? (long long)bytes : max_persist;
+  if (want > reserved) {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want) != cudaSuccess) {
+      cudaGetLastError();
+      max_window = 0;
+      return 0;
+    }
+    reserved = want;
+  }
+  return (long long)window_bytes <= max_window ? window_bytes : 0;      // a clipped window would leave rows unpinned
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {

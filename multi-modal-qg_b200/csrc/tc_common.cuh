@@ -175,7 +175,18 @@ struct TcGemmP {
   const float* Cin; int ldcin; float beta, alpha;
   const float* bias;
   int split_k; long long c_split_stride;
+  // fused vocabulary epilogues of the persistent kernel (gemm_tc_persist.cu, VocabEpi): the logits tile
+  // acc + bias never leaves tensor memory / registers
+  const long long* targets;    // (M) target token per row                        [stats, dlogits]
+  const float* lse;            // (M) log-sum-exp per row                         [dlogits]
+  const float* row_scale;      // (M) scale of d loss / d logits per row          [dlogits]
+  float* stat_a;               // (tiles_n, M) per-tile running max               [stats, argmax]
+  float* stat_b;               // (tiles_n, M) per-tile sum exp(x - max)          [stats]
+  int* stat_i;                 // (tiles_n, M) per-tile arg-max column            [argmax]
+  float* tgt_logit;            // (M) logit of the target column                  [stats]
 };
+enum VocabEpi { VE_NONE = 0, VE_STATS = 1, VE_DLOGITS = 2, VE_ARGMAX = 3 };
+int gemm_tc_vocab_launch(const CUtensorMap& a, const CUtensorMap& b, const TcGemmP& p, int mode, cudaStream_t st);
 // Persistent 128x256-tile variant for large problems (gemm_tc_persist.cu).
 int gemm_tc_persist_launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2,
                            const TcGemmP& p, bool a_mn, bool b_mn, cudaStream_t st);

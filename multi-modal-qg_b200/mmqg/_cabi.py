@@ -86,6 +86,10 @@ SYMBOLS = {
     "mmqg_nll_rows": (_i, [_fp, _i, _fp, _ll, _fp, _i, _i, _f, _fp]),
     "mmqg_argmax_rows": (_i, [_fp, _i, _fp, _ll, _i, _i, _fp]),
     "mmqg_colsum": (_i, [_fp, _i, _fp, _i, _i, _f, _fp]),
+    "mmqg_vocab_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mmqg_vocab_nll_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp, _sz, _fp, _fp, _fp, _fp]),
+    "mmqg_vocab_nll_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _fp, _sz, _fp, _fp, _fp, _i, _fp]),
+    "mmqg_decode_step_argmax": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp, _sz, _fp, _ll, _fp]),
 }
 
 _lib = None
@@ -106,7 +110,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.mmqg_abi_version() != 2:
+        if L.mmqg_abi_version() != 3:
             raise MmqgError("libmmqg.so ABI version mismatch")
         _lib = L
     return _lib

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported(cabi):
     for name in declared:
         assert hasattr(L, name), f"{name} declared in mmqg.h but not exported"
     assert declared == set(cabi.SYMBOLS), declared ^ set(cabi.SYMBOLS)
-    assert L.mmqg_abi_version() == 2
+    assert L.mmqg_abi_version() == 3
 
 
 def test_struct_layouts(cabi):

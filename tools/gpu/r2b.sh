@@ -1,0 +1,12 @@
+set -x
+mkdir -p gpurun_out/r2b
+O=gpurun_out/r2b
+timeout 600 python -m pytest tests/test_gpu_bf16_mode.py tests/test_gpu_bench_shapes.py -x -q -s -k "not cfg4 and not cfg5" > $O/pytest_bwd4.log 2>&1; echo "rc=$?" >> $O/pytest_bwd4.log
+tail -5 $O/pytest_bwd4.log
+timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-parity > $O/bench_bwd4.json 2> $O/bench_bwd4.err
+MMQG_BWD4=0 timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-parity > $O/bench_bwd_old.json 2> $O/bench_bwd_old.err
+MMQG_L2WIN=1 timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-parity > $O/bench_bwd4_l2win.json 2> $O/bench_bwd4_l2win.err
+timeout 120 python tools/sections.py > $O/sections.log 2>&1
+MMQG_L2WIN=1 timeout 120 python tools/sections.py > $O/sections_l2win.log 2>&1
+timeout 120 python tools/ktrace.py --graph > $O/ktrace.log 2>&1
+grep -h '"value"' $O/*.json | cut -c1-120
