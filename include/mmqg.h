@@ -155,12 +155,16 @@ int mmqg_sample_decode(const mmqg_dims* d, const mmqg_tensors* params, const mmq
                        void* workspace, size_t workspace_bytes, int64_t* tokens_out, int max_len,
                        unsigned long long seed, int mode, void* stream);
 
-/* The whole backward (as phase 0, with its internal overlap) for data-parallel callers:
- * ready_events[i] (a cudaEvent_t created by the caller, or NULL) is recorded at the point
- * where gradient group i+1 (1 decoder, 2 video, 3 text + embedding) is final -- on
- * whichever stream finalises it -- so the caller can make its communication stream wait on
- * the event and start that group's all-reduce under the rest of the backward
- * (SURVEY.md section 8e).  All work is joined back onto `stream` before the call returns. */
+/* The whole backward (as phase 0, with its internal overlap) for data-parallel callers.
+ * ready_events: array of 3 + L cudaEvent_t created by the caller (entries may be NULL); each is recorded at
+ * the point -- and on whichever internal stream -- where one gradient group becomes final, so the caller can
+ * make its communication stream wait on the event and start that group's all-reduce under the rest of the
+ * backward:
+ *   [0] decoder (attention Linears + decoder LSTM)      [1] video LSTM
+ *   [2 + k] text LSTM layer L-1-k, k = 0 .. L-1 (the top layer's BPTT and weight gradients finish first)
+ *   [2 + L] the shared embedding (decoder- and encoder-side scatter-adds both landed: last of all).
+ * All work is joined back onto `stream` before the call returns.  Data-parallel callers give every rank its
+ * own dropout `seed`, otherwise local sample b draws the same masks on every rank. */
 int mmqg_train_backward_events(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,
                                void* workspace, size_t workspace_bytes, mmqg_tensors* grads,
                                void* const* ready_events, float dropout_p, unsigned long long seed,
@@ -283,6 +287,26 @@ int mmqg_argmax_rows(const float* logits, int ldl, int64_t* tokens, long long to
 int mmqg_sample_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int R, int V,
                      unsigned long long seed, unsigned long long step, void* stream);
 int mmqg_sample_uniform(float* out, int n, unsigned long long seed, unsigned long long step, void* stream);
+/* ---- one LSTM layer over a whole sequence (K1 + K2 / K5): SURVEY.md section 8b minimum export set ----
+ * What the reference does with T per-token aten::lstm calls (encoder.py:95-100 driven by train.py:164-166;
+ * encoder.py:69; decoder.py:25-34) and autograd's T backward twins, as one forward and one backward call:
+ * hoisted input projection (one tcgen05 GEMM over T*B rows) + persistent recurrent kernel, persistent BPTT
+ * kernel + hoisted weight-gradient products.  bf16 operands, fp32 accumulation / cell state / results.
+ * x (T*B, I) rows t*B + b; weights in PyTorch layout (4H, I) / (4H, H), gate blocks i,f,g,o; h0, c0 (B, H) or
+ * NULL (zeros).  y (T*B, H) = h_t; hn, cn (B, H) may be NULL.  Needs H % 64 == 0, H <= 512 and
+ * (H/16) * ceil(B/128) CTAs co-resident (MMQG_ERR_BAD_ARG otherwise: use the per-step building blocks).
+ * The workspace carries the saved activations from _fwd to _bwd: keep it untouched in between. */
+size_t mmqg_lstm_seq_workspace_bytes(int T, int B, int I, int H);
+int mmqg_lstm_seq_fwd(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                      const float* h0, const float* c0, int T, int B, int I, int H, void* workspace,
+                      size_t workspace_bytes, float* y, float* hn, float* cn, void* stream);
+/* dy (T*B, H), dhn, dcn (B, H): gradients w.r.t. y, hn, cn (any may be NULL = zeros).  Outputs (overwritten):
+ * dx (T*B, I) (NULL to skip), dw_ih, dw_hh, db_ih, db_hh (identical, as autograd gives both biases the same
+ * gradient; db_hh may be NULL), dh0, dc0 (B, H) (NULL to skip). */
+int mmqg_lstm_seq_bwd(const float* dy, const float* dhn, const float* dcn, const float* w_hh, int T, int B, int I, int H,
+                      void* workspace, size_t workspace_bytes, float* dx, float* dw_ih, float* dw_hh, float* db_ih,
+                      float* db_hh, float* dh0, float* dc0, void* stream);
+
 /* ---- fused loss head (K4) and greedy arg-max (K6): SURVEY.md section 8b minimum export set ---- */
 
 /* Scratch for the three calls below for R rows, vocabulary V, hidden size H (multiple of 8). */

@@ -321,8 +321,10 @@ int mmqg_train_backward_events(const mmqg_dims* dp, const mmqg_tensors* params, 
                                size_t workspace_bytes, mmqg_tensors* grads, void* const* ready_events, float dropout_p,
                                unsigned long long seed, int mode, void* stream) {
   MMQG_REQUIRE(ready_events, "ready_events: null pointer (use mmqg_train_backward phase 0)");
-  cudaEvent_t ev[3];
-  for (int i = 0; i < 3; ++i) ev[i] = reinterpret_cast<cudaEvent_t>(ready_events[i]);
+  MMQG_REQUIRE(dp && dp->L >= 1 && dp->L <= MMQG_MAX_LAYERS, "dims: L out of range");
+  const int n_ev = 3 + dp->L;         // decoder, video, text layers L-1 .. 0, shared embedding
+  cudaEvent_t ev[3 + MMQG_MAX_LAYERS];
+  for (int i = 0; i < n_ev; ++i) ev[i] = reinterpret_cast<cudaEvent_t>(ready_events[i]);
   if (mode == MMQG_MODE_BF16) {
     MMQG_TRY(check_dims(dp));
     MMQG_TRY(check_tensors(*dp, params, "params"));
@@ -334,7 +336,12 @@ int mmqg_train_backward_events(const mmqg_dims* dp, const mmqg_tensors* params, 
   }
   for (int ph = 1; ph <= 3; ++ph) {     // fp32 parity mode: phases in order on the caller's stream
     MMQG_TRY(mmqg_train_backward(dp, params, batch, workspace, workspace_bytes, grads, ph, dropout_p, seed, mode, stream));
-    if (ev[ph - 1]) MMQG_CUDA(cudaEventRecord(ev[ph - 1], as_stream(stream)));
+    if (ph < 3) {
+      if (ev[ph - 1]) MMQG_CUDA(cudaEventRecord(ev[ph - 1], as_stream(stream)));
+    } else {
+      for (int i = 2; i < n_ev; ++i)
+        if (ev[i]) MMQG_CUDA(cudaEventRecord(ev[i], as_stream(stream)));
+    }
   }
   return 0;
 }

@@ -647,6 +647,7 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   static const bool lh_env = []() { const char* e = getenv("MMQG_LOSS_OVERLAP"); return !(e && e[0] == '0'); }();
   static const int lh_group_env = []() { const char* e = getenv("MMQG_LH_STEPS"); return e ? atoi(e) : 0; }();
   const int lh_steps = lh_group_env > 0 ? lh_group_env : (w.Rc / B > 1 ? w.Rc / B : 1);      // whole steps per loss-head group
+  static const int lh_tail = []() { const char* e = getenv("MMQG_LH_TAIL"); return e ? atoi(e) : 1; }();
   const bool lh_overlap = lh_env && lh_steps >= 1 && d.T_q > 1;
   int lh_done = 0;      // steps whose loss head has been issued
   PdlScope pdl_scope(pdl_enabled());      // the dependent launches below overlap prologue and tail
@@ -699,7 +700,9 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
                      .bias(w.bsum_dec[l]).run(st));
       MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, c_prev, H, c_new, H, h_new, H, nullptr, 0, B, H, st, dr));
     }
-    if (lh_overlap && (t + 1 - lh_done == lh_steps || t == d.T_q - 1)) {
+    // groups of lh_steps steps; the last lh_tail steps form their own group so that only a short loss-head tail
+    // is exposed after the decoder loop
+    if (lh_overlap && (t + 1 - lh_done == lh_steps || t == d.T_q - 1 || t == d.T_q - 1 - lh_tail)) {
       MMQG_CUDA(cudaEventRecord(g_aux.ev[10], st));
       MMQG_CUDA(cudaStreamWaitEvent(lh, g_aux.ev[10], 0));
       MMQG_TRY(loss_head(lh_done * B, (t + 1 - lh_done) * B, lh_done == 0, lh));
@@ -997,7 +1000,7 @@ struct Bwd16 {
   // text layers pipelined over time chunks (mirror of the forward schedule): layer l runs chunk c
   // once layer l+1 has produced the input gradient of that chunk.  Layer l uses stream S(l); the
   // hoisted weight gradients of a finished layer go to `hoist`.
-  int text_pipelined(int NC, cudaStream_t st, cudaStream_t hoist) {
+  int text_pipelined(int NC, cudaStream_t st, cudaStream_t hoist, cudaEvent_t const* ready = nullptr) {
     const int CL = (d.T_t + NC - 1) / NC;
     auto S = [&](int l) { return l == L - 1 ? st : g_aux.s[L - 2 - l]; };      // stage k of the reverse pipeline on s[k-1]
     const int n_mt = (B + 127) / 128;
@@ -1039,6 +1042,7 @@ struct Bwd16 {
         if (c == 0) {
           MMQG_CUDA(cudaStreamWaitEvent(hoist, ev_bwd(l, 0), 0));
           MMQG_TRY(text_hoisted(l, hoist));
+          if (ready && ready[2 + (L - 1 - l)]) MMQG_CUDA(cudaEventRecord(ready[2 + (L - 1 - l)], hoist));   // this layer's gradients are final
         }
       }
     }
@@ -1115,13 +1119,14 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   MMQG_TRY(b.video(ax));
   if (ready && ready[1]) MMQG_CUDA(cudaEventRecord(ready[1], ax));     // video group final
   if (NC > 1) {
-    MMQG_TRY(b.text_pipelined(NC, st, ax));
+    MMQG_TRY(b.text_pipelined(NC, st, ax, ready));
   } else {
     for (int l = d.L - 1; l >= 0; --l) {
       MMQG_TRY(b.text_bptt(l, st));
       MMQG_CUDA(cudaEventRecord(g_aux.ev[3 + l], st));
       MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[3 + l], 0));
       MMQG_TRY(b.text_hoisted(l, ax));
+      if (ready && ready[2 + (d.L - 1 - l)]) MMQG_CUDA(cudaEventRecord(ready[2 + (d.L - 1 - l)], ax));
     }
   }
   mark(8, st);
@@ -1129,7 +1134,7 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[7], 0));       // join: everything is ordered on `st` again
   MMQG_TRY(b.emb_enc(st, NC > 1));
   mark(9, st);
-  if (ready && ready[2]) MMQG_CUDA(cudaEventRecord(ready[2], st));     // text + embedding group final
+  if (ready && ready[2 + d.L]) MMQG_CUDA(cudaEventRecord(ready[2 + d.L], st));     // shared embedding final (both scatter-adds landed)
   return 0;
 }
 

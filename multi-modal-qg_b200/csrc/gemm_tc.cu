@@ -212,9 +212,11 @@ int gemm_bf16(const mmqg_gemm_bf16_args& g, cudaStream_t st) {
   p.Cin = g.Cin; p.ldcin = g.ldcin; p.beta = g.beta; p.alpha = g.alpha; p.bias = g.bias;
   p.split_k = g.split_k > 1 ? g.split_k : 1; p.c_split_stride = g.c_split_stride;
   MMQG_REQUIRE(p.split_k == 1 || !g.c_bf16, "gemm_bf16: split-K partials are fp32");
-  if (p.split_k > p.nk1 + p.nk2) {
-    // fewer k-blocks than requested slices: the surplus partial tiles are defined as zero
-    const int used = p.nk1 + p.nk2;
+  const int nk_all = p.nk1 + p.nk2, per_slice = ceil_div(nk_all, p.split_k);
+  if (ceil_div(nk_all, per_slice) < p.split_k) {
+    // the k-blocks do not fill every requested slice (fewer blocks than slices, or the rounded-up slice
+    // length leaves trailing slices empty): the surplus partial tiles are defined as zero
+    const int used = ceil_div(nk_all, per_slice);
     MMQG_REQUIRE(g.ldc == g.N, "gemm_bf16: clamped split-K needs contiguous partials");
     MMQG_CUDA(cudaMemsetAsync(reinterpret_cast<float*>(g.C) + (size_t)used * g.c_split_stride, 0,
                               sizeof(float) * (size_t)(p.split_k - used) * g.c_split_stride, st));

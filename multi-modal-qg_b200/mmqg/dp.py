@@ -21,21 +21,23 @@ class GradReducer:
             # ready events the library records where each gradient group becomes final, and the
             # stream the all-reduces are issued from (so they are ordered after the event only,
             # not after the rest of the backward on the compute stream)
-            self.events = [torch.cuda.Event() for _ in range(3)]
+            self.events = [torch.cuda.Event() for _ in range(len(self.buckets) - 1)]    # every group after the loss head
             for e in self.events:
                 e.record()                     # torch creates the cudaEvent_t lazily, at first record
             self.side = torch.cuda.Stream()
 
     def on_phase(self, i):
-        """Called right after gradient group i has been enqueued on the compute stream.
-        ProcessGroupNCCL orders the collective after that work on its own stream, so it runs
-        under the kernels of the next backward phase (NVLink5/NVSwitch, one flat ring/NVLS)."""
-        self.works.append(dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        """Called right after backward PHASE i (0 loss head, 1 decoder, 2 video, 3 text layers + embedding) has
+        been enqueued on the compute stream.  ProcessGroupNCCL orders the collective after that work on its
+        own stream, so it runs under the kernels of the next backward phase (NVLink5/NVSwitch, one flat ring/NVLS)."""
+        groups = [i] if i < 3 else range(3, len(self.buckets))
+        for g in groups:
+            self.works.append(dist.all_reduce(self.buckets[g], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def after_backward(self):
-        """After engine.backward_events(): start the all-reduce of groups 1..3, each behind its
-        ready event on the side stream."""
-        for i in (1, 2, 3):
+        """After engine.backward_events(): start the all-reduce of every group after the loss head, each behind
+        its ready event on the side stream (decoder, video, text layers top to bottom, shared embedding)."""
+        for i in range(1, len(self.buckets)):
             self.side.wait_event(self.events[i - 1])
             with torch.cuda.stream(self.side):
                 self.works.append(dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))

@@ -35,14 +35,15 @@ class TrainEngine:
             if tuple(params[name].shape) != tuple(shape):
                 raise _cabi.MmqgError(f"{name}: shape {tuple(params[name].shape)} != {shape}")
         # Parameters and gradients live in ONE flat fp32 buffer each with identical layout, cut into
-        # four buckets, one per gradient readiness group: the data-parallel
+        # 4 + L buckets, one per gradient readiness group (grad_group()): the data-parallel
         # all-reduce is one NCCL call per bucket and the fused Adam is one launch over everything;
         # self.params / self.grads are views with the reference's names and shapes.
         self.offsets, total, bucket_range = {}, 0, []
-        for g in range(4):
+        self.n_groups = 4 + dims.L
+        for g in range(self.n_groups):
             lo = total
             for n in shapes:
-                if grad_group(n) == g:
+                if grad_group(n, dims.L) == g:
                     self.offsets[n] = total
                     total += (int(torch.Size(shapes[n]).numel()) + 63) // 64 * 64
             bucket_range.append((lo, total))
@@ -113,7 +114,8 @@ class TrainEngine:
         """Whole backward with its internal overlap; events[i] (torch.cuda.Event, already created)
         is recorded where gradient group i+1 becomes final (mmqg_train_backward_events)."""
         cb = self._cbatch(batch)
-        arr = (C.c_void_p * 3)(*[e.cuda_event for e in events])
+        assert len(events) == 3 + self.d.L, "one ready event per gradient group after the loss head"
+        arr = (C.c_void_p * len(events))(*[e.cuda_event for e in events])
         _cabi.check(self.lib.mmqg_train_backward_events(
             C.byref(self._cd), C.byref(self._cp), C.byref(cb), self.ws.data_ptr(), self.ws.numel(),
             C.byref(self._cg), arr, self.dropout_p, self.seed, self.mode, _stream_ptr()))
@@ -129,8 +131,8 @@ class TrainEngine:
 
     def step(self, batch, grad_scale=1.0, on_phase=None):
         """forward + full backward.  Gradients land in self.grads (overwritten).  on_phase(i)
-        is called after the gradient group i (0 loss head, 1 decoder, 2 video, 3 text+emb)
-        has been enqueued -- the hook the data-parallel all-reduce uses."""
+        is called after backward phase i (0 loss head, 1 decoder, 2 video, 3 text layers + embedding)
+        has been enqueued -- the hook the phase-wise data-parallel all-reduce uses."""
         loss = self.forward(batch, True, grad_scale)
         if on_phase is None:
             self.backward(batch, 0)          # whole backward, hoisted products overlapped internally
@@ -214,17 +216,20 @@ class TrainEngine:
         return toks
 
 
-def grad_group(name: str) -> int:
-    """Readiness group of a gradient tensor: 0 loss head (final after the forward's fused
-    loss head), 1 attention Linears + decoder LSTM, 2 video LSTM, 3 text LSTM + the shared
-    embedding (final last: decoder- and encoder-side scatter-adds both land in it)."""
+def grad_group(name: str, L: int = 3) -> int:
+    """Readiness group of a gradient tensor, in the order the groups become final during the backward:
+    0 loss head (final after the forward's fused loss head), 1 attention Linears + decoder LSTM, 2 video LSTM,
+    3 + k text LSTM layer L-1-k (the top layer's BPTT finishes first), 3 + L the shared embedding (final last:
+    decoder- and encoder-side scatter-adds both land in it)."""
     if name.startswith("dec.out_layer."):
         return 0
     if name.startswith("dec."):
         return 1
     if name.startswith("video."):
         return 2
-    return 3
+    if name.startswith("text.lstm."):
+        return 3 + (L - 1 - int(name.rsplit("_l", 1)[1]))
+    return 3 + L
 
 
 def launch_count():

@@ -156,6 +156,55 @@ class LSTMStack(Function):
         return (dx, torch.stack(dh0), torch.stack(dc0), None, *grads)
 
 
+class LSTMLayerSeq(Function):
+    """ONE torch.nn.LSTM layer over a whole (T,B,I) sequence on the tensor-core path
+    (mmqg_lstm_seq_fwd / _bwd: hoisted input projection + persistent recurrent kernel, persistent BPTT
+    kernel + hoisted weight gradients; bf16 operands, fp32 accumulation).  The call TextEncoder.forward
+    makes for a whole context (encoder.py:95-100), VideoConvLstmEncoder for the frame features
+    (encoder.py:69) and the non-attention Decoder for a whole question (decoder.py:25-34)."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, w_ih, w_hh, b_ih, b_hh):
+        T, B, I = x.shape
+        H = h0.shape[1]
+        y, hn, cn, ws = ops.lstm_seq_fwd(_c(x), _c(w_ih), _c(w_hh), _c(b_ih), _c(b_hh), _c(h0), _c(c0))
+        ctx.save_for_backward(w_hh, ws)
+        ctx.dims = (T, B, I, H)
+        return y, hn, cn
+
+    @staticmethod
+    def backward(ctx, dy, dhn, dcn):
+        w_hh, ws = ctx.saved_tensors
+        T, B, I, H = ctx.dims
+        g = ops.lstm_seq_bwd(None if dy is None else _c(dy), None if dhn is None else _c(dhn),
+                             None if dcn is None else _c(dcn), _c(w_hh), ws, T, B, I, H, want_dx=ctx.needs_input_grad[0])
+        return g["dx"], g["dh0"], g["dc0"], g["dw_ih"], g["dw_hh"], g["db_ih"], g["db_hh"]
+
+
+_mask_calls = 0
+
+
+def _dropout_masks(L, T, B, H, p, device):
+    """(L-1,T,B,H) inter-layer dropout masks (0 or 1/(1-p)) drawn by the library's counter-based generator
+    (mmqg_dropout_mask), a fresh stream per call; torch.manual_seed() reseeds it through torch.initial_seed()."""
+    global _mask_calls
+    _mask_calls += 1
+    seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * _mask_calls) & 0xFFFFFFFFFFFFFFFF
+    m = torch.empty(L - 1, T, B, H, device=device, dtype=torch.float32)
+    for l in range(L - 1):
+        ops.dropout_mask(m[l], seed, 30 + l, p)
+    return m
+
+
+def drop_in_mode():
+    """Arithmetic of the step-wise drop-in modules: "fp32" (default: fp32 storage and accumulation, the mode that
+    carries the 1e-3 parity bar) or "bf16" (MMQG_DROPIN_MODE=bf16: whole-sequence LSTM calls run on the
+    tensor-core sequence kernels).  An explicit choice, not a fallback: shapes the sequence kernels do not
+    support raise in bf16 mode only when the call cannot be served by the per-step blocks either."""
+    import os
+    return os.environ.get("MMQG_DROPIN_MODE", "fp32")
+
+
 def lstm_stack(x, hidden, lstm_module, training):
     """Run `lstm_module`'s parameters (a torch.nn.LSTM used purely as the parameter container
     that keeps the reference's state_dict keys) through the CUDA kernels."""
@@ -167,12 +216,37 @@ def lstm_stack(x, hidden, lstm_module, training):
                     getattr(lstm_module, f"bias_ih_l{l}"), getattr(lstm_module, f"bias_hh_l{l}")]
     masks = None
     p = float(lstm_module.dropout)
+    T, B, _ = x.shape
+    H = lstm_module.hidden_size
     if training and p > 0 and L > 1:
-        T, B, _ = x.shape
-        keep = torch.rand(L - 1, T, B, lstm_module.hidden_size, device=x.device) >= p
-        masks = keep.to(torch.float32) / (1.0 - p)
+        masks = _dropout_masks(L, T, B, H, p, x.device)
+    if drop_in_mode() == "bf16" and T > 1 and ops.lstm_seq_ok(B, H):
+        inp, hn, cn = x, [], []
+        for l in range(L):
+            y, h, c = LSTMLayerSeq.apply(inp, h0[l], c0[l], *weights[4 * l:4 * l + 4])
+            hn.append(h)
+            cn.append(c)
+            inp = y * masks[l] if (masks is not None and l < L - 1) else y
+        return inp, (torch.stack(hn), torch.stack(cn))
     y, hn, cn = LSTMStack.apply(x, _c(h0), _c(c0), masks, *weights)
     return y, (hn, cn)
+
+
+_cat_cache = {}
+
+
+def cat_cached(key, tensors, dim=0):
+    """torch.cat of parameters, redone only when one of them changed (optimizer step, load_state_dict) or when
+    autograd needs the graph through it; saves the three attention Linears' re-concatenation on every decoder
+    step in inference loops (decoder.py:78,84,92 as one product)."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        return torch.cat(tensors, dim)
+    ver = tuple((t.data_ptr(), t._version) for t in tensors)
+    hit = _cat_cache.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, torch.cat([t.detach() for t in tensors], dim))
+        _cat_cache[key] = hit
+    return hit[1]
 
 
 def require_cuda(*tensors):

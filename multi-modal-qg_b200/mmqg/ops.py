@@ -208,3 +208,55 @@ def colsum(X, out=None, beta=0.0):
         out = torch.empty(N, device=X.device, dtype=torch.float32)
     check(lib().mmqg_colsum(X.data_ptr(), _ld(X), out.data_ptr(), M, N, float(beta), _st()))
     return out
+
+
+def dropout_mask(out, seed, sid, p):
+    """out <- the multiplicative mask (0 or 1/(1-p)) of the library's counter-based generator (mmqg_dropout_mask)."""
+    _chk(out)
+    check(lib().mmqg_dropout_mask(out.data_ptr(), out.numel(), int(seed), int(sid), float(p), _st()))
+    return out
+
+
+_sm_count = {}
+
+
+def lstm_seq_ok(B, H):
+    """Shapes the persistent sequence kernels take (see mmqg_lstm_seq_fwd in mmqg.h)."""
+    dev = torch.cuda.current_device()
+    if dev not in _sm_count:
+        _sm_count[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return H % 64 == 0 and 64 <= H <= 512 and (H // 16) * ((B + 127) // 128) <= _sm_count[dev]
+
+
+def lstm_seq_fwd(x, w_ih, w_hh, b_ih, b_hh, h0=None, c0=None):
+    """One LSTM layer over x (T,B,I) on the tensor-core sequence kernels.  Returns y (T,B,H), hn, cn (B,H) and the
+    workspace tensor that lstm_seq_bwd needs (saved activations)."""
+    _chk(x, w_ih, w_hh, b_ih, b_hh, h0, c0)
+    T, B, I = x.shape
+    H = w_hh.shape[1]
+    n = lib().mmqg_lstm_seq_workspace_bytes(T, B, I, H)
+    ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+    y = torch.empty(T, B, H, device=x.device, dtype=torch.float32)
+    hn = torch.empty(B, H, device=x.device, dtype=torch.float32)
+    cn = torch.empty_like(hn)
+    check(lib().mmqg_lstm_seq_fwd(x.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
+                                  _cabi.ptr(h0), _cabi.ptr(c0), T, B, I, H, ws.data_ptr(), n, y.data_ptr(), hn.data_ptr(),
+                                  cn.data_ptr(), _st()))
+    return y, hn, cn, ws
+
+
+def lstm_seq_bwd(dy, dhn, dcn, w_hh, ws, T, B, I, H, want_dx=True):
+    """Backward of lstm_seq_fwd (same workspace).  Returns a dict of fp32 gradients."""
+    _chk(dy, dhn, dcn, w_hh)
+    dev = w_hh.device
+    g = {"dx": torch.empty(T, B, I, device=dev, dtype=torch.float32) if want_dx else None,
+         "dw_ih": torch.empty(4 * H, I, device=dev, dtype=torch.float32),
+         "dw_hh": torch.empty(4 * H, H, device=dev, dtype=torch.float32),
+         "db_ih": torch.zeros(4 * H, device=dev, dtype=torch.float32),
+         "db_hh": torch.zeros(4 * H, device=dev, dtype=torch.float32),
+         "dh0": torch.empty(B, H, device=dev, dtype=torch.float32),
+         "dc0": torch.empty(B, H, device=dev, dtype=torch.float32)}
+    check(lib().mmqg_lstm_seq_bwd(_cabi.ptr(dy), _cabi.ptr(dhn), _cabi.ptr(dcn), w_hh.data_ptr(), T, B, I, H, ws.data_ptr(),
+                                  ws.numel(), _cabi.ptr(g["dx"]), g["dw_ih"].data_ptr(), g["dw_hh"].data_ptr(),
+                                  g["db_ih"].data_ptr(), g["db_hh"].data_ptr(), g["dh0"].data_ptr(), g["dc0"].data_ptr(), _st()))
+    return g

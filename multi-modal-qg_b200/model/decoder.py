@@ -88,8 +88,8 @@ class AttnDecoder(Module):
         embedded = MF.Embedding.apply(self.emb_layer.weight, word.reshape(-1))             # (B,E)   decoder.py:75
         query = torch.cat((embedded, hidden[0][-1]), 1)                                    # (B,E+H) decoder.py:78
         # the three score Linears as one product over the concatenated weights [text|audio|video]
-        w_cat = torch.cat((self.text_attn.weight, self.audio_attn.weight, self.vid_attn.weight), 0)
-        b_cat = torch.cat((self.text_attn.bias, self.audio_attn.bias, self.vid_attn.bias), 0)
+        w_cat = MF.cat_cached((id(self), "w"), (self.text_attn.weight, self.audio_attn.weight, self.vid_attn.weight))
+        b_cat = MF.cat_cached((id(self), "b"), (self.text_attn.bias, self.audio_attn.bias, self.vid_attn.bias))
         scores = MF.Linear.apply(query, w_cat, b_cat)
         # no length mask: decoder.py:79,85,93 are no-ops in the reference;
         # enc_seq_len / enc_frames only bound the context sums (rows beyond them are zero padding)

@@ -249,9 +249,56 @@ def run_adam_case(name="adam_a", seed=31, n_iter=3, dtype=torch.float64):
     print(name, "losses", losses, os.path.getsize(path), "bytes")
 
 
+def run_decoder_case(name, T, V, E, A, H, L, seed, dtype=torch.float64):
+    """The reference's non-attention Decoder (model/decoder.py:7-47) on one whole question: forward(text (1,T),
+    av_enc_out (1,A), hidden) -> logits (T,1,V); loss = sum_t CE(logits_t, target_t) as in non_attn_train.py's
+    intent; gradients of every parameter, of av_enc_out and of the initial state."""
+    from model.decoder import Decoder                                     # reference
+    g = torch.Generator().manual_seed(seed)
+    emb = torch.nn.Embedding(V, E)
+    dec = Decoder(L, 0.0, H, V, E, A, emb)
+    for m in (emb, dec):
+        m.to(dtype)
+    with torch.no_grad():
+        emb.weight.copy_(torch.randn(V, E, generator=g).to(dtype))
+        for n_, p_ in dec.named_parameters():
+            if n_.startswith("word_embeddings"):
+                continue
+            if "bias" in n_:
+                p_.mul_(0.3)
+    text = torch.randint(3, V, (1, T), generator=g)
+    target = torch.randint(3, V, (T,), generator=g)
+    av = torch.randn(1, A, generator=g).to(dtype).requires_grad_(True)
+    h0 = (0.5 * torch.randn(L, 1, H, generator=g)).to(dtype).requires_grad_(True)
+    c0 = (0.5 * torch.randn(L, 1, H, generator=g)).to(dtype).requires_grad_(True)
+    logits, (hn, cn) = dec(text, av, (h0, c0))
+    loss = F.cross_entropy(logits.view(T, V), target, reduction="sum") + 0.1 * hn.sum() + 0.05 * cn.sum()
+    loss.backward()
+    fx = {"dims": dict(T=T, V=V, E=E, A=A, H=H, L=L), "seed": seed,
+          "state_dict": {k: v.detach().float().clone() for k, v in dec.state_dict().items()},
+          "text": text, "target": target, "av": av.detach().float(), "h0": h0.detach().float(), "c0": c0.detach().float(),
+          "loss": float(loss), "logits": logits.detach().float(), "hn": hn.detach().float(), "cn": cn.detach().float(),
+          "grads": {n_: p_.grad.detach().float().clone() for n_, p_ in dec.named_parameters()},
+          "d_av": av.grad.detach().float(), "d_h0": h0.grad.detach().float(), "d_c0": c0.grad.detach().float()}
+    path = os.path.join(HERE, f"{name}.pt")
+    torch.save(fx, path)
+    print(name, "loss", float(loss), os.path.getsize(path), "bytes")
+
+
+DECODER_CASES = {
+    "decoder_a": dict(T=6, V=37, E=12, A=20, H=32, L=2, seed=41),      # fp32 building blocks (H not a multiple of 64)
+    "decoder_b": dict(T=9, V=53, E=12, A=20, H=64, L=3, seed=42),      # shape the tensor-core sequence kernels take
+}
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     which = sys.argv[1:]
+    for name, c in DECODER_CASES.items():
+        if not which or name in which:
+            run_decoder_case(name, **c)
+    if which and all(w in DECODER_CASES for w in which):
+        sys.exit(0)
     if not which or "adam_a" in which:
         run_adam_case()
     for name, c in CASES.items():

@@ -18,11 +18,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class _FakeEngine:
     """grad_buckets / grads laid out exactly like mmqg.engine.TrainEngine, on the CPU."""
 
-    def __init__(self, shapes):
+    def __init__(self, shapes, L):
         from mmqg.engine import grad_group
         self.grads, self.grad_buckets = {}, []
-        for g in range(4):
-            names = [n for n in shapes if grad_group(n) == g]
+        for g in range(4 + L):
+            names = [n for n in shapes if grad_group(n, L) == g]
             offs, total = {}, 0
             for n in names:
                 offs[n] = total
@@ -51,12 +51,12 @@ def _worker(rank, world, port, ret):
     local = shard_batch(gbatch, rank, world)
     assert local["context"].shape[0] == dg.B // world
     loss_l, grads_l = O.loss_and_grads(params, local, dg.L, dg.TM, dg.AM, torch.float64)
-    eng = _FakeEngine(param_shapes(dg))
+    eng = _FakeEngine(param_shapes(dg), dg.L)
     scale = (dg.B // world) / dg.B
     for k, g in grads_l.items():
         eng.grads[k].copy_((scale * g).float())
     red = GradReducer(eng, world)
-    for phase in range(4):                       # readiness order: loss head, decoder, video, text+emb
+    for phase in range(4):                       # backward phases: loss head, decoder, video, text layers + embedding
         red.on_phase(phase)
     red.finish()
     loss_g, grads_g = O.loss_and_grads(params, gbatch, dg.L, dg.TM, dg.AM, torch.float64)
@@ -83,7 +83,10 @@ def test_grad_groups_cover_every_parameter_once():
     from mmqg.dims import Dims, param_shapes
     from mmqg.engine import grad_group
     d = Dims(B=1, T_t=2, T_v=1, T_q=2, V=11, E=4, H=8, L=3, H_a=4, H_v=8, F_v=4, TM=3, AM=2)
-    groups = {n: grad_group(n) for n in param_shapes(d)}
-    assert set(groups.values()) == {0, 1, 2, 3}
+    groups = {n: grad_group(n, d.L) for n in param_shapes(d)}
+    assert set(groups.values()) == set(range(4 + d.L))
     assert groups["dec.out_layer.weight"] == 0 and groups["dec.lstm.weight_hh_l2"] == 1
-    assert groups["video.lstm.bias_ih_l0"] == 2 and groups["emb.weight"] == 3 and groups["text.lstm.weight_ih_l0"] == 3
+    assert groups["video.lstm.bias_ih_l0"] == 2
+    # text layers in BPTT completion order (top layer first), the shared embedding last
+    assert groups["text.lstm.weight_ih_l2"] == 3 and groups["text.lstm.bias_hh_l1"] == 4 and groups["text.lstm.weight_ih_l0"] == 5
+    assert groups["emb.weight"] == 6
