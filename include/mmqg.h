@@ -133,7 +133,11 @@ int mmqg_train_forward(const mmqg_dims* d, const mmqg_tensors* params, const mmq
                        int want_grads, mmqg_tensors* grads, float grad_scale,
                        float dropout_p, unsigned long long seed, int mode, void* stream);
 
-/* Backward of the same step (reference train.py:177).  `phase` selects which gradient
+/* NOTE on the loss-head gradients (d out_w, d out_b): in MMQG_MODE_BF16 with the persistent decoder kernel they are
+ * produced by the BACKWARD call of the step (phase 0 / 1 or mmqg_train_backward_events), not by mmqg_train_forward:
+ * callers must not read or reduce them between the two calls.  The forward call still needs `grads` (unchanged ABI).
+ *
+ * Backward of the same step (reference train.py:177).  `phase` selects which gradient
  * groups to produce, in the order they become final, so the caller can start the
  * all-reduce of one group while the next is computed:
  *   1 decoder (attention Linears, decoder LSTM; also d/d memories, d/d encoder state)
@@ -156,13 +160,15 @@ int mmqg_sample_decode(const mmqg_dims* d, const mmqg_tensors* params, const mmq
                        unsigned long long seed, int mode, void* stream);
 
 /* The whole backward (as phase 0, with its internal overlap) for data-parallel callers.
- * ready_events: array of 3 + L cudaEvent_t created by the caller (entries may be NULL); each is recorded at
- * the point -- and on whichever internal stream -- where one gradient group becomes final, so the caller can
- * make its communication stream wait on the event and start that group's all-reduce under the rest of the
- * backward:
- *   [0] decoder (attention Linears + decoder LSTM)      [1] video LSTM
- *   [2 + k] text LSTM layer L-1-k, k = 0 .. L-1 (the top layer's BPTT and weight gradients finish first)
- *   [2 + L] the shared embedding (decoder- and encoder-side scatter-adds both landed: last of all).
+ * ready_events: array of 4 + L cudaEvent_t created by the caller (entries may be NULL), one per gradient group;
+ * each is recorded at the point -- and on whichever internal stream -- where that group becomes final, so the
+ * caller can make its communication stream wait on the event and start the group's all-reduce under the rest
+ * of the backward:
+ *   [0] loss head (out_layer): final since the forward call, or -- when the persistent decoder kernel is in use and
+ *       the backward half of the loss head is deferred to this call -- once that half has run under the decoder BPTT
+ *   [1] decoder (attention Linears + decoder LSTM)      [2] video LSTM
+ *   [3 + k] text LSTM layer L-1-k, k = 0 .. L-1 (the top layer's BPTT and weight gradients finish first)
+ *   [3 + L] the shared embedding (decoder- and encoder-side scatter-adds both landed: last of all).
  * All work is joined back onto `stream` before the call returns.  Data-parallel callers give every rank its
  * own dropout `seed`, otherwise local sample b draws the same masks on every rank. */
 int mmqg_train_backward_events(const mmqg_dims* d, const mmqg_tensors* params, const mmqg_batch* batch,

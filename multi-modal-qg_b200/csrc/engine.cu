@@ -322,8 +322,8 @@ int mmqg_train_backward_events(const mmqg_dims* dp, const mmqg_tensors* params, 
                                unsigned long long seed, int mode, void* stream) {
   MMQG_REQUIRE(ready_events, "ready_events: null pointer (use mmqg_train_backward phase 0)");
   MMQG_REQUIRE(dp && dp->L >= 1 && dp->L <= MMQG_MAX_LAYERS, "dims: L out of range");
-  const int n_ev = 3 + dp->L;         // decoder, video, text layers L-1 .. 0, shared embedding
-  cudaEvent_t ev[3 + MMQG_MAX_LAYERS];
+  const int n_ev = 4 + dp->L;         // loss head, decoder, video, text layers L-1 .. 0, shared embedding
+  cudaEvent_t ev[4 + MMQG_MAX_LAYERS];
   for (int i = 0; i < n_ev; ++i) ev[i] = reinterpret_cast<cudaEvent_t>(ready_events[i]);
   if (mode == MMQG_MODE_BF16) {
     MMQG_TRY(check_dims(dp));
@@ -334,12 +334,13 @@ int mmqg_train_backward_events(const mmqg_dims* dp, const mmqg_tensors* params, 
     MMQG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p=%g not in [0,1)", dropout_p);
     return train_backward_bf16(*dp, *params, *batch, workspace, workspace_bytes, *grads, 0, dropout_p, seed, as_stream(stream), ev);
   }
+  if (ev[0]) MMQG_CUDA(cudaEventRecord(ev[0], as_stream(stream)));      // fp32 mode: the loss-head gradients are final since the forward call
   for (int ph = 1; ph <= 3; ++ph) {     // fp32 parity mode: phases in order on the caller's stream
     MMQG_TRY(mmqg_train_backward(dp, params, batch, workspace, workspace_bytes, grads, ph, dropout_p, seed, mode, stream));
     if (ph < 3) {
-      if (ev[ph - 1]) MMQG_CUDA(cudaEventRecord(ev[ph - 1], as_stream(stream)));
+      if (ev[ph]) MMQG_CUDA(cudaEventRecord(ev[ph], as_stream(stream)));
     } else {
-      for (int i = 2; i < n_ev; ++i)
+      for (int i = 3; i < n_ev; ++i)
         if (ev[i]) MMQG_CUDA(cudaEventRecord(ev[i], as_stream(stream)));
     }
   }

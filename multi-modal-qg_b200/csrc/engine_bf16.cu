@@ -55,6 +55,9 @@ struct Ws16 {
   int *shift_t, *shift_v;             // variable lengths: first real time step of every sample (text / video)
   float* row_w;                       // ... and the 0/1 weight of every (target step, sample) loss row
   float *dh_last, *dh_last_l[MMQG_MAX_LAYERS], *dx_emb;
+  // persistent decoder-step kernel (dec_persist.cu): decoder weights in 16-unit gate-slice row order, arrival counters
+  b16 *wdp_hh[MMQG_MAX_LAYERS], *wdp_in[MMQG_MAX_LAYERS];
+  uint32_t* flags_dec;
   // fused loss head (vocab_nll.cu): per-tile softmax partials, per-row lse / gradient scale / target logit, split-K scratch of dH
   float *stat_a, *stat_b, *lse, *rscale, *tgt_logit, *dh_part;
   int Sp, Ep, Vp, Rc, Rs;     // Rc: rows of one bf16 d-logits chunk; Rs: rows of the fp32 logits scratch of the sampling decode
@@ -149,6 +152,8 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.dx_emb = c.take<float>(Rt * d.E);
   for (int l = 0; l + 1 < d.L; ++l) { w.xdrop_text[l] = c.take<b16>(Rt * H); w.hdrop_dec[l] = c.take<b16>(R * H); }
   w.shift_t = c.take<int>(B); w.shift_v = c.take<int>(B); w.row_w = c.take<float>(R);
+  for (int l = 0; l < d.L; ++l) { w.wdp_hh[l] = c.take<b16>(G * H); w.wdp_in[l] = c.take<b16>(G * (l == 0 ? C : H)); }
+  w.flags_dec = c.take<uint32_t>((size_t)((B + 63) / 64) * (3 * (T_q + 1) + 2 * T_q) + 64);
   w.m_txt16 = c.take<b16>(B * d.TM * H);
   w.m_vid16 = c.take<b16>(B * d.AM * Hv);
   w.bytes = align_up(c.off, 256);
@@ -294,6 +299,30 @@ static int rec_bwd(const float* acts, const float* cs, void* dg, const void* wp,
   return lstm_seq_bwd_persist(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, flags, T, B, H, 0, nullptr, st, DropSpec(), true, len);
 }
 
+// The decoder's teacher-forced steps run inside the persistent decoder-step kernel (dec_persist.cu) when the
+// shape allows it; MMQG_DEC_PERSIST=0 keeps the launch-per-phase loop (for A/B comparison).
+static DecPersistShape dec_shape(const mmqg_dims& d, const Ws16& w) {
+  return DecPersistShape{d.B, d.H, d.H + d.H_a + d.H_v, w.Sp, d.TM, d.AM, d.T_t, d.T_v, d.H_a, d.H_v, d.L};
+}
+static bool dec_persist_enabled(const mmqg_dims& d, const Ws16& w) {
+  const char* e = getenv("MMQG_DEC_PERSIST");
+  if (e && e[0] == '0') return false;
+  return dec_persist_ok(dec_shape(d, w));
+}
+
+// With the persistent decoder kernel holding 128 SMs, the loss head cannot hide under the decoder's forward steps
+// any more.  Its forward half (the loss) then runs right behind the decoder, and its backward half (d logits -> dH,
+// dW_out, db_out) is DEFERRED to the backward call, where it runs group by group, last steps first, on its own stream
+// under the launch-per-phase decoder BPTT loop, each BPTT step waiting only for the group that holds its rows.
+// Forward and backward of one step must agree on this, so it depends on the shape and the environment only.
+static bool lh_deferred(const mmqg_dims& d, const Ws16& w) {
+  const char* e = getenv("MMQG_LH_DEFER");
+  if (e && e[0] == '0') return false;
+  return dec_persist_enabled(d, w);
+}
+static constexpr int kMaxLhGroups = 16;
+static cudaEvent_t ev_lh(int g);      // defined behind AuxStream
+
 // fp32 parameters -> packed bf16 caches + summed biases + concatenated attention bias.
 // Two halves so that only what the text encoder needs sits in front of it on the caller's
 // stream; the rest is packed on an auxiliary stream beside the text encoder.
@@ -332,6 +361,11 @@ static int pack_weights_rest(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w,
     MMQG_CUDA(cudaMemcpyAsync(w.attn_b_cat + off[i], P.attn_b[i], sizeof(float) * len[i], cudaMemcpyDeviceToDevice, st));
   }
   MMQG_TRY(cvt_f32_bf16_2d(P.out_w, H, w.wo, H, d.V, H, H, st));
+  if (dec_persist_enabled(d, w))
+    for (int l = 0; l < d.L; ++l) {
+      MMQG_TRY(pack_whh(P.dec_w_hh[l], w.wdp_hh[l], nullptr, H, st));
+      MMQG_TRY(pack_rows_gate16(l == 0 ? P.dec_w_ih[0] + E : P.dec_w_ih[l], l == 0 ? X0 : H, l == 0 ? C : H, l == 0 ? C : H, w.wdp_in[l], H, st));
+    }
   if (persist_video(d)) MMQG_TRY(pack_rec(P.vid_w_hh, w.wvp_f, w.wvp_b, d.B, Hv, st));
   if (persist_text(d))      // BPTT layouts of the text layers: not needed before the backward pass
     for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_rec(P.text_w_hh[l], nullptr, w.wtp_b[l], d.B, H, st));
@@ -425,6 +459,7 @@ static cudaEvent_t ev_fwd(int l, int c) { return g_aux.ev[16 + l * kMaxChunks + 
 static cudaEvent_t ev_bwd(int l, int c) { return g_aux.ev[48 + l * kMaxChunks + c]; }
 static cudaEvent_t ev_gf(int l, int c) { return g_aux.ev[96 + l * kMaxChunks + c]; }
 static cudaEvent_t ev_gb(int l, int c) { return g_aux.ev[128 + l * kMaxChunks + c]; }
+static cudaEvent_t ev_lh(int g) { return g_aux.ev[80 + g]; }       // slots [80, 96): loss-head groups of the deferred backward
 static bool split_products() {
   static const bool on = []() { const char* e = getenv("MMQG_GSTREAMS"); return !(e && e[0] == '0'); }();
   return on && g_aux.prio;
@@ -631,13 +666,14 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   // and its backward (vocab_nll.cu); logits are never stored (decoder.py:106, train.py:174).
   const b16* htop = w.hs_dec[d.L - 1] + (size_t)B * H;
   const float dscale = want_grads ? grad_scale / (float)B : 0.f;
+  const bool defer_bwd = lh_deferred(d, w);
   auto loss_head = [&](int r0, int n, bool first, cudaStream_t s) -> int {
     PdlScope no_pdl(false);
     // forward: logits tiles live in tensor memory only; per-row (max, sum exp, target logit) -> lse, NLL
     MMQG_TRY(vocab_nll_fwd(htop + (size_t)r0 * H, H, w.wo, H, P.out_b, w.tgt_tm + r0, g_len.on ? w.row_w + r0 : nullptr, n, d.V, H, dscale,
                            w.nll + r0, w.lse + r0, w.rscale + r0, w.stat_a, w.stat_b, w.tgt_logit + r0, s));
     // backward: tiles recomputed, bf16 d-logits in L2-sized row chunks -> dH, dW_out (+=), db_out (+=)
-    if (want_grads)
+    if (want_grads && !defer_bwd)
       MMQG_TRY(vocab_nll_bwd(htop + (size_t)r0 * H, H, w.wo, H, P.out_b, w.tgt_tm + r0, w.lse + r0, w.rscale + r0, n, d.V, H, w.dlogits16,
                              w.Vp, w.Rc, w.dh_part, w.dhtop + (size_t)r0 * H, H, grads->out_w, grads->out_b, !first, s));
     return 0;
@@ -648,7 +684,7 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   static const int lh_group_env = []() { const char* e = getenv("MMQG_LH_STEPS"); return e ? atoi(e) : 0; }();
   const int lh_steps = lh_group_env > 0 ? lh_group_env : (w.Rc / B > 1 ? w.Rc / B : 1);      // whole steps per loss-head group
   static const int lh_tail = []() { const char* e = getenv("MMQG_LH_TAIL"); return e ? atoi(e) : 1; }();
-  const bool lh_overlap = lh_env && lh_steps >= 1 && d.T_q > 1;
+  const bool lh_overlap = lh_env && lh_steps >= 1 && d.T_q > 1 && !defer_bwd;     // deferred: one decoder launch, then the loss
   int lh_done = 0;      // steps whose loss head has been issued
   PdlScope pdl_scope(pdl_enabled());      // the dependent launches below overlap prologue and tail
   L2WindowScope l2_scope(w.m_txt16, attn_l2_window(d, w));     // attention memories stay in L2 across the T_q steps
@@ -656,7 +692,40 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   static const int step_mode_env = []() { const char* e = getenv("MMQG_STEP_FUSE"); return e ? atoi(e) : 2; }();
   const int step_mode = step_mode_env;
   const bool step_fused = step_mode == 1 && lstm_step_tc_ok(H, G, H, H, H, G);
+  const bool dec_persist = dec_persist_enabled(d, w);
+  DecPersistArgs dpa{};
+  int seg_start = 0;
+  if (dec_persist) {
+    dpa.shape = dec_shape(d, w);
+    dpa.Tq = d.T_q; dpa.attn_all = w.attn_all; dpa.ctx16 = w.ctx16;
+    for (int l = 0; l < d.L; ++l) {
+      dpa.acts[l] = w.acts_dec[l]; dpa.cs[l] = w.cs_dec[l]; dpa.hs[l] = w.hs_dec[l];
+      dpa.hdrop[l] = (g_drop_p > 0.f && l + 1 < d.L) ? w.hdrop_dec[l] : nullptr;
+      dpa.bias[l] = l == 0 ? nullptr : w.bsum_dec[l];
+      dpa.w_hh[l] = w.wdp_hh[l]; dpa.w_in[l] = w.wdp_in[l];
+    }
+    dpa.wa_h = w.wa_h; dpa.m_txt16 = w.m_txt16; dpa.m_vid16 = w.m_vid16; dpa.m_aud = w.m_aud; dpa.flags = w.flags_dec;
+    dpa.drop_p = g_drop_p; dpa.seed = g_drop_seed; dpa.ctr = g_drop_ctr; dpa.sid0 = kSidDec;
+    MMQG_CUDA(cudaMemsetAsync(w.flags_dec, 0, sizeof(uint32_t) * dec_persist_flag_words(dpa.shape, d.T_q), st));
+  }
   for (int t = 0; t < d.T_q; ++t) {
+    if (dec_persist) {
+      // the steps of one loss-head group (or all of them) run inside ONE persistent launch
+      const bool group_end = lh_overlap && (t + 1 - lh_done == lh_steps || t == d.T_q - 1 - lh_tail);
+      if (group_end || t == d.T_q - 1) {
+        PdlScope no_pdl(false);
+        MMQG_TRY(dec_seq_fwd_persist(dpa, seg_start, t + 1 - seg_start, st));
+        seg_start = t + 1;
+        if (lh_overlap) {
+          MMQG_CUDA(cudaEventRecord(g_aux.ev[10], st));
+          MMQG_CUDA(cudaStreamWaitEvent(lh, g_aux.ev[10], 0));
+          MMQG_TRY(loss_head(lh_done * B, (t + 1 - lh_done) * B, lh_done == 0, lh));
+          lh_done = t + 1;
+          if (t == d.T_q - 1) MMQG_CUDA(cudaEventRecord(g_aux.ev[11], lh));
+        }
+      }
+      continue;
+    }
     StepGemmScope step_scope;
     const b16* htop_prev = w.hs_dec[d.L - 1] + (size_t)t * B * H;
     float* sc = w.attn_all + (size_t)t * B * Sp;
@@ -816,17 +885,47 @@ struct Bwd16 {
     R = d.T_q * B; Sp = w.Sp; L = d.L; ps = (long long)B * H;
   }
 
+  // Deferred backward of the loss head (see lh_deferred()): rows of the steps [t_lo, t_hi) in chunks of Rc rows.
+  int loss_head_bwd(int t_lo, int t_hi, bool first, cudaStream_t s) {
+    PdlScope no_pdl(false);
+    const b16* htop = w.hs_dec[L - 1] + (size_t)B * H;
+    const size_t r0 = (size_t)t_lo * B;
+    return vocab_nll_bwd(htop + r0 * H, H, w.wo, H, P.out_b, w.tgt_tm + r0, w.lse + r0, w.rscale + r0, (t_hi - t_lo) * B, d.V, H,
+                         w.dlogits16, w.Vp, w.Rc, w.dh_part, w.dhtop + r0 * H, H, Gd.out_w, Gd.out_b, !first, s);
+  }
+  // Groups of decoder steps in the order the BPTT needs them (last steps first): a short first group so that the
+  // BPTT can start early, then groups of about Rc rows.  lo[k] = first step of group k (its last is lo[k-1] - 1).
+  int lh_groups(int* lo) const {
+    int n = 0, hi = d.T_q;
+    int size = 2;
+    const int cap = w.Rc / B > 1 ? w.Rc / B : 1;
+    while (hi > 0 && n < kMaxLhGroups - 1) {
+      int take = size < cap ? size : cap;
+      if (take > hi) take = hi;
+      hi -= take;
+      lo[n++] = hi;
+      size *= 2;
+    }
+    if (hi > 0) lo[n - 1] = 0;        // (cannot happen with 15 doubling groups; keeps the cover complete)
+    return n;
+  }
+
   // decoder BPTT, reverse of decoder.py:74-107 for t = T_q-1 .. 0
-  int dec_loop(cudaStream_t st) {
+  int dec_loop(cudaStream_t st, const int* lh_lo = nullptr, int lh_n = 0) {
     AttnShape as = attn_shape16(d, w);
     as.ldds16 = Sp;
     MMQG_CUDA(cudaMemsetAsync(w.ds_all, 0, sizeof(float) * (size_t)R * Sp, st));
     MMQG_CUDA(cudaMemsetAsync(w.ds16, 0, sizeof(b16) * (size_t)R * Sp, st));
     PdlScope pdl_scope(pdl_enabled());
     L2WindowScope l2_scope(w.m_txt16, attn_l2_window(d, w));
+    int lh_next = 0;          // next loss-head group whose d h_top this loop has not waited for yet
     for (int t = d.T_q - 1; t >= 0; --t) {
       StepGemmScope step_scope;
       const bool last = t == d.T_q - 1;
+      if (lh_next < lh_n && (lh_next == 0 || t < lh_lo[lh_next - 1])) {        // first step inside group lh_next
+        MMQG_CUDA(cudaStreamWaitEvent(st, ev_lh(lh_next), 0));
+        ++lh_next;
+      }
       // t > 0: ONE product per layer, dG_l [W_hh | W_in] -> (d h_rec for step t-1 | d input of this step);
       // t == 0 writes the recurrent part where the text encoder's BPTT picks it up (dh_rec[l]).
       const bool fused = t > 0;
@@ -1042,7 +1141,7 @@ struct Bwd16 {
         if (c == 0) {
           MMQG_CUDA(cudaStreamWaitEvent(hoist, ev_bwd(l, 0), 0));
           MMQG_TRY(text_hoisted(l, hoist));
-          if (ready && ready[2 + (L - 1 - l)]) MMQG_CUDA(cudaEventRecord(ready[2 + (L - 1 - l)], hoist));   // this layer's gradients are final
+          if (ready && ready[3 + (L - 1 - l)]) MMQG_CUDA(cudaEventRecord(ready[3 + (L - 1 - l)], hoist));   // this layer's gradients are final
         }
       }
     }
@@ -1083,7 +1182,9 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   g_drop_ctr = w.seed_ctr;      // unchanged since the forward of this step: the same masks
   MMQG_TRY(set_len_state(d, bt, w));      // shift arrays were filled by the forward of this step
   Bwd16 b(d, P, bt, w, Gd);
+  const bool lh_def = lh_deferred(d, w);
   if (phase == 1) {
+    if (lh_def) MMQG_TRY(b.loss_head_bwd(0, d.T_q, true, st));      // phase-wise callers: serially, in front of the BPTT
     MMQG_TRY(b.dec_loop(st));
     return b.dec_hoisted(st);
   }
@@ -1110,14 +1211,32 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   MMQG_TRY(g_aux.init());
   cudaStream_t ax = g_aux.s[AuxStream::NS - 1];
   mark(6, st);
-  MMQG_TRY(b.dec_loop(st));
+  if (lh_def) {
+    // loss-head backward on its own stream under the BPTT loop, one event per group
+    cudaStream_t lh = g_aux.s[AuxStream::NS - 2];
+    int lo[kMaxLhGroups];
+    const int n = b.lh_groups(lo);
+    MMQG_CUDA(cudaEventRecord(g_aux.ev[10], st));
+    MMQG_CUDA(cudaStreamWaitEvent(lh, g_aux.ev[10], 0));
+    for (int k = 0; k < n; ++k) {
+      MMQG_TRY(b.loss_head_bwd(lo[k], k == 0 ? d.T_q : lo[k - 1], k == 0, lh));
+      MMQG_CUDA(cudaEventRecord(ev_lh(k), lh));
+    }
+    if (ready && ready[0]) MMQG_CUDA(cudaEventRecord(ready[0], lh));          // loss-head group final
+    MMQG_CUDA(cudaEventRecord(g_aux.ev[11], lh));
+    MMQG_TRY(b.dec_loop(st, lo, n));
+    MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[11], 0));                     // join the loss-head stream
+  } else {
+    if (ready && ready[0]) MMQG_CUDA(cudaEventRecord(ready[0], st));          // final since the forward call
+    MMQG_TRY(b.dec_loop(st));
+  }
   mark(7, st);
   MMQG_CUDA(cudaEventRecord(g_aux.ev[0], st));
   MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[0], 0));
   MMQG_TRY(b.dec_hoisted(ax));
-  if (ready && ready[0]) MMQG_CUDA(cudaEventRecord(ready[0], ax));     // decoder group final
+  if (ready && ready[1]) MMQG_CUDA(cudaEventRecord(ready[1], ax));     // decoder group final
   MMQG_TRY(b.video(ax));
-  if (ready && ready[1]) MMQG_CUDA(cudaEventRecord(ready[1], ax));     // video group final
+  if (ready && ready[2]) MMQG_CUDA(cudaEventRecord(ready[2], ax));     // video group final
   if (NC > 1) {
     MMQG_TRY(b.text_pipelined(NC, st, ax, ready));
   } else {
@@ -1126,7 +1245,7 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
       MMQG_CUDA(cudaEventRecord(g_aux.ev[3 + l], st));
       MMQG_CUDA(cudaStreamWaitEvent(ax, g_aux.ev[3 + l], 0));
       MMQG_TRY(b.text_hoisted(l, ax));
-      if (ready && ready[2 + (d.L - 1 - l)]) MMQG_CUDA(cudaEventRecord(ready[2 + (d.L - 1 - l)], ax));
+      if (ready && ready[3 + (d.L - 1 - l)]) MMQG_CUDA(cudaEventRecord(ready[3 + (d.L - 1 - l)], ax));
     }
   }
   mark(8, st);
@@ -1134,7 +1253,7 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   MMQG_CUDA(cudaStreamWaitEvent(st, g_aux.ev[7], 0));       // join: everything is ordered on `st` again
   MMQG_TRY(b.emb_enc(st, NC > 1));
   mark(9, st);
-  if (ready && ready[2 + d.L]) MMQG_CUDA(cudaEventRecord(ready[2 + d.L], st));     // shared embedding final (both scatter-adds landed)
+  if (ready && ready[3 + d.L]) MMQG_CUDA(cudaEventRecord(ready[3 + d.L], st));     // shared embedding final (both scatter-adds landed)
   return 0;
 }
 

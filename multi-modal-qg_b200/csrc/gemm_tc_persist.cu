@@ -291,8 +291,12 @@ static int launch_vocab(const CUtensorMap& a, const CUtensorMap& b, const TcGemm
     MMQG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr = true;
   }
+  // MMQG_LH_CTAS caps the CTAs of the loss-head products: they share the GPU with the latency-bound decoder loops,
+  // whose kernels cannot co-reside with a ~200 KB-shared-memory CTA on the same SM
+  static const int cap = []() { const char* e = getenv("MMQG_LH_CTAS"); return e ? atoi(e) : 0; }();
   const int n_tiles = ceil_div(p.M, PBM) * ceil_div(p.N, PBN);
-  const int grid = n_tiles < sms ? n_tiles : sms;
+  int grid = n_tiles < sms ? n_tiles : sms;
+  if (cap > 0 && grid > cap) grid = cap;
   gemm_tc_persist_kernel<false, false, EPI><<<grid, 192, PSMEM, st>>>(a, b, a, b, p);
   MMQG_LAUNCH_CHECK();
   return 0;

@@ -123,6 +123,23 @@ int lstm_seq_fwd_cluster(float* gates, float* cs, void* hs, const void* wp_fwd32
                          int H, cudaStream_t st);
 int lstm_seq_bwd_cluster(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext, long long ext_ts,
                          long long ext_ld, const float* dh_last, const float* dc_last, int T, int B, int H, cudaStream_t st);
+// persistent decoder-step kernel, forward (dec_persist.cu)
+struct DecPersistShape { int B, H, C, Sp, TM, AM, T_t, T_v, H_a, H_v, L; };
+struct DecPersistArgs {
+  DecPersistShape shape;
+  int Tq;                                   // decoder steps of the whole sequence (sizes of the buffers below)
+  float* attn_all; void* ctx16;             // (Tq*B, Sp) fp32, (Tq*B, C) bf16
+  float* acts[3]; float* cs[3]; void* hs[3]; void* hdrop[3]; const float* bias[3];
+  const void* w_hh[3]; const void* w_in[3]; // 16-unit gate-slice row order (pack_whh forward layout / pack_rows_gate16), bf16
+  const void* wa_h;                         // (Sp, H) bf16
+  const void* m_txt16; const void* m_vid16; const float* m_aud;
+  uint32_t* flags;                          // dec_persist_flag_words() words, zeroed before the first launch of a sequence
+  float drop_p; unsigned long long seed; const unsigned long long* ctr; int sid0;
+};
+bool dec_persist_ok(const DecPersistShape& s);
+size_t dec_persist_flag_words(const DecPersistShape& s, int Tq);
+int pack_rows_gate16(const float* w, int ld, int K, int Kp, void* out, int H, cudaStream_t st);
+int dec_seq_fwd_persist(const DecPersistArgs& a, int t0, int T, cudaStream_t st);
 // bf16-mode orchestration (engine_bf16.cu)
 size_t train_workspace_bytes_bf16(const mmqg_dims& d, int T_q);
 int check_dims_bf16(const mmqg_dims& d);

@@ -21,7 +21,7 @@ class GradReducer:
             # ready events the library records where each gradient group becomes final, and the
             # stream the all-reduces are issued from (so they are ordered after the event only,
             # not after the rest of the backward on the compute stream)
-            self.events = [torch.cuda.Event() for _ in range(len(self.buckets) - 1)]    # every group after the loss head
+            self.events = [torch.cuda.Event() for _ in range(len(self.buckets))]        # one per gradient group
             for e in self.events:
                 e.record()                     # torch creates the cudaEvent_t lazily, at first record
             self.side = torch.cuda.Stream()
@@ -35,10 +35,10 @@ class GradReducer:
             self.works.append(dist.all_reduce(self.buckets[g], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def after_backward(self):
-        """After engine.backward_events(): start the all-reduce of every group after the loss head, each behind
-        its ready event on the side stream (decoder, video, text layers top to bottom, shared embedding)."""
-        for i in range(1, len(self.buckets)):
-            self.side.wait_event(self.events[i - 1])
+        """After engine.backward_events(): start the all-reduce of every group, each behind its ready event on
+        the side stream (loss head, decoder, video, text layers top to bottom, shared embedding)."""
+        for i in range(len(self.buckets)):
+            self.side.wait_event(self.events[i])
             with torch.cuda.stream(self.side):
                 self.works.append(dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 

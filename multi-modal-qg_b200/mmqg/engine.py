@@ -114,17 +114,17 @@ class TrainEngine:
         """Whole backward with its internal overlap; events[i] (torch.cuda.Event, already created)
         is recorded where gradient group i+1 becomes final (mmqg_train_backward_events)."""
         cb = self._cbatch(batch)
-        assert len(events) == 3 + self.d.L, "one ready event per gradient group after the loss head"
+        assert len(events) == 4 + self.d.L, "one ready event per gradient group"
         arr = (C.c_void_p * len(events))(*[e.cuda_event for e in events])
         _cabi.check(self.lib.mmqg_train_backward_events(
             C.byref(self._cd), C.byref(self._cp), C.byref(cb), self.ws.data_ptr(), self.ws.numel(),
             C.byref(self._cg), arr, self.dropout_p, self.seed, self.mode, _stream_ptr()))
 
     def step_dp(self, batch, reducer, grad_scale):
-        """Data-parallel step: forward, all-reduce of the loss-head bucket, then the overlapped
-        backward with one all-reduce per gradient group started from the group's ready event."""
+        """Data-parallel step: forward, then the overlapped backward with one all-reduce per gradient group
+        (loss head included: its gradients may only be final inside the backward call, see mmqg.h) started from
+        the group's ready event."""
         loss = self.forward(batch, True, grad_scale)
-        reducer.on_phase(0)
         self.backward_events(batch, reducer.events)
         reducer.after_backward()
         return loss
@@ -137,9 +137,10 @@ class TrainEngine:
         if on_phase is None:
             self.backward(batch, 0)          # whole backward, hoisted products overlapped internally
         else:
-            on_phase(0)
             for ph in (1, 2, 3):
                 self.backward(batch, ph)
+                if ph == 1:
+                    on_phase(0)              # the loss-head gradients are final at the latest after phase 1 (mmqg.h)
                 on_phase(ph)
         return loss
 
