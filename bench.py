@@ -547,7 +547,9 @@ def main():
         ms, ms_e2e = float(t[0]), float(t[1])
 
     # ---- data-parallel correctness (N > 1), visible in the bench line ------------------------
+    print(f"[bench rank {rank}] timed regions done: {ms / args.steps:.3f} ms/step", file=sys.stderr, flush=True)
     dpc = dp_check(eng, d, params, reducer, world, rank, dev, dbatch) if world > 1 else None
+    print(f"[bench rank {rank}] dp_check done", file=sys.stderr, flush=True)
 
     # ---- roofline probe of the dominant kernel class (separate eager pass, same step) ---------
     roof = None
