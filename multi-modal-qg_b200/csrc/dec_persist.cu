@@ -60,9 +60,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 __device__ __forceinline__ void wait_count(const uint32_t* f, uint32_t target) {
-  while (ld_relaxed_gpu(f) < target) {
+  while (ld_acquire_gpu(f) < target) {      // acquire load: no MEMBAR behind the poll (see lstm_persist.cu)
   }
-  fence_acq_rel_gpu();
 }
 
 // warp-cooperative tile movers (same scheme as lstm_persist.cu: 4 lanes share a 64-byte row segment)
@@ -132,6 +131,7 @@ struct Maps {
 struct P {
   int T, t0, Tq, B, H, C, Sp, TM, AM, T_t, T_v, H_a, H_v, L;
   int n_slices, n_nt, KBh, KBc;
+  int g0;                          // first group of this launch (batches with more groups than fit on the SMs run in waves)
   float* attn_all;                 // (Tq*B, Sp): in = hoisted embedding part + bias, out = softmax weights
   bf16* ctx16;                     // (Tq*B, C)
   float* acts[MAXL];               // (Tq*B, 4H): layer 0 in = hoisted embedding product + bias; out = activated gates
@@ -184,7 +184,7 @@ dec_seq_fwd_kernel(const __grid_constant__ Maps maps, const P p) {
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x / p.n_slices, s = blockIdx.x % p.n_slices;      // group, unit slice
+  const int g = p.g0 + blockIdx.x / p.n_slices, s = blockIdx.x % p.n_slices;      // group, unit slice
   const int B = p.B, H = p.H, G = 4 * p.H, L = p.L;
   const int row_g0 = g * ROWS;                                 // first batch row of the group
   const int rows_grp = min(ROWS, B - row_g0);
@@ -608,14 +608,13 @@ static int dec_sms() {
   return n;
 }
 
+// Rows per group: 64 (shorter steps: half the attention samples per CTA) when all groups of the batch fit on the
+// SMs at once, else 128; batches with more 128-row groups than fit run in waves of co-resident groups.
 int dec_persist_rows(int B, int H) {
   static const int want = []() { const char* e = getenv("MMQG_DEC_ROWS"); return e ? atoi(e) : 64; }();
-  if (want == 0) return 0;
-  for (int rows : {want == 128 ? 128 : 64, 128}) {
-    const int n_grp = ceil_div(B, rows);
-    if (n_grp * (H / 16) <= dec_sms()) return rows;
-  }
-  return 0;
+  if (want == 0 || H / 16 > dec_sms()) return 0;
+  if (want != 128 && ceil_div(B, 64) * (H / 16) <= dec_sms()) return 64;
+  return 128;
 }
 
 bool dec_persist_ok(const DecPersistShape& s) {
@@ -631,6 +630,13 @@ int pack_rows_gate16(const float* w, int ld, int K, int Kp, void* out, int H, cu
   dp::pack_rows_gate16_kernel<<<4 * H, 128, 0, st>>>(w, ld, K, Kp, reinterpret_cast<bf16*>(out), H);
   MMQG_LAUNCH_CHECK();
   return 0;
+}
+
+// launches one call needs: groups beyond the co-resident ones run in further waves
+int dec_persist_waves(const DecPersistShape& s) {
+  const int rows = dec_persist_rows(s.B, s.H);
+  if (!rows) return 0;
+  return ceil_div(ceil_div(s.B, rows), dec_sms() / (s.H / 16));
 }
 
 size_t dec_persist_flag_words(const DecPersistShape& s, int Tq) {
@@ -697,9 +703,14 @@ int dec_seq_fwd_persist(const DecPersistArgs& a, int t0, int T, cudaStream_t st)
   const double fl = 2.0 * T * s.B * ((double)s.Sp * s.H + 4.0 * s.H * ((double)s.C + s.H + (s.L - 1) * 2.0 * s.H) +
                                      (double)s.T_t * s.H + (double)s.T_v * (s.H_a + s.H_v));
   MMQG_PROBE(KC_GEMM_STEP, fl, 0);
-  if (rows == 64) MMQG_TRY(launch_dec<64>(maps, p, n_grp, st));
-  else MMQG_TRY(launch_dec<128>(maps, p, n_grp, st));
-  MMQG_LAUNCH_CHECK();
+  const int per_wave = dec_sms() / p.n_slices;       // co-resident groups
+  for (int g0 = 0; g0 < n_grp; g0 += per_wave) {
+    p.g0 = g0;
+    const int ng = n_grp - g0 < per_wave ? n_grp - g0 : per_wave;
+    if (rows == 64) MMQG_TRY(launch_dec<64>(maps, p, ng, st));
+    else MMQG_TRY(launch_dec<128>(maps, p, ng, st));
+    MMQG_LAUNCH_CHECK();
+  }
   return 0;
 }
 

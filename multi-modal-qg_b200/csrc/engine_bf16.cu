@@ -265,10 +265,11 @@ static bool cluster_enabled() {
   return v != 0;
 }
 // 2 = cluster kernels (barrier.cluster + TMA multicast), 1 = global-flag persistent kernels, 0 = per-step launches
+static thread_local bool g_fwd_only = false;      // greedy decode: only the forward kernels (which cover twice the batch rows) are needed
 static int persist_kind(int B, int H) {
   if (!persist_enabled()) return 0;
   if (cluster_enabled() && lstm_cluster_ok(B, H)) return 2;
-  return lstm_persist_ok(B, H) ? 1 : 0;
+  return (g_fwd_only ? lstm_persist_fwd_ok(B, H) : lstm_persist_ok(B, H)) ? 1 : 0;
 }
 static bool persist_text(const mmqg_dims& d) { return persist_kind(d.B, d.H) != 0; }
 static bool persist_video(const mmqg_dims& d) { return persist_kind(d.B, d.H_v) != 0; }
@@ -389,7 +390,7 @@ static int pack_weights_rest(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w,
 // crawls on the 20 spare SMs for 50-100 us while the layer that needs it idles (measured with
 // tools/ktrace.py).  MMQG_PRIO=0 creates all streams alike.
 struct AuxStream {
-  static constexpr int NS = 4, NE = 160;
+  static constexpr int NS = 4, NE = 288;
   cudaStream_t s[NS] = {};
   cudaStream_t g[NS] = {};
   cudaStream_t chain = nullptr;
@@ -452,14 +453,14 @@ struct AuxStream {
   }
 };
 static AuxStream g_aux;
-static constexpr int kMaxChunks = 8;
-// event slots: [0,16) misc, [16,48) forward done(l,c), [48,80) backward done(l,c),
-// [96,128) / [128,160) hand-over between a layer stream and its product stream g[l]
-static cudaEvent_t ev_fwd(int l, int c) { return g_aux.ev[16 + l * kMaxChunks + c]; }
-static cudaEvent_t ev_bwd(int l, int c) { return g_aux.ev[48 + l * kMaxChunks + c]; }
-static cudaEvent_t ev_gf(int l, int c) { return g_aux.ev[96 + l * kMaxChunks + c]; }
-static cudaEvent_t ev_gb(int l, int c) { return g_aux.ev[128 + l * kMaxChunks + c]; }
-static cudaEvent_t ev_lh(int g) { return g_aux.ev[80 + g]; }       // slots [80, 96): loss-head groups of the deferred backward
+static constexpr int kMaxChunks = 16;
+// event slots: [0,16) misc, [16,32) loss-head groups of the deferred backward, then 64 each (NS layers x kMaxChunks):
+// forward done(l,c), backward done(l,c), and the two hand-overs between a layer stream and its product stream g[l]
+static cudaEvent_t ev_lh(int g) { return g_aux.ev[16 + g]; }
+static cudaEvent_t ev_fwd(int l, int c) { return g_aux.ev[32 + l * kMaxChunks + c]; }
+static cudaEvent_t ev_bwd(int l, int c) { return g_aux.ev[96 + l * kMaxChunks + c]; }
+static cudaEvent_t ev_gf(int l, int c) { return g_aux.ev[160 + l * kMaxChunks + c]; }
+static cudaEvent_t ev_gb(int l, int c) { return g_aux.ev[224 + l * kMaxChunks + c]; }
 static bool split_products() {
   static const bool on = []() { const char* e = getenv("MMQG_GSTREAMS"); return !(e && e[0] == '0'); }();
   return on && g_aux.prio;
@@ -475,6 +476,7 @@ static int text_chunks(const mmqg_dims& d) {
   if (want < 1) want = 1;
   if (want > kMaxChunks) want = kMaxChunks;
   if (persist_kind(d.B, d.H) != 1 || d.L < 2 || d.L > AuxStream::NS) return 1;
+  if (2 * lstm_persist_fwd_ctas(d.B, d.H) > device_sms()) return 1;      // two layer kernels cannot be co-resident: nothing to pipeline
   int nc = want;
   while (nc > 1 && d.T_t / nc < 8) --nc;
   return nc;
@@ -631,6 +633,7 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   MMQG_TRY(check_dims_bf16(d));
   g_drop_p = dropout_p;
   g_drop_seed = seed;
+  g_fwd_only = false;
   Ws16 w = carve16(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   const int B = d.B, H = d.H, G = 4 * d.H, C = d.H + d.H_a + d.H_v, R = d.T_q * B, Sp = w.Sp, Ep = w.Ep;
@@ -802,6 +805,7 @@ int greedy_decode_bf16(const mmqg_dims& d, const mmqg_tensors& P, const mmqg_bat
   g_drop_p = 0.f;
   g_drop_seed = 0;
   g_drop_ctr = w.seed_ctr;
+  g_fwd_only = true;
   MMQG_TRY(set_len_state(d, bt, w));
   cudaStream_t st;
   MMQG_TRY(g_aux.enter(user, &st));
@@ -828,6 +832,25 @@ static int greedy_decode_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   as.ldctx16 = C;
   MMQG_TRY(fill_i64(w.idx_cur, B, 1, st));                      // <start>, train.py:84
   PdlScope pdl_scope(pdl_enabled());
+  // K6: one decoder step = embedding gather, the two embedding-column products, ONE launch of the persistent
+  // decoder-step kernel (scores, attention heads, the three LSTM cells; dec_persist.cu with T = 1) and the
+  // vocabulary projection with the arg-max in its epilogue
+  // (measured at B = 1024, two waves of 128-row groups: 8.2 ms per batch against 7.9 ms for the launch-per-phase step,
+  // so batches that need more than one wave keep the latter)
+  const bool dec_persist = dec_persist_enabled(d, w) && dec_persist_waves(dec_shape(d, w)) == 1;
+  DecPersistArgs dpa{};
+  if (dec_persist) {
+    dpa.shape = dec_shape(d, w);
+    dpa.Tq = max_len; dpa.attn_all = w.attn_all; dpa.ctx16 = w.ctx16;
+    for (int l = 0; l < d.L; ++l) {
+      dpa.acts[l] = w.acts_dec[l]; dpa.cs[l] = w.cs_dec[l]; dpa.hs[l] = w.hs_dec[l];
+      dpa.hdrop[l] = nullptr; dpa.bias[l] = l == 0 ? nullptr : w.bsum_dec[l];
+      dpa.w_hh[l] = w.wdp_hh[l]; dpa.w_in[l] = w.wdp_in[l];
+    }
+    dpa.wa_h = w.wa_h; dpa.m_txt16 = w.m_txt16; dpa.m_vid16 = w.m_vid16; dpa.m_aud = w.m_aud; dpa.flags = w.flags_dec;
+    dpa.drop_p = 0.f; dpa.sid0 = kSidDec;
+    MMQG_CUDA(cudaMemsetAsync(w.flags_dec, 0, sizeof(uint32_t) * dec_persist_flag_words(dpa.shape, max_len), st));
+  }
   for (int t = 0; t < max_len; ++t) {
     StepGemmScope step_scope;
     b16* e_t = w.e_dec + (size_t)t * B * Ep;
@@ -838,6 +861,12 @@ static int greedy_decode_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
     const b16* htop_prev = w.hs_dec[d.L - 1] + (size_t)t * B * H;
     float* sc = w.attn_all + (size_t)t * B * Sp;
     b16* ctx = w.ctx16 + (size_t)t * B * C;
+    if (dec_persist) {
+      PdlScope no_pdl(false);
+      MMQG_TRY(Tc(e_t, Ep, false, w.wd_e, Ep, false, B, G, Ep, w.acts_dec[0] + (size_t)t * B * G, G).bias(w.bsum_dec[0]).run(st));
+      MMQG_TRY(Tc(e_t, Ep, false, w.wa_e, Ep, false, B, Sp, Ep, sc, Sp).bias(w.attn_b_cat).run(st));
+      MMQG_TRY(dec_seq_fwd_persist(dpa, t, 1, st));
+    } else {
     MMQG_TRY(Tc(e_t, Ep, false, w.wa_e, Ep, false, B, Sp, Ep, sc, Sp).second(htop_prev, H, w.wa_h, H, H).bias(w.attn_b_cat).run(st));
     as.ctx16 = ctx;
     MMQG_TRY(attn_fwd(sc, Sp, w.m_txt, w.m_aud, w.m_vid, w.ctx_tmp, C, as, st));
@@ -854,6 +883,7 @@ static int greedy_decode_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
       }
       MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
                                        w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st));
+    }
     }
     const b16* htop = w.hs_dec[d.L - 1] + (size_t)(t + 1) * B * H;
     PdlScope no_pdl(false);
@@ -1177,6 +1207,7 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   MMQG_TRY(check_dims_bf16(d));
   g_drop_p = dropout_p;
   g_drop_seed = seed;
+  g_fwd_only = false;
   Ws16 w = carve16(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes) return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   g_drop_ctr = w.seed_ctr;      // unchanged since the forward of this step: the same masks

@@ -97,6 +97,9 @@ int audio_pad(const float* audio, float* m_aud, const int* n_frames, int B, int 
 int dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, cudaStream_t st);
 // persistent recurrent-cell kernels (lstm_persist.cu)
 bool lstm_persist_ok(int B, int H);
+bool lstm_persist_fwd_ok(int B, int H);     // forward kernel alone (two m-tiles per CTA)
+int lstm_persist_fwd_ctas(int B, int H);    // CTAs of one forward launch
+int device_sms();
 int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st);
 // Variable-length batches in the persistent recurrent kernels: sample (row) m is right-aligned in time,
 // its steps t_base + t < shift[m] are masked (state held at zero, no gradient); with mem_shift the
@@ -137,6 +140,7 @@ struct DecPersistArgs {
   float drop_p; unsigned long long seed; const unsigned long long* ctr; int sid0;
 };
 bool dec_persist_ok(const DecPersistShape& s);
+int dec_persist_waves(const DecPersistShape& s);     // launches per call (1 = all groups co-resident)
 size_t dec_persist_flag_words(const DecPersistShape& s, int Tq);
 int pack_rows_gate16(const float* w, int ld, int K, int Kp, void* out, int H, cudaStream_t st);
 int dec_seq_fwd_persist(const DecPersistArgs& a, int t0, int T, cudaStream_t st);

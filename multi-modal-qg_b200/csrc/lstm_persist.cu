@@ -207,10 +207,10 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         if (t > 0) {
           mbar_wait(&mma_done, (t - 1) & 1);                       // sA is free again
           const uint32_t* f = p.flags + (size_t)t * p.n_mt + mt;    // h_{t-1} complete for this m-tile?
-          while (ld_relaxed_gpu(f) < (uint32_t)p.n_slices) {
+          // acquire load (measured 0.4 us per step cheaper than a relaxed poll + fence.acq_rel.gpu, which costs a MEMBAR)
+          while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
           }
-          fence_acq_rel_gpu();      // acquire: orders the counter observation before the loads below
-          fence_proxy_async();      // ... and hands that ordering to the async proxy (TMA)
+          fence_proxy_async();      // hands the ordering of the counter observation to the async proxy (TMA)
         }
         if (tr) { const long long g = gtime(); atomicMin((unsigned long long*)&tr[t * 8 + 0], (unsigned long long)g); atomicMax((unsigned long long*)&tr[t * 8 + 1], (unsigned long long)g); }
         for (int kb = 0; kb < p.KB; ++kb) {
@@ -363,6 +363,230 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two m-tiles per CTA.  The recurrences of different batch rows are independent chains, and one step of a chain
+// is a sequence of latencies (counter poll -> TMA -> MMA -> TMEM load -> cell math -> store -> fence -> counter)
+// that leaves the SM idle most of the time.  Here CTA (s, pair) serves m-tiles 2*pair and 2*pair+1 with ONE
+// resident weight slice: the TMA and MMA threads alternate between the two chains through one 8-stage operand
+// ring, each chain has its own accumulator columns in tensor memory, its own 4 epilogue warps and its own
+// barriers, so the operand ingest of one chain runs under the hand-over latency of the other.  Same per-step
+// time with half the CTAs per layer (32 at H = 512, B = 256): three or four layer/chunk kernels are co-resident
+// on the 148 SMs instead of two.  Arrival counters and data layouts are those of lstm_seq_fwd_kernel.
+static constexpr int FWD2_STAGES = 8;
+
+__global__ void __launch_bounds__(320, 1)
+lstm_seq_fwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;                              // KB x (64 rows x 128 B), resident
+  uint8_t* sA = smem + p.KB * 8192;                // FWD2_STAGES x (128 rows x 128 B) ring shared by both chains
+  float* stg_base = reinterpret_cast<float*>(sA + FWD2_STAGES * 16384);
+  __shared__ uint64_t w_full, full[FWD2_STAGES], empty[FWD2_STAGES], mma_done[2], tmem_free[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x;
+  const int H = p.H, B = p.B, G = 4 * p.H;
+  const int mt0 = 2 * blockIdx.y;
+  const int n_chain = min(2, p.n_mt - mt0);        // 1 when the number of m-tiles is odd and this is the last CTA row
+
+  if (threadIdx.x == 0) {
+    mbar_init(&w_full, 1);
+    for (int s = 0; s < FWD2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int q = 0; q < 2; ++q) { mbar_init(&mma_done[q], 1); mbar_init(&tmem_free[q], 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmH);
+  }
+  if (warp == 9) tmem_alloc(&tmem_slot, 128);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 8) {
+    // ---- TMA producer: chains alternate step by step ----
+    if (elect_one()) {
+      long long* trp = (p.trace && slice == 0 && blockIdx.y == 0) ? p.trace : nullptr;   // debug stamps, see tools/trace_lstm2.py
+      mbar_expect_tx(&w_full, p.KB * 8192);
+      for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, &w_full, kb * 64, slice * 64);
+      int i = 0;
+      for (int t = 0; t < p.T; ++t) {
+        for (int q = 0; q < n_chain; ++q) {
+          const int mt = mt0 + q;
+          if (t > 0) {
+            const uint32_t* f = p.flags + (size_t)t * p.n_mt + mt;    // h_{t-1} complete for this m-tile?
+            if (trp) trp[t * 16 + q * 8 + 7] = gtime();
+            while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
+            }
+            fence_proxy_async();
+          }
+          if (trp) trp[t * 16 + q * 8 + 0] = gtime();
+          for (int kb = 0; kb < p.KB; ++kb, ++i) {
+            const int st = i % FWD2_STAGES, ph = (i / FWD2_STAGES) & 1;
+            mbar_wait(&empty[st], ph ^ 1);
+            mbar_expect_tx(&full[st], 16384);
+            tma_load_2d(sA + st * 16384, &tmH, &full[st], kb * 64, t * B + mt * 128);
+          }
+          if (trp) trp[t * 16 + q * 8 + 1] = gtime();
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ---- MMA issuer: same job order as the producer ----
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      long long* trm = (p.trace && slice == 0 && blockIdx.y == 0) ? p.trace : nullptr;
+      mbar_wait(&w_full, 0);
+      int i = 0;
+      for (int t = 0; t < p.T; ++t) {
+        for (int q = 0; q < n_chain; ++q) {
+          if (t > 0) mbar_wait(&tmem_free[q], (t - 1) & 1);           // the chain's epilogue has drained its accumulator
+          tc_fence_after_sync();
+          for (int kb = 0; kb < p.KB; ++kb, ++i) {
+            const int st = i % FWD2_STAGES, ph = (i / FWD2_STAGES) & 1;
+            mbar_wait(&full[st], ph);
+            tc_fence_after_sync();
+            const uint32_t a_addr = smem_u32(sA + st * 16384), b_addr = smem_u32(sW + kb * 8192);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + q * 64, umma_smem_desc(a_addr + k * 32, 16, 1024), umma_smem_desc(b_addr + k * 32, 16, 1024),
+                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[st]);
+          }
+          umma_commit(&mma_done[q]);
+          if (trm) trm[t * 16 + q * 8 + 2] = gtime();
+        }
+      }
+    }
+  } else if ((warp >> 2) < n_chain) {
+    // ---- epilogue warps of chain q: thread = batch row, 16 hidden units x 4 gates ----
+    const int q = warp >> 2, ws = warp & 3;
+    const int mt = mt0 + q;
+    const int row = ws * 32 + lane;
+    const int m0w = mt * 128 + ws * 32;
+    const int m = m0w + lane;
+    const bool valid = m < B;
+    const int rows_valid = max(0, min(32, B - m0w));
+    const int j0 = slice * 16;
+    float* stg = stg_base + warp * STG_WARP;
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(32 * ws) << 16) + q * 64;
+    const bool kt = p.ktrace && row == 0 && slice == 0 && mt == 0;
+    const int kslot = kt ? ktrace_begin(p.ktrace, p.ktag) : 0;
+    const int sh = (p.len.shift && valid) ? p.len.shift[m] : 0;
+    long long* tre = (p.trace && row == 0 && slice == 0 && blockIdx.y == 0) ? p.trace : nullptr;
+    float c[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) c[u] = 0.f;
+    if (p.load_c0) {
+      float4 c4[4];
+      coop_ldg(p.cs + (size_t)m0w * H + j0, H, rows_valid, lane, c4);
+      coop_to_row(stg, lane, c4, c);
+    }
+    for (int t = 0; t < p.T; ++t) {
+      float* gbase = p.gates + ((size_t)t * B + m0w) * G + j0;
+      float gxr[64];
+      {
+        float4 gxc[4][4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) coop_ldg(gbase + g * H, G, rows_valid, lane, gxc[g]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) coop_to_row(stg, lane, gxc[g], gxr + g * 16);
+      }
+      mbar_wait(&mma_done[q], t & 1);
+      if (tre) tre[t * 16 + q * 8 + 3] = gtime();
+      tc_fence_after_sync();
+      float acc[64];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld_32x16(tacc + g * 16, acc + g * 16);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_free[q]);
+#pragma unroll
+      for (int u = 0; u < 64; ++u) acc[u] += gxr[u];
+      float hv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const float ig = sigm_fast(acc[u]);
+        const float fg = sigm_fast(acc[16 + u]);
+        const float gg = tanh_fast(acc[32 + u]);
+        const float og = sigm_fast(acc[48 + u]);
+        c[u] = fmaf(fg, c[u], ig * gg);
+        hv[u] = og * tanh_fast(c[u]);
+        acc[u] = ig; acc[16 + u] = fg; acc[32 + u] = gg; acc[48 + u] = og;
+      }
+      const int tg = p.len.t_base + t;
+      if (tg < sh) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { c[u] = 0.f; hv[u] = 0.f; }
+      }
+      uint32_t hp[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(hv[2 * v], hv[2 * v + 1]);
+        hp[v] = *reinterpret_cast<uint32_t*>(&t2);
+      }
+      row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.hs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid);
+      // publish: barrier over the chain's 4 warps, then ONE thread fences and bumps the m-tile's counter
+      if (q == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (row == 0) {
+        if (tre) tre[t * 16 + q * 8 + 4] = gtime();
+        __threadfence();
+        red_relaxed_gpu_add(p.flags + (size_t)(t + 1) * p.n_mt + mt, 1u);
+        if (tre) tre[t * 16 + q * 8 + 5] = gtime();
+      }
+      // saved activations, c_t, attention-memory copy, dropped copy: off the critical path
+      {
+        float4 tmp[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          row_to_coop(stg, lane, acc + g * 16, tmp);
+          coop_stg(gbase + g * H, G, rows_valid, lane, tmp);
+        }
+        row_to_coop(stg, lane, c, tmp);
+        coop_stg(p.cs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid, lane, tmp);
+        const bool shifted = p.len.shift && p.len.mem_shift;
+        if (p.mem) {
+          row_to_coop(stg, lane, hv, tmp);
+          if (shifted) coop_stg_shift(p.mem + (size_t)m0w * p.mem_ld + (size_t)t * H + j0, (size_t)p.mem_ld, rows_valid, lane, tmp, sh, tg, H);
+          else coop_stg(p.mem + (size_t)m0w * p.mem_ld + (size_t)t * H + j0, (size_t)p.mem_ld, rows_valid, lane, tmp);
+        }
+        if (p.mem16) {
+          if (shifted)
+            row_bf16_to_global_shift(reinterpret_cast<uint32_t*>(stg), lane, hp, p.mem16 + (size_t)m0w * p.mem_ld + (size_t)t * H + j0,
+                                     (size_t)p.mem_ld, rows_valid, sh, tg, H);
+          else
+            row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, hp, p.mem16 + (size_t)m0w * p.mem_ld + (size_t)t * H + j0,
+                               (size_t)p.mem_ld, rows_valid);
+        }
+        if (p.dr.out) {
+          const float ik = 1.0f / (1.0f - p.dr.p);
+          const unsigned long long sd = p.dr.seed + (p.dr.ctr ? *p.dr.ctr : 0ull);
+          const unsigned long long e0 = p.dr.base + ((unsigned long long)t * B + m) * H + j0;
+          uint32_t dp[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(hv[2 * v] * drop_scale(sd, p.dr.sid, e0 + 2 * v, p.dr.p, ik),
+                                                      hv[2 * v + 1] * drop_scale(sd, p.dr.sid, e0 + 2 * v + 1, p.dr.p, ik));
+            dp[v] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, dp, reinterpret_cast<bf16*>(p.dr.out) + ((size_t)t * B + m0w) * p.dr.ld + j0,
+                             (size_t)p.dr.ld, rows_valid);
+        }
+      }
+      if (tre) tre[t * 16 + q * 8 + 6] = gtime();
+    }
+    if (kt) ktrace_end(p.ktrace, kslot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct LstmBwdP {
   const float* acts;   // (T*B, 4H) activated gates from the forward
   const float* cs;     // ((T+1)*B, H) cell states (slab 0 must hold c_{-1}: zeros for the encoders)
@@ -418,9 +642,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       for (int t = T - 1 - (p.has_next ? 0 : 1); t >= 0; --t) {   // step t consumes dG_{t+1}
         if (t + 1 < T) {                           // slab T comes from an earlier launch: already complete
           const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
-          while (ld_relaxed_gpu(f) < (uint32_t)p.n_slices) {
+          while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
           }
-          fence_acq_rel_gpu();
           fence_proxy_async();
         }
         for (int kb = 0; kb < p.NKB; ++kb, ++i) {
@@ -674,9 +897,8 @@ lstm_seq_bwd4_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
       for (int t = t_first; t >= 0; --t) {          // step t consumes dG_{t+1}
         if (t + 1 < T) {                            // slab T comes from an earlier launch: already complete
           const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
-          while (ld_relaxed_gpu(f) < (uint32_t)p.n_slices) {
+          while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
           }
-          fence_acq_rel_gpu();
           fence_proxy_async();
         }
         for (int kb = 0; kb < KB; ++kb, ++i) {
@@ -917,6 +1139,28 @@ bool lstm_persist_ok(int B, int H) {
   return (H / 16) * n_mt <= num_sms();
 }
 
+int device_sms() { return num_sms(); }
+// Which forward kernel: one m-tile per CTA runs a step in 5.3 us, two per CTA in 7.4 us (the operand ingest of the two
+// chains, 2 x 128 KB per step, serialises on the SM's ~107 GB/s L2 port) -- so the two-chain kernel is taken when
+// the one-chain grid does not leave room for a second co-resident launch (B > 256 at H = 512: the layer wavefront
+// would collapse, or the grid would not fit at all).  MMQG_FWD2=2 forces it wherever it applies.
+static bool fwd2_launch(int n_slices, int n_mt) {
+  static const int mode = []() { const char* e = getenv("MMQG_FWD2"); return e ? atoi(e) : 1; }();
+  if (mode == 0 || n_mt < 2) return false;
+  return mode == 2 || 2 * n_slices * n_mt > num_sms();
+}
+// the forward kernel alone: with two m-tiles per CTA it covers twice the batch rows of the BPTT kernel
+bool lstm_persist_fwd_ok(int B, int H) {
+  if (H % 64 != 0 || H > 512 || H < 64) return false;
+  const int n_mt = ceil_div(B, 128);
+  return (H / 16) * (fwd2_launch(H / 16, n_mt) ? ceil_div(n_mt, 2) : n_mt) <= num_sms();
+}
+
+int lstm_persist_fwd_ctas(int B, int H) {
+  const int n_mt = ceil_div(B, 128);
+  return (H / 16) * (fwd2_launch(H / 16, n_mt) ? ceil_div(n_mt, 2) : n_mt);
+}
+
 int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st) {
   MMQG_REQUIRE(w_hh && H % 32 == 0, "pack_whh: bad args");
   if (fwd_packed) {
@@ -956,7 +1200,7 @@ static int launch_coop(Kern kern, dim3 grid, int threads, size_t smem, const CUt
 // gates: (T*B,4H) fp32 pre-gates -> activated gates.  wp_fwd: pack_whh forward layout.  hs slab 0 must be zeros.
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,
                          uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st, DropSpec dr, bool zero_flags, LenSpec len) {
-  MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
+  MMQG_REQUIRE(lstm_persist_fwd_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
   LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, reinterpret_cast<bf16*>(mem16), mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace, g_ktrace, tl_ktag, dr, len};
   CUtensorMap tmW, tmH;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_fwd, 4 * (uint64_t)H, H, H, 64, 64));
@@ -969,6 +1213,19 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
   }
   if (zero_flags) MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(T + 1) * p.n_mt, st));
   const double fl = 2.0 * T * B * 4.0 * H * H;
+  if (fwd2_launch(p.n_slices, p.n_mt)) {      // two m-tiles per CTA: half the CTAs per launch
+    const size_t smem2 = (size_t)p.KB * 8192 + FWD2_STAGES * 16384 + 8 * STG_WARP * sizeof(float) + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     8 * 8192 + FWD2_STAGES * 16384 + 8 * STG_WARP * (int)sizeof(float) + 1024));
+      attr2 = true;
+    }
+    MMQG_PROBE(KC_LSTM_PERSIST, fl, 0);
+    MMQG_TRY(launch_coop(lstm_seq_fwd2_kernel, dim3(p.n_slices, ceil_div(p.n_mt, 2)), 320, smem2, tmW, tmH, p, st));
+    MMQG_LAUNCH_CHECK();
+    return 0;
+  }
   MMQG_PROBE(KC_LSTM_PERSIST, fl, 0);
   MMQG_TRY(launch_coop(lstm_seq_fwd_kernel, dim3(p.n_slices, p.n_mt), 160, smem, tmW, tmH, p, st));
   MMQG_LAUNCH_CHECK();
