@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "dec_common.cuh"
 #include "dropout.cuh"
 
 namespace mmqg {
@@ -35,89 +36,6 @@ using namespace tc;
 typedef __nv_bfloat16 bf16;
 
 namespace dp {
-
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sigm_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
-__device__ __forceinline__ float wmax(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float wsum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ void bar_epi(int nthreads) { asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void wait_count(const uint32_t* f, uint32_t target) {
-  while (ld_acquire_gpu(f) < target) {      // acquire load: no MEMBAR behind the poll (see lstm_persist.cu)
-  }
-}
-
-// warp-cooperative tile movers (same scheme as lstm_persist.cu: 4 lanes share a 64-byte row segment)
-static constexpr int STG_LD = 20;
-static constexpr int STG_WARP = 32 * STG_LD;
-__device__ __forceinline__ void coop_ldg(const float* base, size_t row_stride, int rows_valid, int lane, float4 (&v)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = 8 * i + (lane >> 2);
-    v[i] = r < rows_valid ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)r * row_stride + 4 * (lane & 3)))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-__device__ __forceinline__ void coop_stg(float* base, size_t row_stride, int rows_valid, int lane, const float4 (&v)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = 8 * i + (lane >> 2);
-    if (r < rows_valid) *reinterpret_cast<float4*>(base + (size_t)r * row_stride + 4 * (lane & 3)) = v[i];
-  }
-}
-__device__ __forceinline__ void coop_to_row(float* stg, int lane, const float4 (&v)[4], float* mine) {
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (8 * i + (lane >> 2)) * STG_LD + 4 * (lane & 3)) = v[i];
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 x = *reinterpret_cast<const float4*>(stg + lane * STG_LD + 4 * q);
-    mine[4 * q] = x.x; mine[4 * q + 1] = x.y; mine[4 * q + 2] = x.z; mine[4 * q + 3] = x.w;
-  }
-}
-__device__ __forceinline__ void row_to_coop(float* stg, int lane, const float* mine, float4 (&v)[4]) {
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * q) = make_float4(mine[4 * q], mine[4 * q + 1], mine[4 * q + 2], mine[4 * q + 3]);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(stg + (8 * i + (lane >> 2)) * STG_LD + 4 * (lane & 3));
-}
-__device__ __forceinline__ void row_bf16_to_global(uint32_t* stg, int lane, const uint32_t (&w8)[8], bf16* base, size_t row_stride,
-                                                   int rows_valid) {
-  __syncwarp();
-  *reinterpret_cast<uint4*>(stg + lane * 12) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-  *reinterpret_cast<uint4*>(stg + lane * 12 + 4) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r = 16 * i + (lane >> 1), hsel = lane & 1;
-    const uint4 x = *reinterpret_cast<const uint4*>(stg + r * 12 + 4 * hsel);
-    if (r < rows_valid) *reinterpret_cast<uint4*>(base + (size_t)r * row_stride + 8 * hsel) = x;
-  }
-}
-
-static constexpr int MAXL = 3;
-static constexpr int ASLOT = 24 * 1024;         // bytes of one attention-memory chunk
 
 struct Maps {
   CUtensorMap hs[MAXL];     // state sequences h_l: ((T_q+1)*B, H) bf16, box ROWS x 64
@@ -145,26 +63,9 @@ struct P {
   long long* trace;                // debug: 8 %globaltimer stamps per step written by CTA 0 (mmqg_debug_dec_trace), nullable
 };
 
-__device__ __forceinline__ long long gtime() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 __device__ __forceinline__ uint32_t* flag_h(const P& p, int g, int l, int slab) { return p.flags + (size_t)g * p.fstride + l * (p.Tq + 1) + slab; }
 __device__ __forceinline__ uint32_t* flag_s(const P& p, int g, int ta) { return p.flags + (size_t)g * p.fstride + MAXL * (p.Tq + 1) + ta; }
 __device__ __forceinline__ uint32_t* flag_c(const P& p, int g, int ta) { return p.flags + (size_t)g * p.fstride + MAXL * (p.Tq + 1) + p.Tq + ta; }
-
-// chunks of one sample's attention memories, in the order loader and workers both walk them:
-// text rows, audio rows, video rows
-struct Chunker {
-  int cr_t, cr_a, cr_v, n_t, n_a, n_v;
-  __device__ Chunker(const P& p) {
-    cr_t = ASLOT / (p.H * 2); cr_a = ASLOT / (p.H_a * 4); cr_v = ASLOT / (p.H_v * 2);
-    n_t = (p.T_t + cr_t - 1) / cr_t; n_a = (p.T_v + cr_a - 1) / cr_a; n_v = (p.T_v + cr_v - 1) / cr_v;
-  }
-  __device__ int count() const { return n_t + n_a + n_v; }
-};
 
 template <int ROWS>
 __global__ void __launch_bounds__(224, 1)
@@ -300,7 +201,7 @@ dec_seq_fwd_kernel(const __grid_constant__ Maps maps, const P p) {
   } else if (warp == 6) {
     // ---------------- loader of the attention memories (they do not change during the decode) ----------------
     if (elect_one()) {
-      const Chunker ck(p);
+      const Chunker ck(p.H, p.H_a, p.H_v, p.T_t, p.T_v);
       int i = 0;
       for (int t = 0; t < p.T; ++t) {
         for (int b = row_g0 + s; b < row_g0 + rows_grp; b += p.n_slices) {
@@ -334,7 +235,7 @@ dec_seq_fwd_kernel(const __grid_constant__ Maps maps, const P p) {
     const int rows_valid = max(0, min(32, B - m0w));
     const int j0 = s * 16;
     float* stg = stg_all + warp * STG_WARP;
-    const Chunker ck(p);
+    const Chunker ck(p.H, p.H_a, p.H_v, p.T_t, p.T_v);
     int ai = 0;                                      // attention ring position
     const int off_a = p.TM, off_v = p.TM + p.AM;     // slots: [text | audio | video]
     long long* tr = (p.trace && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;

@@ -58,6 +58,11 @@ struct Ws16 {
   // persistent decoder-step kernel (dec_persist.cu): decoder weights in 16-unit gate-slice row order, arrival counters
   b16 *wdp_hh[MMQG_MAX_LAYERS], *wdp_in[MMQG_MAX_LAYERS];
   uint32_t* flags_dec;
+  // persistent decoder BPTT kernel (dec_persist_bwd.cu): transposed decoder weights (W_hh_l^T, W_ih_l^T / context columns of
+  // W_ih_l0^T: rows = output column, K = gate index), transposed state columns of the attention Linears, arrival counters
+  b16 *wdpb[MMQG_MAX_LAYERS], *wahT;
+  uint32_t* flags_decb;
+  int Spp;
   // fused loss head (vocab_nll.cu): per-tile softmax partials, per-row lse / gradient scale / target logit, split-K scratch of dH
   float *stat_a, *stat_b, *lse, *rscale, *tgt_logit, *dh_part;
   int Sp, Ep, Vp, Rc, Rs;     // Rc: rows of one bf16 d-logits chunk; Rs: rows of the fp32 logits scratch of the sampling decode
@@ -154,6 +159,10 @@ static Ws16 carve16(const mmqg_dims& d, int T_q, void* base) {
   w.shift_t = c.take<int>(B); w.shift_v = c.take<int>(B); w.row_w = c.take<float>(R);
   for (int l = 0; l < d.L; ++l) { w.wdp_hh[l] = c.take<b16>(G * H); w.wdp_in[l] = c.take<b16>(G * (l == 0 ? C : H)); }
   w.flags_dec = c.take<uint32_t>((size_t)((B + 63) / 64) * (3 * (T_q + 1) + 2 * T_q) + 64);
+  w.Spp = (w.Sp + 63) / 64 * 64;
+  for (int l = 0; l < d.L; ++l) w.wdpb[l] = c.take<b16>(dec_bwd_weight_rows(d.H, l) * G);
+  w.wahT = c.take<b16>(H * (size_t)w.Spp);
+  w.flags_decb = c.take<uint32_t>((size_t)((B + 63) / 64) * 5 * T_q + 64);
   w.m_txt16 = c.take<b16>(B * d.TM * H);
   w.m_vid16 = c.take<b16>(B * d.AM * Hv);
   w.bytes = align_up(c.off, 256);
@@ -311,6 +320,17 @@ static bool dec_persist_enabled(const mmqg_dims& d, const Ws16& w) {
   return dec_persist_ok(dec_shape(d, w));
 }
 
+// Their BPTT has a persistent kernel too (dec_persist_bwd.cu: one launch for all T_q steps, 187 instead of 348 launches
+// per train step at cfg-2).  It is selected with MMQG_DEC_BWD_PERSIST=1 and is NOT the default: measured on B200 at
+// cfg-2 it runs a step in 50 us against 68 us for the launch-per-phase loop, but it holds 128 SMs, so the loss-head
+// backward (0.45 ms when it has the GPU to itself) can no longer run beside it -- 1.47 ms against 1.37 ms for
+// loss-head backward + decoder BPTT together, 5.60 against 5.44 ms per train step.
+static bool dec_bwd_persist_enabled(const mmqg_dims& d, const Ws16& w) {
+  const char* e = getenv("MMQG_DEC_BWD_PERSIST");      // read per call: tests switch it inside one process
+  if (!(e && e[0] == '1')) return false;
+  return dec_persist_enabled(d, w) && dec_bwd_persist_ok(dec_shape(d, w));
+}
+
 // With the persistent decoder kernel holding 128 SMs, the loss head cannot hide under the decoder's forward steps
 // any more.  Its forward half (the loss) then runs right behind the decoder, and its backward half (d logits -> dH,
 // dW_out, db_out) is DEFERRED to the backward call, where it runs group by group, last steps first, on its own stream
@@ -367,6 +387,12 @@ static int pack_weights_rest(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w,
       MMQG_TRY(pack_whh(P.dec_w_hh[l], w.wdp_hh[l], nullptr, H, st));
       MMQG_TRY(pack_rows_gate16(l == 0 ? P.dec_w_ih[0] + E : P.dec_w_ih[l], l == 0 ? X0 : H, l == 0 ? C : H, l == 0 ? C : H, w.wdp_in[l], H, st));
     }
+  if (dec_bwd_persist_enabled(d, w) && !g_fwd_only) {
+    for (int l = 0; l < d.L; ++l)
+      MMQG_TRY(pack_decb_weights(P.dec_w_hh[l], H, l == 0 ? P.dec_w_ih[0] + E : P.dec_w_ih[l], l == 0 ? X0 : H, l == 0 ? C : H, l, w.wdpb[l], st));
+    MMQG_CUDA(cudaMemsetAsync(w.wahT, 0, sizeof(b16) * (size_t)H * w.Spp, st));
+    for (int i = 0; i < 3; ++i) MMQG_TRY(transpose_f32_bf16(P.attn_w[i] + E, Q, len[i], H, w.wahT + off[i], w.Spp, st));
+  }
   if (persist_video(d)) MMQG_TRY(pack_rec(P.vid_w_hh, w.wvp_f, w.wvp_b, d.B, Hv, st));
   if (persist_text(d))      // BPTT layouts of the text layers: not needed before the backward pass
     for (int l = 0; l < d.L; ++l) MMQG_TRY(pack_rec(P.text_w_hh[l], nullptr, w.wtp_b[l], d.B, H, st));
@@ -940,6 +966,36 @@ struct Bwd16 {
     return n;
   }
 
+  // decoder BPTT inside the persistent kernel: one launch for all T_q steps (dec_persist_bwd.cu)
+  bool dec_pers() const { return dec_bwd_persist_enabled(d, w); }
+  int dec_loop_persist(cudaStream_t st) {
+    AttnShape as = attn_shape16(d, w);
+    MMQG_CUDA(cudaMemsetAsync(w.ds_all, 0, sizeof(float) * (size_t)R * Sp, st));       // padding columns stay zero
+    MMQG_CUDA(cudaMemsetAsync(w.ds16, 0, sizeof(b16) * (size_t)R * Sp, st));
+    DecPersistBwdArgs a{};
+    a.shape = dec_shape(d, w);
+    a.Tq = d.T_q; a.attn_all = w.attn_all; a.ds_all = w.ds_all; a.ds16 = w.ds16; a.dctx_all = w.dctx_all; a.dhtop = w.dhtop;
+    for (int l = 0; l < L; ++l) {
+      a.acts[l] = w.acts_dec[l]; a.cs[l] = w.cs_dec[l]; a.dg[l] = w.dg_dec[l]; a.dc[l] = w.dc[l]; a.dh_rec[l] = w.dh_rec[l];
+      a.wT[l] = w.wdpb[l];
+    }
+    a.wahT = w.wahT; a.Spp = w.Spp;
+    a.m_txt16 = w.m_txt16; a.m_vid16 = w.m_vid16; a.m_aud = w.m_aud; a.flags = w.flags_decb;
+    a.drop_p = g_drop_p; a.seed = g_drop_seed; a.ctr = g_drop_ctr; a.sid0 = kSidDec;
+    MMQG_CUDA(cudaMemsetAsync(w.flags_decb, 0, sizeof(uint32_t) * dec_bwd_persist_flag_words(a.shape, d.T_q), st));
+    {
+      PdlScope no_pdl(false);
+      MMQG_TRY(dec_seq_bwd_persist(a, 0, d.T_q, st));
+    }
+    return attn_dmem(w.attn_all, Sp, w.dctx_all, C, w.dm_txt, w.dm_vid, d.T_q, as, st);
+  }
+  // d loss / d (final encoder state of layer l) = the decoder's gradient w.r.t. its initial state (train.py:169) plus, for
+  // the top layer, the step-0 attention query: split-K partials of the launch-per-phase loop, one full sum from the kernel
+  int sum_dh_last(int l, float* out, cudaStream_t s) {
+    if (dec_pers()) return sum_partials(w.dh_rec[l], 1, nullptr, 0, ps, out, B * H, s);
+    return sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, out, B * H, s);
+  }
+
   // decoder BPTT, reverse of decoder.py:74-107 for t = T_q-1 .. 0
   int dec_loop(cudaStream_t st, const int* lh_lo = nullptr, int lh_n = 0) {
     AttnShape as = attn_shape16(d, w);
@@ -1078,7 +1134,7 @@ struct Bwd16 {
     if (persist_text(d)) {
       // d loss / d h_final = the decoder's gradient w.r.t. its initial state (train.py:169) plus,
       // for the top layer, the step-0 attention query; d loss / d c_final sits in dc[l].
-      MMQG_TRY(sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, w.dh_last, B * H, st));
+      MMQG_TRY(sum_dh_last(l, w.dh_last, st));
       const float* ext = l == L - 1 ? w.dm_txt : w.dx_text;
       const long long ts = l == L - 1 ? H : (long long)B * H, ld = l == L - 1 ? (long long)d.TM * H : H;
       MMQG_TRY(rec_bwd(w.acts_text[l], w.cs_text[l], w.dg_text[l], w.wtp_b[l], ext, ts, ld, w.dh_last, w.dc[l], w.flags,
@@ -1150,8 +1206,7 @@ struct Bwd16 {
           }
         }
         if (tail)   // d loss / d h_final of this layer (decoder initial state, + step-0 attention query on top)
-          MMQG_TRY(sum_partials(w.dh_rec[l], kSplitB, l == L - 1 ? w.dq_h : nullptr, l == L - 1 ? kSplitB : 0, ps, w.dh_last_l[l],
-                                B * H, s));
+          MMQG_TRY(sum_dh_last(l, w.dh_last_l[l], s));
         const float* ext = l == L - 1 ? w.dm_txt + (size_t)t0 * H : w.dx_text + (size_t)t0 * B * H;
         const long long ts = l == L - 1 ? H : (long long)B * H, ld = l == L - 1 ? (long long)d.TM * H : H;
         tl_ktag = l * 16 + c;
@@ -1216,7 +1271,8 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   const bool lh_def = lh_deferred(d, w);
   if (phase == 1) {
     if (lh_def) MMQG_TRY(b.loss_head_bwd(0, d.T_q, true, st));      // phase-wise callers: serially, in front of the BPTT
-    MMQG_TRY(b.dec_loop(st));
+    if (b.dec_pers()) MMQG_TRY(b.dec_loop_persist(st));
+    else MMQG_TRY(b.dec_loop(st));
     return b.dec_hoisted(st);
   }
   if (phase == 2) return b.video(st);
@@ -1242,7 +1298,12 @@ static int train_backward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, con
   MMQG_TRY(g_aux.init());
   cudaStream_t ax = g_aux.s[AuxStream::NS - 1];
   mark(6, st);
-  if (lh_def) {
+  if (b.dec_pers()) {
+    // the persistent BPTT kernel holds 128 SMs: the loss-head backward (0.26 ms on the whole GPU) runs in front of it
+    if (lh_def) MMQG_TRY(b.loss_head_bwd(0, d.T_q, true, st));
+    if (ready && ready[0]) MMQG_CUDA(cudaEventRecord(ready[0], st));
+    MMQG_TRY(b.dec_loop_persist(st));
+  } else if (lh_def) {
     // loss-head backward on its own stream under the BPTT loop, one event per group
     cudaStream_t lh = g_aux.s[AuxStream::NS - 2];
     int lo[kMaxLhGroups];

@@ -144,6 +144,27 @@ int dec_persist_waves(const DecPersistShape& s);     // launches per call (1 = a
 size_t dec_persist_flag_words(const DecPersistShape& s, int Tq);
 int pack_rows_gate16(const float* w, int ld, int K, int Kp, void* out, int H, cudaStream_t st);
 int dec_seq_fwd_persist(const DecPersistArgs& a, int t0, int T, cudaStream_t st);
+int dec_persist_rows(int B, int H);                  // batch rows per group (64 / 128), 0 = shape not supported
+// persistent decoder-step kernel, backward through time (dec_persist_bwd.cu)
+struct DecPersistBwdArgs {
+  DecPersistShape shape;
+  int Tq;
+  const float* attn_all; float* ds_all; void* ds16; float* dctx_all;     // (Tq*B, Sp) fp32 in, (Tq*B, Sp) fp32 / bf16 out, (Tq*B, C) fp32 out
+  const float* dhtop;                                                   // (Tq*B, H) fp32 from the loss head
+  const float* acts[3]; const float* cs[3]; void* dg[3];                // saved activations / cell states; dG_l (Tq*B, 4H) bf16 out
+  float* dc[3]; float* dh_rec[3];                                       // (B, H) fp32 state handed over between calls / to the encoders
+  const void* wT[3];                                                    // packed transposed bf16 weights per layer (pack_decb_weights)
+  const void* wahT; int Spp;                                            // attention Linears, state columns, transposed: (H, Spp), Spp % 64 == 0
+  const void* m_txt16; const void* m_vid16; const float* m_aud;
+  uint32_t* flags;                                                      // dec_bwd_persist_flag_words() words, zeroed before the first call
+  float drop_p; unsigned long long seed; const unsigned long long* ctr; int sid0;
+};
+bool dec_bwd_persist_ok(const DecPersistShape& s);
+size_t dec_bwd_persist_flag_words(const DecPersistShape& s, int Tq);
+int dec_seq_bwd_persist(const DecPersistBwdArgs& a, int t_lo, int t_hi, cudaStream_t st);
+int transpose_f32_bf16(const float* src, long long ld_src, int R, int Cc, void* dst, long long ld_dst, cudaStream_t st);
+size_t dec_bwd_weight_rows(int H, int l);
+int pack_decb_weights(const float* w_hh, int H, const float* w_in, long long ld_in, int n_in_total, int l, void* out, cudaStream_t st);
 // bf16-mode orchestration (engine_bf16.cu)
 size_t train_workspace_bytes_bf16(const mmqg_dims& d, int T_q);
 int check_dims_bf16(const mmqg_dims& d);

@@ -207,9 +207,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         if (t > 0) {
           mbar_wait(&mma_done, (t - 1) & 1);                       // sA is free again
           const uint32_t* f = p.flags + (size_t)t * p.n_mt + mt;    // h_{t-1} complete for this m-tile?
-          // acquire load (measured 0.4 us per step cheaper than a relaxed poll + fence.acq_rel.gpu, which costs a MEMBAR)
-          while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
-          }
+          // relaxed poll + one acquire load (measured 0.4 us per step cheaper than a poll + fence.acq_rel.gpu, which costs a MEMBAR)
+          wait_counter_acquire(f, (uint32_t)p.n_slices);
           fence_proxy_async();      // hands the ordering of the counter observation to the async proxy (TMA)
         }
         if (tr) { const long long g = gtime(); atomicMin((unsigned long long*)&tr[t * 8 + 0], (unsigned long long)g); atomicMax((unsigned long long*)&tr[t * 8 + 1], (unsigned long long)g); }
@@ -416,8 +415,7 @@ lstm_seq_fwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
           if (t > 0) {
             const uint32_t* f = p.flags + (size_t)t * p.n_mt + mt;    // h_{t-1} complete for this m-tile?
             if (trp) trp[t * 16 + q * 8 + 7] = gtime();
-            while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
-            }
+            wait_counter_acquire(f, (uint32_t)p.n_slices);
             fence_proxy_async();
           }
           if (trp) trp[t * 16 + q * 8 + 0] = gtime();
@@ -602,6 +600,7 @@ struct LstmBwdP {
   long long* ktrace; int ktag;
   DropSpec dr;          // dr.p > 0: dh_ext is the gradient w.r.t. the DROPPED h_t -> multiplied by the mask here
   LenSpec len;
+  long long* trace;     // debug: per-step %globaltimer stamps of CTA (0,0) of lstm_seq_bwd4_kernel, 16 per step (tools/trace_lstm_bwd.py)
 };
 
 static constexpr int BWD_STAGES = 6;     // 144 KB in flight: the streaming rate is ring bytes / TMA round trip
@@ -642,8 +641,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       for (int t = T - 1 - (p.has_next ? 0 : 1); t >= 0; --t) {   // step t consumes dG_{t+1}
         if (t + 1 < T) {                           // slab T comes from an earlier launch: already complete
           const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
-          while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
-          }
+          wait_counter_acquire(f, (uint32_t)p.n_slices);
           fence_proxy_async();
         }
         for (int kb = 0; kb < p.NKB; ++kb, ++i) {
@@ -894,12 +892,19 @@ lstm_seq_bwd4_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
       mbar_expect_tx(&w_full, KB * 8192);
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * 8192, &tmW, &w_full, rank * H + kb * 64, unit0);
       int i = 0;
+      long long* trp = (p.trace && slice == 0 && mt == 0) ? p.trace : nullptr;
       for (int t = t_first; t >= 0; --t) {          // step t consumes dG_{t+1}
+        if (trp) trp[t * 16 + 0] = gtime();
         if (t + 1 < T) {                            // slab T comes from an earlier launch: already complete
           const uint32_t* f = p.flags + (size_t)(t + 1) * p.n_mt + mt;
-          while (ld_acquire_gpu(f) < (uint32_t)p.n_slices) {
-          }
+          wait_counter_acquire(f, (uint32_t)p.n_slices);
           fence_proxy_async();
+        }
+        if (trp) trp[t * 16 + 1] = gtime();
+        if (p.trace && mt == 0) {      // spread over the CTAs of m-tile 0
+          const unsigned long long g = (unsigned long long)gtime();
+          atomicMax((unsigned long long*)&p.trace[t * 16 + 12], g);
+          atomicMin((unsigned long long*)&p.trace[t * 16 + 13], g);
         }
         for (int kb = 0; kb < KB; ++kb, ++i) {
           const int s = i % STAGES, ph = (i / STAGES) & 1;
@@ -907,6 +912,7 @@ lstm_seq_bwd4_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
           mbar_expect_tx(&full[s], 16384);
           tma_load_2d(sA + s * 16384, &tmG, &full[s], rank * H + kb * 64, (t + 1) * B + mt * 128);
         }
+        if (trp) trp[t * 16 + 2] = gtime();
       }
     }
   } else if (warp == 5) {
@@ -957,6 +963,7 @@ lstm_seq_bwd4_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     float dc[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) dc[u] = (p.dc_last && valid) ? p.dc_last[(size_t)m * H + j0 + u] : 0.f;
+    long long* tre = (p.trace && row == 0 && slice == 0 && mt == 0) ? p.trace : nullptr;
     int it = 0;
     for (int t = T - 1; t >= 0; --t) {
       float4 a4[4][4], cn4[4], cp4[4], ex4[4];
@@ -992,7 +999,9 @@ lstm_seq_bwd4_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         for (int u = 0; u < 16; ++u) dh[u] = (p.dh_last && valid) ? p.dh_last[(size_t)m * H + j0 + u] : 0.f;
       } else {
         const int xb = it & 1;
+        if (tre) tre[t * 16 + 3] = gtime();
         mbar_wait(&mma_done, it & 1);
+        if (tre) tre[t * 16 + 4] = gtime();
         tc_fence_after_sync();
         float part[64];
 #pragma unroll
@@ -1014,7 +1023,9 @@ lstm_seq_bwd4_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                         part[16 * rr + 4 * c + 2], part[16 * rr + 4 * c + 3]);
         }
         // receive the three peers' partials of this warp's 32 rows
+        if (tre) tre[t * 16 + 5] = gtime();
         mbar_wait_cluster(&xfull[xb][warp], (uint32_t)(it >> 1) & 1u);
+        if (tre) tre[t * 16 + 6] = gtime();
 #pragma unroll
         for (int u = 0; u < 16; ++u) dh[u] = 0.f;
 #pragma unroll
@@ -1066,10 +1077,18 @@ lstm_seq_bwd4_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
           row_bf16_to_global(reinterpret_cast<uint32_t*>(stg), lane, w8, dbase + g * H, G, rows_valid);
         }
       }
+      if (tre) tre[t * 16 + 7] = gtime();
       epi_bar_sync();
       if (row == 0) {
+        if (tre) tre[t * 16 + 8] = gtime();
         __threadfence();
         red_relaxed_gpu_add(p.flags + (size_t)t * p.n_mt + mt, 1u);
+        if (tre) tre[t * 16 + 9] = gtime();
+        if (p.trace && mt == 0) {
+          const unsigned long long g = (unsigned long long)gtime();
+          atomicMax((unsigned long long*)&p.trace[t * 16 + 10], g);
+          atomicMin((unsigned long long*)&p.trace[t * 16 + 11], g);
+        }
       }
     }
     if (p.dc_out) {
@@ -1249,8 +1268,11 @@ static cudaError_t launch_coop_cluster4(Kern kern, dim3 grid, int threads, size_
   attr[1].val.clusterDim.x = 4;
   attr[1].val.clusterDim.y = 1;
   attr[1].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  // Profiling aid: Nsight Compute refuses a launch that is both cooperative and clustered (LaunchFailed).  Under ncu the
+  // kernels of a process are serialised anyway, so MMQG_NCU=1 drops the cooperative attribute (attr[0]) for its runs only.
+  static const bool ncu = []() { const char* e = getenv("MMQG_NCU"); return e && e[0] == '1'; }();
+  cfg.attrs = ncu ? attr + 1 : attr;
+  cfg.numAttrs = ncu ? 1 : 2;
   return cudaLaunchKernelEx(&cfg, kern, m0, m1, p);
 }
 
@@ -1295,7 +1317,7 @@ int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const voi
                          int T, int B, int H, int has_next, float* dc_out, cudaStream_t st, DropSpec dr, bool zero_flags, LenSpec len) {
   MMQG_REQUIRE(lstm_persist_ok(B, H), "lstm_seq_bwd_persist: shape B=%d H=%d not supported", B, H);
   LstmBwdP p{acts, cs, reinterpret_cast<bf16*>(dg), dh_ext, ext_ts, ext_ld, dh_last, dc_last, flags,
-             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64, has_next, dc_out, g_ktrace, 1000 + tl_ktag, dr, len};
+             T, B, H, ceil_div(B, 128), H / 16, 4 * H / 64, has_next, dc_out, g_ktrace, 1000 + tl_ktag, dr, len, g_lstm_trace};
   if (bwd4_state(H) == 1) {
     CUtensorMap tmW4, tmG4;
     MMQG_TRY(make_tmap_bf16_2d(&tmW4, wp_bwd, H, 4 * (uint64_t)H, 4 * (uint64_t)H, 64, 64));

@@ -148,6 +148,17 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Wait until an arrival counter reaches `target`, then acquire it.  The poll itself is a RELAXED load: an acquire load
+// costs a CCTL.IVALL (L1 invalidate, which shares the array with shared memory) per iteration and a fence.acq_rel a
+// MEMBAR; one acquire load after the counter has been seen synchronises with the writers' release pattern
+// (fence + red.add) just the same -- the counter only grows.
+__device__ __forceinline__ void wait_counter_acquire(const uint32_t* p, uint32_t target) {
+  uint32_t v;
+  do {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  } while (v < target);
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_relaxed_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
