@@ -339,6 +339,12 @@ int mmqg_vocab_nll_bwd(const void* h_bf16, const void* w_bf16, const float* bias
 int mmqg_decode_step_argmax(const void* h_bf16, const void* w_bf16, const float* bias, int R, int V, int H, void* workspace,
                             size_t workspace_bytes, int64_t* tokens, long long tok_stride, void* stream);
 
+/* Gradient exchange in bf16 (multi-GPU; the reference has no parallelism): a flat fp32 gradient
+ * bucket is rounded to bf16 before the NCCL all-reduce and widened back afterwards, halving the bytes on NVLink.
+ * pack: dst[i] = bf16(src[i]);  unpack: dst[i] = float(src[i]).  n elements, any alignment of n. */
+int mmqg_pack_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+int mmqg_unpack_bf16(const void* src_bf16, float* dst, long long n, void* stream);
+
 /* out(n) = sum_m X(m,n)  (bias gradients). */
 int mmqg_colsum(const float* X, int ldx, float* out, int M, int N, float beta, void* stream);
 

@@ -261,23 +261,10 @@ static bool persist_enabled() {
   }
   return v != 0;
 }
-static bool cluster_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    // Off by default: measured on B200 at B=256, H=512 the cluster variant (16-CTA clusters, TMA
-    // multicast, 4-slot ring recycled cluster-wide) runs 7.7 / 16 us per step forward / backward
-    // against 6.0 / 9.7 us for the global-flag kernels -- the cluster-wide slot round trip caps
-    // the streaming rate at ring_bytes / latency.  MMQG_CLUSTER=1 selects it.
-    const char* e = getenv("MMQG_CLUSTER");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
-// 2 = cluster kernels (barrier.cluster + TMA multicast), 1 = global-flag persistent kernels, 0 = per-step launches
+// 1 = persistent recurrent kernels (global arrival counters), 0 = per-step launches
 static thread_local bool g_fwd_only = false;      // greedy decode: only the forward kernels (which cover twice the batch rows) are needed
 static int persist_kind(int B, int H) {
   if (!persist_enabled()) return 0;
-  if (cluster_enabled() && lstm_cluster_ok(B, H)) return 2;
   return (g_fwd_only ? lstm_persist_fwd_ok(B, H) : lstm_persist_ok(B, H)) ? 1 : 0;
 }
 static bool persist_text(const mmqg_dims& d) { return persist_kind(d.B, d.H) != 0; }
@@ -285,27 +272,16 @@ static bool persist_video(const mmqg_dims& d) { return persist_kind(d.B, d.H_v) 
 // packed W_hh of a persistent layer: the forward layout is needed at once, the backward (transposed)
 // layout only by the BPTT -- either may be null
 static int pack_rec(const float* w_hh, void* fwd, void* bwd, int B, int H, cudaStream_t st) {
-  if (persist_kind(B, H) == 2) {
-    if (fwd) MMQG_TRY(pack_whh_cluster(w_hh, fwd, H, st));
-    return bwd ? pack_whh(w_hh, nullptr, bwd, H, st) : 0;
-  }
+  (void)B;
   return pack_whh(w_hh, fwd, bwd, H, st);
 }
 static int rec_fwd(float* gates, float* cs, void* hs, const void* wp, float* mem, long long mem_ld, uint32_t* flags, int T, int B,
                    int H, cudaStream_t st, LenSpec len = LenSpec()) {
-  if (persist_kind(B, H) == 2) {
-    MMQG_REQUIRE(!len.shift, "variable-length batches are not supported by the cluster kernels (unset MMQG_CLUSTER)");
-    return lstm_seq_fwd_cluster(gates, cs, hs, wp, mem, mem_ld, T, B, H, st);
-  }
   return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, nullptr, mem_ld, flags, T, B, H, 0, st, DropSpec(), true, len);
 }
 static int rec_bwd(const float* acts, const float* cs, void* dg, const void* wp, const float* ext, long long ts, long long ld,
                    const float* dh_last, const float* dc_last, uint32_t* flags, int T, int B, int H, cudaStream_t st,
                    LenSpec len = LenSpec()) {
-  if (persist_kind(B, H) == 2) {
-    MMQG_REQUIRE(!len.shift, "variable-length batches are not supported by the cluster kernels (unset MMQG_CLUSTER)");
-    return lstm_seq_bwd_cluster(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, T, B, H, st);
-  }
   return lstm_seq_bwd_persist(acts, cs, dg, wp, ext, ts, ld, dh_last, dc_last, flags, T, B, H, 0, nullptr, st, DropSpec(), true, len);
 }
 
@@ -717,10 +693,9 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
   int lh_done = 0;      // steps whose loss head has been issued
   PdlScope pdl_scope(pdl_enabled());      // the dependent launches below overlap prologue and tail
   L2WindowScope l2_scope(w.m_txt16, attn_l2_window(d, w));     // attention memories stay in L2 across the T_q steps
-  // MMQG_STEP_FUSE: 0 = product + cell kernel, 1 = one fused launch (lstm_step_tc.cu), 2 = split-K product + summing cell kernel
+  // MMQG_STEP_FUSE (launch-per-phase loop only): 2 = split-K product + summing cell kernel (default), 0 = product + cell kernel
   static const int step_mode_env = []() { const char* e = getenv("MMQG_STEP_FUSE"); return e ? atoi(e) : 2; }();
   const int step_mode = step_mode_env;
-  const bool step_fused = step_mode == 1 && lstm_step_tc_ok(H, G, H, H, H, G);
   const bool dec_persist = dec_persist_enabled(d, w);
   DecPersistArgs dpa{};
   int seg_start = 0;
@@ -775,11 +750,6 @@ static int train_forward_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
       float* c_prev = w.cs_dec[l] + (size_t)t * B * H;
       float* c_new = w.cs_dec[l] + (size_t)(t + 1) * B * H;
       b16* h_new = w.hs_dec[l] + (size_t)(t + 1) * B * H;
-      if (step_fused) {      // GEMM + cell update in one launch; layer 0 adds the hoisted embedding product (in acts)
-        MMQG_TRY(lstm_step_tc(xin, Kin, Kin, w.wd_cat[l] + H, Nl, hprev, H, w.wd_cat[l], Nl, l == 0 ? nullptr : w.bsum_dec[l],
-                              l == 0 ? acts : nullptr, G, acts, G, c_prev, H, c_new, H, h_new, H, B, H, dr, st));
-        continue;
-      }
       if (step_mode == 2) {  // split-K over twice as many CTAs (the product is bound by per-SM operand ingest); the
                              // cell kernel sums the partials, the bias and (layer 0) the hoisted embedding product
         MMQG_TRY(Tc(xin, Kin, false, w.wd_cat[l] + H, Nl, false, B, G, Kin, w.gpart, G).second(hprev, H, w.wd_cat[l], Nl, H)

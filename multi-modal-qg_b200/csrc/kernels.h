@@ -77,11 +77,6 @@ int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int
                             const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1,
                             long long s1, const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, void* dg,
                             int lddg, int B, int H, cudaStream_t st, DropSpec dr = DropSpec());
-// one decoder LSTM layer step, GEMM + cell update in one launch (lstm_step_tc.cu)
-bool lstm_step_tc_ok(int H, int ldg, int ldc, int ldh, int ldcp, int ldpre);
-int lstm_step_tc(const void* X, int ldx, int K1, const void* W_in, int ldw1, const void* Hprev, int ldhp, const void* W_hh,
-                 int ldw2, const float* bias, const float* pre, int ldpre, float* acts, int ldg, const float* c_prev, int ldcp,
-                 float* c_out, int ldc, void* h_out, int ldh, int B, int H, DropSpec dr, cudaStream_t st);
 int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
 int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, const unsigned long long* ctr, int sid,
                  unsigned long long base, float p, cudaStream_t st);
@@ -119,13 +114,6 @@ int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const voi
                          long long ext_ts, long long ext_ld, const float* dh_last, const float* dc_last, uint32_t* flags,
                          int T, int B, int H, int has_next, float* dc_out, cudaStream_t st, DropSpec dr = DropSpec(),
                          bool zero_flags = true, LenSpec len = LenSpec());
-// cluster variant (lstm_cluster.cu): cluster barrier + TMA multicast instead of global flags
-bool lstm_cluster_ok(int B, int H);
-int pack_whh_cluster(const float* w_hh, void* fwd_packed, int H, cudaStream_t st);
-int lstm_seq_fwd_cluster(float* gates, float* cs, void* hs, const void* wp_fwd32, float* mem, long long mem_ld, int T, int B,
-                         int H, cudaStream_t st);
-int lstm_seq_bwd_cluster(const float* acts, const float* cs, void* dg, const void* wp_bwd, const float* dh_ext, long long ext_ts,
-                         long long ext_ld, const float* dh_last, const float* dc_last, int T, int B, int H, cudaStream_t st);
 // persistent decoder-step kernel, forward (dec_persist.cu)
 struct DecPersistShape { int B, H, C, Sp, TM, AM, T_t, T_v, H_a, H_v, L; };
 struct DecPersistArgs {

@@ -416,3 +416,53 @@ int nll_rows_bf16(const float* logits, int ldl, const int64_t* targets, float* n
 extern "C" int mmqg_dropout_mask(float* out, long long n, unsigned long long seed, int sid, float p, void* stream) {
   return mmqg::dropout_mask(out, n, seed, sid, p, mmqg::as_stream(stream));
 }
+
+// ---- bf16 gradient exchange: flat fp32 bucket <-> bf16 staging buffer (mmqg/dp.py) ---------------------------------
+namespace mmqg {
+__global__ void pack_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = u;
+  }
+  for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void unpack_bf16_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint2 u = reinterpret_cast<const uint2*>(src)[i];
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    reinterpret_cast<float4*>(dst)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+}  // namespace mmqg
+
+extern "C" int mmqg_pack_bf16(const float* src, void* dst_bf16, long long n, void* stream) {
+  using namespace mmqg;
+  MMQG_REQUIRE(src && dst_bf16 && n > 0, "pack_bf16: bad args");
+  MMQG_REQUIRE(((reinterpret_cast<uintptr_t>(src) & 15) | (reinterpret_cast<uintptr_t>(dst_bf16) & 7)) == 0, "pack_bf16: src must be 16-byte, dst 8-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int blocks = (int)std::min<long long>(148 * 8, (n / 4 + 255) / 256 + 1);
+  MMQG_PROBE(KC_EMBED, 0, 6.0 * n);
+  pack_bf16_kernel<<<blocks, 256, 0, st>>>(src, reinterpret_cast<bf16*>(dst_bf16), n);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mmqg_unpack_bf16(const void* src_bf16, float* dst, long long n, void* stream) {
+  using namespace mmqg;
+  MMQG_REQUIRE(src_bf16 && dst && n > 0, "unpack_bf16: bad args");
+  MMQG_REQUIRE(((reinterpret_cast<uintptr_t>(dst) & 15) | (reinterpret_cast<uintptr_t>(src_bf16) & 7)) == 0, "unpack_bf16: dst must be 16-byte, src 8-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int blocks = (int)std::min<long long>(148 * 8, (n / 4 + 255) / 256 + 1);
+  MMQG_PROBE(KC_EMBED, 0, 6.0 * n);
+  unpack_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(src_bf16), dst, n);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}

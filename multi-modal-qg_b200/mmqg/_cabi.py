@@ -86,6 +86,8 @@ SYMBOLS = {
     "mmqg_nll_rows": (_i, [_fp, _i, _fp, _ll, _fp, _i, _i, _f, _fp]),
     "mmqg_argmax_rows": (_i, [_fp, _i, _fp, _ll, _i, _i, _fp]),
     "mmqg_colsum": (_i, [_fp, _i, _fp, _i, _i, _f, _fp]),
+    "mmqg_pack_bf16": (_i, [_fp, _fp, _ll, _fp]),
+    "mmqg_unpack_bf16": (_i, [_fp, _fp, _ll, _fp]),
     "mmqg_lstm_seq_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mmqg_lstm_seq_fwd": (_i, [_fp] * 7 + [_i] * 4 + [_fp, _sz, _fp, _fp, _fp, _fp]),
     "mmqg_lstm_seq_bwd": (_i, [_fp] * 4 + [_i] * 4 + [_fp, _sz] + [_fp] * 8),

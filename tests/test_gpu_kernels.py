@@ -182,3 +182,19 @@ def test_embedding(ops):
     ops.embedding_scatter_add(demb, idx, dx)
     ref = torch.zeros_like(emb).double().index_add_(0, idx.reshape(-1), dx.double())
     assert rel(demb, ref) < 1e-6
+
+
+def test_pack_unpack_bf16_round_trip(ops):
+    """mmqg_pack_bf16 / mmqg_unpack_bf16 (bf16 gradient exchange): round-to-nearest-even like torch, tail elements included."""
+    from mmqg import _cabi
+    lib = _cabi.lib()
+    for n in (1, 3, 4, 1027, 1 << 20):
+        x = torch.randn(n, device="cuda") * 3
+        y = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+        z = torch.empty(n, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        _cabi.check(lib.mmqg_pack_bf16(x.data_ptr(), y.data_ptr(), n, st))
+        _cabi.check(lib.mmqg_unpack_bf16(y.data_ptr(), z.data_ptr(), n, st))
+        torch.cuda.synchronize()
+        assert torch.equal(y, x.to(torch.bfloat16))
+        assert torch.equal(z, x.to(torch.bfloat16).float())
