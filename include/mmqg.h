@@ -122,8 +122,8 @@ size_t mmqg_train_workspace_bytes(const mmqg_dims* d, int mode);
  * If want_grads != 0 the loss head also produces d loss/d h_top, d out_w, d out_b
  * (logits are produced and consumed in row chunks and never stored in full);
  * grad_scale multiplies every gradient (use B_local/B_global for data parallelism,
- * 1.0 otherwise).  dropout_p is torch.nn.LSTM's inter-layer dropout (0 disables; bf16 mode
- * only).  Its masks are a function of seed + the number of forward calls with dropout made on
+ * 1.0 otherwise).  dropout_p is torch.nn.LSTM's inter-layer dropout (0 disables; both modes).
+ * Its masks are a function of seed + the number of forward calls with dropout made on
  * this workspace so far: the FIRST 8 BYTES of the bf16-mode workspace are that call counter
  * (uint64; the caller zeroes the workspace once, everything else in it is scratch), advanced on
  * the device, so every step -- also every replay of a captured CUDA graph -- draws fresh masks

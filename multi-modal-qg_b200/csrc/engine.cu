@@ -33,6 +33,8 @@ struct Carver {
 };
 
 struct Ws {
+  unsigned long long* seed_ctr;       // FIRST 8 bytes of the workspace: dropout call counter (same convention as the bf16 mode)
+  float *xdrop_text[MMQG_MAX_LAYERS], *hdrop_dec[MMQG_MAX_LAYERS];   // dropped layer outputs = inputs of the next layer
   int64_t *idx_ctx, *idx_dec, *tgt_tm, *idx_cur;
   float *bsum_text[MMQG_MAX_LAYERS], *bsum_dec[MMQG_MAX_LAYERS], *bsum_vid;
   float *attn_w_cat, *attn_b_cat, *attn_dw_cat, *attn_db_cat;
@@ -66,6 +68,7 @@ static Ws carve(const mmqg_dims& d, int T_q, void* base) {
   const size_t Q = d.E + d.H, C = (size_t)d.H + d.H_a + d.H_v, X0 = d.E + C;
   const size_t R = (size_t)T_q * B;
   w.Rc = vocab_chunk_rows32((int)R, d.V);
+  w.seed_ctr = c.take<unsigned long long>(1);
   w.idx_ctx = c.take<int64_t>((size_t)d.T_t * B);
   w.idx_dec = c.take<int64_t>(R);
   w.tgt_tm = c.take<int64_t>(R);
@@ -112,6 +115,7 @@ static Ws carve(const mmqg_dims& d, int T_q, void* base) {
   w.dx_text = c.take<float>((size_t)d.T_t * B * (d.E > d.H ? d.E : d.H));
   w.dc_v = c.take<float>(B * d.H_v);
   w.xcat = c.take<float>(B * X0);
+  for (int l = 0; l + 1 < d.L; ++l) { w.xdrop_text[l] = c.take<float>((size_t)d.T_t * B * H); w.hdrop_dec[l] = c.take<float>(R * H); }
   w.bytes = align_up(c.off, 256);
   return w;
 }
@@ -155,6 +159,11 @@ struct GemmCall {
   int run(cudaStream_t st) { return gemm_f32(a, st); }
 };
 
+// inter-layer dropout of the current call (0 = off); stream ids as in engine_bf16.cu
+static thread_local float g32_drop_p = 0.f;
+static thread_local unsigned long long g32_drop_seed = 0;
+static const int kSidText32 = 10, kSidDec32 = 20;
+
 static AttnShape attn_shape(const mmqg_dims& d) { return AttnShape{d.B, d.TM, d.AM, d.H, d.H_a, d.H_v, d.T_t, d.T_v}; }
 
 // ----------------------------------------------------------------------------------------
@@ -184,7 +193,10 @@ static int encoder_forward(const mmqg_dims& d, const mmqg_tensors& P, const mmqg
   MMQG_TRY(embedding_gather(P.emb, w.idx_ctx, w.x0_text, d.E, d.T_t * B, d.E, d.V, st));
   for (int l = 0; l < d.L; ++l) {
     MMQG_TRY(add2(P.text_b_ih[l], P.text_b_hh[l], w.bsum_text[l], G, st));
-    const float* X = l == 0 ? w.x0_text : w.hs_text[l - 1] + (size_t)B * H;
+    if (l > 0 && g32_drop_p > 0.f)      // encoder.py:91: dropout between the LSTM layers (train mode)
+      MMQG_TRY(dropout_f32(w.hs_text[l - 1] + (size_t)B * H, w.xdrop_text[l - 1], (long long)d.T_t * B * H, g32_drop_seed, w.seed_ctr,
+                           kSidText32 + l - 1, 0, g32_drop_p, st));
+    const float* X = l == 0 ? w.x0_text : (g32_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);
     const int I = l == 0 ? d.E : H;
     MMQG_TRY(GemmCall(X, I, false, P.text_w_ih[l], I, true, d.T_t * B, G, I, w.acts_text[l], G)
                  .bias(w.bsum_text[l]).run(st));
@@ -257,7 +269,8 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   if (mode == MMQG_MODE_BF16)
     return train_forward_bf16(d, *params, *batch, workspace, workspace_bytes, loss_out, want_grads, grads, grad_scale,
                               dropout_p, seed, as_stream(stream));
-  MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: the fp32 parity mode runs without dropout (use the bf16 mode)", dropout_p);
+  g32_drop_p = dropout_p;
+  g32_drop_seed = seed;
   MMQG_REQUIRE(!batch->ctx_len && !batch->tgt_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
   Ws w = carve(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes)
@@ -267,6 +280,7 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   const int B = d.B, H = d.H, G = 4 * d.H, E = d.E, Q = d.E + d.H, C = d.H + d.H_a + d.H_v, X0 = E + C;
   const int R = d.T_q * B, Sp = w.S_pad;
 
+  if (dropout_p > 0.f) MMQG_TRY(bump_counter(w.seed_ctr, st));     // this call's masks: seed + (calls so far)
   MMQG_TRY(build_indices(batch->context, batch->target, w.idx_ctx, w.idx_dec, w.tgt_tm, B, d.T_t, d.T_q, st));
   MMQG_TRY(encoder_forward(d, P, *batch, w, st));
   MMQG_TRY(handoff_state(d, w, st));
@@ -292,11 +306,15 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
         MMQG_TRY(GemmCall(ctx, C, false, P.dec_w_ih[0] + E, X0, true, B, G, C, acts, G)
                      .second(hprev, H, P.dec_w_hh[0], H, H).accumulate(true).run(st));
       } else {
-        MMQG_TRY(GemmCall(w.hs_dec[l - 1] + (size_t)(t + 1) * B * H, H, false, P.dec_w_ih[l], H, true, B, G, H, acts, G)
+        const float* xin = g32_drop_p > 0.f ? w.hdrop_dec[l - 1] + (size_t)t * B * H : w.hs_dec[l - 1] + (size_t)(t + 1) * B * H;
+        MMQG_TRY(GemmCall(xin, H, false, P.dec_w_ih[l], H, true, B, G, H, acts, G)
                      .second(hprev, H, P.dec_w_hh[l], H, H).bias(w.bsum_dec[l]).run(st));
       }
       MMQG_TRY(lstm_pointwise_fwd(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
                                   w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st));
+      if (g32_drop_p > 0.f && l + 1 < d.L)      // decoder.py:69: dropout between the LSTM layers
+        MMQG_TRY(dropout_f32(w.hs_dec[l] + (size_t)(t + 1) * B * H, w.hdrop_dec[l] + (size_t)t * B * H, (long long)B * H, g32_drop_seed,
+                             w.seed_ctr, kSidDec32 + l, (unsigned long long)t * B * H, g32_drop_p, st));
     }
   }
   // loss head in row chunks (rows r = t*B + b of h_top)
@@ -361,7 +379,8 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   MMQG_REQUIRE(phase >= 0 && phase <= 3, "phase %d not in 0..3", phase);
   if (mode == MMQG_MODE_BF16)
     return train_backward_bf16(d, *params, *batch, workspace, workspace_bytes, *grads, phase, dropout_p, seed, as_stream(stream));
-  MMQG_REQUIRE(dropout_p == 0.f, "dropout_p=%g: the fp32 parity mode runs without dropout (use the bf16 mode)", dropout_p);
+  g32_drop_p = dropout_p;
+  g32_drop_seed = seed;
   MMQG_REQUIRE(!batch->ctx_len && !batch->tgt_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
   Ws w = carve(d, d.T_q, workspace);
   if (w.bytes > workspace_bytes)
@@ -397,6 +416,9 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
           if (!last) { dh1 = w.dq_h; n1 = kSplit; }
         } else {
           dh1 = w.dx_above; n1 = kSplit;
+          if (g32_drop_p > 0.f)      // dx_above is d/d(dropped h_l(t)): back through the mask of layer l's output
+            MMQG_TRY(dropout_scale_f32(w.dx_above, kSplit, ps, (long long)B * H, g32_drop_seed, w.seed_ctr, kSidDec32 + l,
+                                       (unsigned long long)t * B * H, g32_drop_p, st));
         }
         MMQG_TRY(lstm_pointwise_bwd(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
                                     dh0, H, kSplit, ps, dh1, H, n1, ps, dh2, H, w.dc[l], H, last ? 1 : 0, B, H, st));
@@ -418,7 +440,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
       const float* dG = w.acts_dec[l];
       MMQG_TRY(GemmCall(dG, G, true, w.hs_dec[l], H, false, G, H, R, Gd.dec_w_hh[l], H).run(st));
       if (l > 0) {
-        MMQG_TRY(GemmCall(dG, G, true, w.hs_dec[l - 1] + (size_t)B * H, H, false, G, H, R, Gd.dec_w_ih[l], H).run(st));
+        MMQG_TRY(GemmCall(dG, G, true, g32_drop_p > 0.f ? w.hdrop_dec[l - 1] : w.hs_dec[l - 1] + (size_t)B * H, H, false, G, H, R, Gd.dec_w_ih[l], H).run(st));
       } else {
         MMQG_TRY(GemmCall(dG, G, true, w.e_dec, E, false, G, E, R, Gd.dec_w_ih[0], X0).run(st));
         MMQG_TRY(GemmCall(dG, G, true, w.ctx_all, C, false, G, C, R, Gd.dec_w_ih[0] + E, X0).run(st));
@@ -475,6 +497,8 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   // ---- phase 3: text LSTM stack BPTT (encoder.py:95-100) + encoder-side embedding gradient ----
   for (int l = L - 1; l >= 0; --l) {
     const int I = l == 0 ? E : H;
+    if (g32_drop_p > 0.f && l < L - 1)   // dx_text holds d/d(dropped h_l): back through the mask
+      MMQG_TRY(dropout_scale_f32(w.dx_text, 1, 0, (long long)d.T_t * B * H, g32_drop_seed, w.seed_ctr, kSidText32 + l, 0, g32_drop_p, st));
     for (int t = d.T_t - 1; t >= 0; --t) {
       StepGemmScope step_scope;
       const bool last = t == d.T_t - 1;
@@ -492,7 +516,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
         MMQG_TRY(GemmCall(acts, G, false, P.text_w_hh[l], H, false, B, H, G, w.dh_rec_enc, H).split(kSplit, ps).run(st));
     }
     const float* dG = w.acts_text[l];
-    const float* X = l == 0 ? w.x0_text : w.hs_text[l - 1] + (size_t)B * H;
+    const float* X = l == 0 ? w.x0_text : (g32_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);
     MMQG_TRY(GemmCall(dG, G, true, X, I, false, G, I, d.T_t * B, Gd.text_w_ih[l], I).run(st));
     if (d.T_t > 1)
       MMQG_TRY(GemmCall(dG + (size_t)B * G, G, true, w.hs_text[l] + (size_t)B * H, H, false, G, H, (d.T_t - 1) * B,
@@ -534,6 +558,7 @@ static int decode_impl(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   if (mode == MMQG_MODE_BF16)
     return greedy_decode_bf16(d, *params, *batch, workspace, workspace_bytes, tokens_out, max_len, as_stream(stream), sample, seed);
   MMQG_REQUIRE(!batch->ctx_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
+  g32_drop_p = 0.f;      // decoding is eval mode: no dropout
   Ws w = carve(d, max_len, workspace);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);

@@ -80,6 +80,8 @@ int lstm_pointwise_bwd_bf16(const float* acts, int ldg, const float* c_prev, int
 int colsum_bf16(const void* X, int ldx, float* out, float* out2, int M, int N, float beta, cudaStream_t st);
 int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, const unsigned long long* ctr, int sid,
                  unsigned long long base, float p, cudaStream_t st);
+int dropout_f32(const float* x, float* y, long long n, unsigned long long seed, const unsigned long long* ctr, int sid,
+                unsigned long long base, float p, cudaStream_t st);
 int bump_counter(unsigned long long* ctr, cudaStream_t st);
 int dropout_scale_f32(float* x, int n_part, long long stride, long long n, unsigned long long seed, const unsigned long long* ctr, int sid, unsigned long long base,
                       float p, cudaStream_t st);

@@ -268,6 +268,13 @@ __global__ void dropout_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict
   if (i < n) y[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * drop_scale(seed + (ctr ? *ctr : 0ull), sid, base + i, p, inv_keep));
 }
 
+// fp32 twin of dropout_bf16 (fp32 parity mode): y = x * mask
+__global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, unsigned long long seed,
+                                   const unsigned long long* __restrict__ ctr, int sid, unsigned long long base, float p, float inv_keep) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * drop_scale(seed + (ctr ? *ctr : 0ull), sid, base + i, p, inv_keep);
+}
+
 // x[k*stride + i] *= mask(i) for k < n_part (gradient w.r.t. a dropped tensor, possibly split-K partials)
 __global__ void dropout_scale_f32_kernel(float* __restrict__ x, int n_part, long long stride, long long n, unsigned long long seed,
                                          const unsigned long long* __restrict__ ctr,
@@ -288,6 +295,13 @@ int dropout_bf16(const void* x, void* y, long long n, unsigned long long seed, c
   MMQG_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout_bf16: bad args");
   dropout_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), n, seed, ctr,
                                                                   sid, base, p, 1.0f / (1.0f - p));
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+int dropout_f32(const float* x, float* y, long long n, unsigned long long seed, const unsigned long long* ctr, int sid,
+                unsigned long long base, float p, cudaStream_t st) {
+  MMQG_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout_f32: bad args");
+  dropout_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n, seed, ctr, sid, base, p, 1.0f / (1.0f - p));
   MMQG_LAUNCH_CHECK();
   return 0;
 }

@@ -105,12 +105,21 @@ def test_bf16_dropout_fresh_masks_under_graph_replay(eng_mod):
     assert len(set(round(x, 5) for x in got)) == 3
 
 
-def test_fp32_mode_rejects_dropout(eng_mod):
-    from mmqg import _cabi
-    d = Dims(B=2, T_t=3, T_v=2, T_q=2, V=11, E=10, H=12, L=2, H_a=6, H_v=12, F_v=10, TM=4, AM=3)
-    eng = eng_mod.TrainEngine(d, make_params(d), mode="fp32", dropout_p=0.2)
-    with pytest.raises(_cabi.MmqgError):
-        eng.step(eng.to_device(make_batch(d)))
+def test_fp32_and_bf16_modes_draw_the_same_masks(eng_mod):
+    """Both modes apply the same counter-based inter-layer dropout masks (same seed, same call counter): their losses
+    with dropout agree to the bf16 bar, and differ from the dropout-free loss."""
+    d = Dims(B=8, T_t=9, T_v=3, T_q=5, V=203, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101)
+    params, batch = make_params(d, seed=5), make_batch(d, seed=6)
+    losses = {}
+    for mode in ("fp32", "bf16"):
+        eng = eng_mod.TrainEngine(d, round_params_bf16(params), mode=mode, dropout_p=0.2)
+        eng.seed = 77
+        losses[mode] = float(eng.step(eng.to_device(batch)))
+    e0 = eng_mod.TrainEngine(d, round_params_bf16(params), mode="fp32")
+    l0 = float(e0.step(e0.to_device(batch)))
+    torch.cuda.synchronize()
+    assert abs(losses["fp32"] - losses["bf16"]) < LOSS_TOL * abs(losses["fp32"]), losses
+    assert abs(losses["fp32"] - l0) > 1e-4 * abs(l0)
 
 
 def test_bf16_long_sequence_split_weight_gradients(eng_mod):

@@ -138,3 +138,30 @@ def test_errors_are_loud(eng_mod):
     bad = dict(fx["batch"])
     with pytest.raises(AssertionError):
         eng.step({k: v for k, v in bad.items()})          # CPU tensors are rejected
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=6, T_t=11, T_v=4, T_q=6, V=703, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101),
+    dict(B=9, T_t=5, T_v=2, T_q=4, V=120, E=20, H=32, L=2, H_a=8, H_v=16, F_v=24, TM=9, AM=5),
+])
+def test_fp32_step_with_dropout_matches_oracle_with_same_masks(eng_mod, cfg):
+    """The reference trains with torch.nn.LSTM's inter-layer dropout p = 0.2 (encoder.py:91, decoder.py:69).  The fp32
+    parity mode applies the same counter-based masks as the bf16 mode; they are exported (mmqg_dropout_mask) and fed
+    to the oracle, so the north-star bar holds with dropout on: loss and every gradient tensor <= 1e-3 relative."""
+    from oracle import mmqg_oracle as O
+    d = Dims(**cfg)
+    params = make_params(d, seed=71)
+    batch = make_batch(d, seed=72)
+    eng = eng_mod.TrainEngine(d, params, mode="fp32", dropout_p=0.2)
+    eng.seed = 2024
+    for _ in range(2):                      # second step: the device-side call counter has advanced, masks are fresh
+        masks = {k: v.cpu() for k, v in eng.dropout_masks().items()}
+        loss_ref, grads_ref = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64, drop=masks)
+        loss = float(eng.step(eng.to_device(batch)))
+        torch.cuda.synchronize()
+        assert abs(loss - float(loss_ref)) < TOL * abs(float(loss_ref)), (loss, float(loss_ref))
+        worst = max((rel(eng.grads[k], g), k) for k, g in grads_ref.items())
+        print("fp32 + dropout: worst grad rel err", worst)
+        assert worst[0] < TOL, worst
+    loss_nodrop, _ = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
+    assert abs(loss - float(loss_nodrop)) > 1e-4 * abs(loss)      # the masks do act
