@@ -339,6 +339,35 @@ int mmqg_vocab_nll_bwd(const void* h_bf16, const void* w_bf16, const float* bias
 int mmqg_decode_step_argmax(const void* h_bf16, const void* w_bf16, const float* bias, int R, int V, int H, void* workspace,
                             size_t workspace_bytes, int64_t* tokens, long long tok_stride, void* stream);
 
+/* ---- f2: conv stack of VideoConvLstmEncoder on raw frames (reference model/encoder.py:40-52, :58-67) -----------------
+ * 4 x [Conv2d(k, stride) -> ReLU -> BatchNorm2d], MaxPool2d(k, k) behind the 2nd and 4th; NCHW fp32, channels <= 16, k <= 5.
+ * Train-mode BatchNorm is split and folded into its neighbours (see csrc/convstack.cu):
+ *   conv_relu_fwd : y = relu(conv2d(x * in_scale[c] + in_shift[c], w) + b)  (in_scale/in_shift = the previous BatchNorm, NULL = none);
+ *                   stats (2*Cout floats, zeroed here, NULL = skip) receives per-channel sum and sum of squares of y
+ *   bn_finalize   : stats over `count` = N*H*W elements -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd,
+ *                   running_mean / running_var updated like torch.nn.BatchNorm2d (momentum, unbiased variance; NULL = skip)
+ *   bn_maxpool_fwd: out = maxpool_K(y * scale + shift) (kernel = stride = K, floor), idx = position of the first maximum in the window
+ * Backward:
+ *   maxpool_bwd   : dense gradient w.r.t. the BatchNorm output from the pooled gradient
+ *   bn_relu_bwd   : dz = gradient w.r.t. the conv output (through BatchNorm, batch statistics included, and ReLU);
+ *                   sums (2*C floats) receives d beta = sum d and d gamma = sum d*xhat; sums == NULL: eval-mode BatchNorm
+ *   conv_bwd_w    : dw (Cout,Cin,K,K), db (Cout) from dz and the (re-normalised) layer input
+ *   conv_bwd_x    : gradient w.r.t. the normalised layer input = the previous BatchNorm's output */
+int mmqg_conv_relu_fwd(const float* x, const float* in_scale, const float* in_shift, const float* w, const float* b, float* y,
+                       float* stats, int N, int Cin, int Hin, int Win, int Cout, int K, int stride, void* stream);
+int mmqg_bn_finalize(const float* stats, long long count, const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
+                     void* stream);
+int mmqg_bn_maxpool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* idx, int N, int C, int H,
+                        int W, int K, void* stream);
+int mmqg_maxpool_bwd(const float* dpool, const unsigned char* idx, float* dbn, int N, int C, int H, int W, int K, void* stream);
+int mmqg_bn_relu_bwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* dbn, float* dz,
+                     float* sums, int N, int C, int H, int W, void* stream);
+int mmqg_conv_bwd_w(const float* x, const float* in_scale, const float* in_shift, const float* dz, float* dw, float* db, int N,
+                    int Cin, int Hin, int Win, int Cout, int K, int stride, void* stream);
+int mmqg_conv_bwd_x(const float* dz, const float* w, float* dxn, int N, int Cin, int Hin, int Win, int Cout, int K, int stride,
+                    void* stream);
+
 /* Gradient exchange in bf16 (multi-GPU; the reference has no parallelism): a flat fp32 gradient
  * bucket is rounded to bf16 before the NCCL all-reduce and widened back afterwards, halving the bytes on NVLink.
  * pack: dst[i] = bf16(src[i]);  unpack: dst[i] = float(src[i]).  n elements, any alignment of n. */

@@ -1,0 +1,373 @@
+// f2 ("next"): the conv stack of VideoConvLstmEncoder on raw frames, forward and backward
+// (reference model/encoder.py:40-52 layers, :58-67 forward):  4 x [Conv2d(k, stride) -> ReLU -> BatchNorm2d] with a
+// MaxPool2d(k, k) behind the second and the fourth, channels 3 -> 4 -> 6 -> 8 -> 10, 112x112 frames -> 10x10x10 features.
+// Channel counts are tiny (<= 16), so nothing here is GEMM-shaped: every kernel is a coalesced pass over the
+// activation tensors (HBM/L2-bound), with the small weight set in shared memory.  Train-mode BatchNorm needs the batch
+// statistics of its input before it can normalise, so each BatchNorm is split in two and folded into its neighbours:
+//   conv_relu_fwd   : y = relu(conv(x * in_scale + in_shift) + b)       (the PREVIOUS BatchNorm applied on the load)
+//                     + per-channel sum / sum of squares of y           (statistics of the NEXT BatchNorm, atomics)
+//   bn_finalize     : statistics -> scale / shift, saved mean / invstd, running-stat update (BatchNorm2d, momentum 0.1)
+//   bn_maxpool_fwd  : out = maxpool(y * scale + shift), arg-max kept for the backward pass (first maximum on ties)
+// Backward, per layer: maxpool_bwd (dense gradient w.r.t. the BatchNorm output) -> bn_bwd_stats (sum d, sum d*xhat)
+//   -> bn_relu_bwd (d conv output) -> conv_bwd_w (dW, db) and conv_bwd_x (gradient w.r.t. the normalised input).
+// NCHW fp32 throughout (the reference's layout); the `view` that scrambles channels and time is the
+// caller's business: these kernels see (N, C, H, W).
+#include "kernels.h"
+
+namespace mmqg {
+namespace cs {
+
+static constexpr int MAXC = 16;          // channels per tensor
+static constexpr int MAXW = 4096;        // weights of one conv layer kept in shared memory (Cout * Cin * K * K)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// grid (ceil(Ho*Wo / 256), N).  Thread = one output pixel, all output channels.
+__global__ void __launch_bounds__(256)
+conv_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
+                     const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y, float* __restrict__ stats,
+                     int Cin, int Hin, int Win, int Cout, int K, int stride, int Ho, int Wo) {
+  __shared__ float sw[MAXW];
+  __shared__ float ssc[MAXC], ssh[MAXC], sb[MAXC];
+  const int nw = Cout * Cin * K * K;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < Cin) {
+    ssc[threadIdx.x] = in_scale ? in_scale[threadIdx.x] : 1.f;
+    ssh[threadIdx.x] = in_shift ? in_shift[threadIdx.x] : 0.f;
+  }
+  if (threadIdx.x < Cout) sb[threadIdx.x] = b ? b[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = p < Ho * Wo;
+  const int oy = live ? p / Wo : 0, ox = live ? p % Wo : 0;
+  float acc[MAXC];
+#pragma unroll
+  for (int co = 0; co < MAXC; ++co) acc[co] = 0.f;
+  if (live) {
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* xp = x + (((size_t)n * Cin + ci) * Hin + (size_t)oy * stride) * Win + (size_t)ox * stride;
+      const float sc = ssc[ci], sh = ssh[ci];
+      for (int ky = 0; ky < K; ++ky)
+        for (int kx = 0; kx < K; ++kx) {
+          const float xv = fmaf(xp[(size_t)ky * Win + kx], sc, sh);
+          const float* wp = sw + (ci * K + ky) * K + kx;
+#pragma unroll
+          for (int co = 0; co < MAXC; ++co)
+            if (co < Cout) acc[co] = fmaf(xv, wp[co * Cin * K * K], acc[co]);
+        }
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int co = 0; co < MAXC; ++co) {
+    if (co >= Cout) break;
+    const float v = live ? fmaxf(acc[co] + sb[co], 0.f) : 0.f;
+    if (live) y[(((size_t)n * Cout + co) * Ho + oy) * Wo + ox] = v;
+    if (stats) {
+      const float s1 = warp_sum(v), s2 = warp_sum(v * v);
+      if (lane == 0) { atomicAdd(stats + co, s1); atomicAdd(stats + Cout + co, s2); }
+    }
+  }
+}
+
+// one block, one thread per channel
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const float mean = stats[c] / count;
+  const float var = fmaxf(stats[C + c] / count - mean * mean, 0.f);     // biased, as BatchNorm normalises with
+  const float invstd = rsqrtf(var + eps);
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = bt - mean * g * invstd;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+  if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (count > 1.f ? count / (count - 1.f) : 1.f);
+}
+
+// thread = one pooled output element; window K x K, stride K, floor mode
+__global__ void bn_maxpool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                      float* __restrict__ out, unsigned char* __restrict__ idx, int C, int H, int W, int K, int Hp,
+                                      int Wp, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int px = (int)(i % Wp), py = (int)((i / Wp) % Hp);
+  const long long nc = i / ((long long)Wp * Hp);
+  const int c = (int)(nc % C);
+  const float sc = scale[c], sh = shift[c];
+  const float* yp = y + (nc * H + (long long)py * K) * W + (long long)px * K;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int ky = 0; ky < K; ++ky)
+    for (int kx = 0; kx < K; ++kx) {
+      const float v = fmaf(yp[(long long)ky * W + kx], sc, sh);
+      if (v > best || v != v) { best = v; bi = ky * K + kx; }      // first maximum on ties, NaN propagates (as torch)
+    }
+  out[i] = best;
+  idx[i] = (unsigned char)bi;
+}
+
+// dense gradient w.r.t. the BatchNorm output from the pooled gradient: thread = one element of the (N,C,H,W) tensor
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dpool, const unsigned char* __restrict__ idx, float* __restrict__ dbn,
+                                   int H, int W, int K, int Hp, int Wp, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xw = (int)(i % W), yh = (int)((i / W) % H);
+  const long long nc = i / ((long long)W * H);
+  const int py = yh / K, px = xw / K;
+  float g = 0.f;
+  if (py < Hp && px < Wp) {
+    const long long o = (nc * Hp + py) * Wp + px;
+    if (idx[o] == (unsigned char)((yh - py * K) * K + (xw - px * K))) g = dpool[o];
+  }
+  dbn[i] = g;
+}
+
+// sums[c] += sum d, sums[C + c] += sum d * xhat over (n, h, w); grid (blocks per plane, N*C)
+__global__ void __launch_bounds__(256)
+bn_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ dbn, float* __restrict__ sums, int C, int HW) {
+  __shared__ float r1[8], r2[8];
+  const int nc = blockIdx.y, c = nc % C;
+  const float m = mean[c], is = invstd[c];
+  const float* yp = y + (size_t)nc * HW;
+  const float* dp = dbn + (size_t)nc * HW;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float d = dp[i];
+    s1 += d;
+    s2 = fmaf(d, (yp[i] - m) * is, s2);
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { r1[warp] = s1; r2[warp] = s2; }
+  __syncthreads();
+  if (warp == 0) {
+    s1 = lane < 8 ? r1[lane] : 0.f; s2 = lane < 8 ? r2[lane] : 0.f;
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { atomicAdd(sums + c, s1); atomicAdd(sums + C + c, s2); }
+  }
+}
+
+// dz = gamma * invstd * (d - sum_d / M - xhat * sum_dxhat / M) * (y > 0)     (sums == NULL: eval-mode BatchNorm, dz = d * scale * (y > 0))
+__global__ void bn_relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   const float* __restrict__ gamma, const float* __restrict__ sums, const float* __restrict__ dbn,
+                                   float* __restrict__ dz, int C, int HW, float inv_count, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)((i / HW) % C);
+  const float yv = y[i];
+  const float g = gamma ? gamma[c] : 1.f;
+  float v;
+  if (sums) {
+    const float xhat = (yv - mean[c]) * invstd[c];
+    v = g * invstd[c] * (dbn[i] - sums[c] * inv_count - xhat * sums[C + c] * inv_count);
+  } else {
+    v = dbn[i] * g * invstd[c];
+  }
+  dz[i] = yv > 0.f ? v : 0.f;
+}
+
+// grid (Cout * Cin, chunks).  Block = one (co, ci) pair over a chunk of the N*Ho*Wo positions; thread accumulates the K*K taps.
+__global__ void __launch_bounds__(256)
+conv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
+                  const float* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db, int N, int Cin, int Hin, int Win,
+                  int Cout, int K, int stride, int Ho, int Wo) {
+  __shared__ float red[8][26];
+  const int co = blockIdx.x / Cin, ci = blockIdx.x % Cin;
+  const float sc = in_scale ? in_scale[ci] : 1.f, sh = in_shift ? in_shift[ci] : 0.f;
+  const long long P = (long long)N * Ho * Wo;
+  float acc[25], accb = 0.f;
+#pragma unroll
+  for (int k = 0; k < 25; ++k) acc[k] = 0.f;
+  for (long long p = (long long)blockIdx.y * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.y * blockDim.x) {
+    const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), n = (int)(p / ((long long)Wo * Ho));
+    const float g = dz[(((size_t)n * Cout + co) * Ho + oy) * Wo + ox];
+    accb += g;
+    const float* xp = x + (((size_t)n * Cin + ci) * Hin + (size_t)oy * stride) * Win + (size_t)ox * stride;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx)
+        if (ky < K && kx < K) acc[ky * 5 + kx] = fmaf(g, fmaf(xp[(size_t)ky * Win + kx], sc, sh), acc[ky * 5 + kx]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 25; ++k) {
+    const float s = warp_sum(acc[k]);
+    if (lane == 0) red[warp][k] = s;
+  }
+  {
+    const float s = warp_sum(accb);
+    if (lane == 0) red[warp][25] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 26) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+    if (threadIdx.x == 25) {
+      if (ci == 0 && db) atomicAdd(db + co, s);
+    } else {
+      const int ky = threadIdx.x / 5, kx = threadIdx.x % 5;
+      if (ky < K && kx < K) atomicAdd(dw + ((size_t)(co * Cin + ci) * K + ky) * K + kx, s);
+    }
+  }
+}
+
+// grid (ceil(Hin*Win / 256), N).  Thread = one input pixel, all input channels: dxn = sum_{co,ky,kx} dz[oy, ox] * w[co][ci][ky][kx]
+__global__ void __launch_bounds__(256)
+conv_bwd_x_kernel(const float* __restrict__ dz, const float* __restrict__ w, float* __restrict__ dxn, int Cin, int Hin, int Win,
+                  int Cout, int K, int stride, int Ho, int Wo) {
+  __shared__ float sw[MAXW];
+  const int nw = Cout * Cin * K * K;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Hin * Win) return;
+  const int iy = p / Win, ix = p % Win;
+  float acc[MAXC];
+#pragma unroll
+  for (int ci = 0; ci < MAXC; ++ci) acc[ci] = 0.f;
+  for (int ky = 0; ky < K; ++ky) {
+    const int ty = iy - ky;
+    if (ty < 0 || ty % stride) continue;
+    const int oy = ty / stride;
+    if (oy >= Ho) continue;
+    for (int kx = 0; kx < K; ++kx) {
+      const int tx = ix - kx;
+      if (tx < 0 || tx % stride) continue;
+      const int ox = tx / stride;
+      if (ox >= Wo) continue;
+      for (int co = 0; co < Cout; ++co) {
+        const float g = dz[(((size_t)n * Cout + co) * Ho + oy) * Wo + ox];
+        const float* wp = sw + (size_t)co * Cin * K * K + ky * K + kx;
+#pragma unroll
+        for (int ci = 0; ci < MAXC; ++ci)
+          if (ci < Cin) acc[ci] = fmaf(g, wp[ci * K * K], acc[ci]);
+      }
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < MAXC; ++ci)
+    if (ci < Cin) dxn[(((size_t)n * Cin + ci) * Hin + iy) * Win + ix] = acc[ci];
+}
+
+static int conv_out(int in, int K, int stride) { return (in - K) / stride + 1; }
+
+}  // namespace cs
+}  // namespace mmqg
+
+using namespace mmqg;
+
+extern "C" int mmqg_conv_relu_fwd(const float* x, const float* in_scale, const float* in_shift, const float* w, const float* b, float* y,
+                                  float* stats, int N, int Cin, int Hin, int Win, int Cout, int K, int stride, void* stream) {
+  MMQG_REQUIRE(x && w && y && N > 0 && Cin > 0 && Cin <= cs::MAXC && Cout > 0 && Cout <= cs::MAXC && K >= 1 && K <= 5 && stride >= 1 &&
+                   Hin >= K && Win >= K && Cout * Cin * K * K <= cs::MAXW,
+               "conv_relu_fwd: unsupported shape N=%d Cin=%d Cout=%d K=%d stride=%d H=%d W=%d", N, Cin, Cout, K, stride, Hin, Win);
+  cudaStream_t st = as_stream(stream);
+  const int Ho = cs::conv_out(Hin, K, stride), Wo = cs::conv_out(Win, K, stride);
+  if (stats) MMQG_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, st));
+  MMQG_PROBE(KC_OTHER, 2.0 * N * Ho * Wo * Cout * Cin * K * K, 4.0 * N * ((double)Cin * Hin * Win + (double)Cout * Ho * Wo));
+  cs::conv_relu_fwd_kernel<<<dim3(ceil_div(Ho * Wo, 256), N), 256, 0, st>>>(x, in_scale, in_shift, w, b, y, stats, Cin, Hin, Win, Cout, K,
+                                                                            stride, Ho, Wo);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmqg_bn_finalize(const float* stats, long long count, const float* gamma, const float* beta, float eps, float momentum,
+                                float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
+                                void* stream) {
+  MMQG_REQUIRE(stats && scale && shift && mean && invstd && C > 0 && C <= cs::MAXC && count > 0, "bn_finalize: bad args");
+  cudaStream_t st = as_stream(stream);
+  cs::bn_finalize_kernel<<<1, 32, 0, st>>>(stats, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
+                                           invstd, C);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmqg_bn_maxpool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* idx, int N, int C,
+                                   int H, int W, int K, void* stream) {
+  MMQG_REQUIRE(y && scale && shift && out && idx && N > 0 && C > 0 && C <= cs::MAXC && K >= 1 && K <= 15 && H >= K && W >= K,
+               "bn_maxpool_fwd: bad args");
+  cudaStream_t st = as_stream(stream);
+  const int Hp = (H - K) / K + 1, Wp = (W - K) / K + 1;
+  const long long total = (long long)N * C * Hp * Wp;
+  MMQG_PROBE(KC_OTHER, 0, 4.0 * N * C * ((double)H * W + (double)Hp * Wp));
+  cs::bn_maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, scale, shift, out, idx, C, H, W, K, Hp, Wp, total);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmqg_maxpool_bwd(const float* dpool, const unsigned char* idx, float* dbn, int N, int C, int H, int W, int K, void* stream) {
+  MMQG_REQUIRE(dpool && idx && dbn && N > 0 && C > 0 && K >= 1 && H >= K && W >= K, "maxpool_bwd: bad args");
+  cudaStream_t st = as_stream(stream);
+  const int Hp = (H - K) / K + 1, Wp = (W - K) / K + 1;
+  const long long total = (long long)N * C * H * W;
+  MMQG_PROBE(KC_OTHER, 0, 4.0 * total);
+  cs::maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dpool, idx, dbn, H, W, K, Hp, Wp, total);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward of train-mode BatchNorm + ReLU: y = relu output (the BatchNorm's input), dbn = gradient w.r.t. the BatchNorm output,
+// dz = gradient w.r.t. the conv output (may alias dbn).  sums (2*C floats: sum d = d beta, sum d*xhat = d gamma) is filled here.
+// sums == NULL: eval-mode BatchNorm (fixed affine map, invstd = 1/sqrt(running_var + eps)).
+extern "C" int mmqg_bn_relu_bwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* dbn, float* dz,
+                                float* sums, int N, int C, int H, int W, void* stream) {
+  MMQG_REQUIRE(y && invstd && dbn && dz && N > 0 && C > 0 && C <= cs::MAXC && H > 0 && W > 0 && (!sums || mean), "bn_relu_bwd: bad args");
+  cudaStream_t st = as_stream(stream);
+  const int HW = H * W;
+  const long long total = (long long)N * C * HW;
+  if (sums) {
+    MMQG_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
+    int bx = ceil_div(HW, 256 * 4);
+    if (bx > 64) bx = 64;
+    cs::bn_bwd_stats_kernel<<<dim3(bx, N * C), 256, 0, st>>>(y, mean, invstd, dbn, sums, C, HW);
+    MMQG_LAUNCH_CHECK();
+  }
+  MMQG_PROBE(KC_OTHER, 0, 12.0 * total);
+  cs::bn_relu_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, mean, invstd, gamma, sums, dbn, dz, C, HW,
+                                                                          1.0f / ((float)N * HW), total);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmqg_conv_bwd_w(const float* x, const float* in_scale, const float* in_shift, const float* dz, float* dw, float* db, int N,
+                               int Cin, int Hin, int Win, int Cout, int K, int stride, void* stream) {
+  MMQG_REQUIRE(x && dz && dw && N > 0 && Cin > 0 && Cin <= cs::MAXC && Cout > 0 && Cout <= cs::MAXC && K >= 1 && K <= 5 && stride >= 1 &&
+                   Hin >= K && Win >= K, "conv_bwd_w: unsupported shape");
+  cudaStream_t st = as_stream(stream);
+  const int Ho = cs::conv_out(Hin, K, stride), Wo = cs::conv_out(Win, K, stride);
+  MMQG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * K * K, st));
+  if (db) MMQG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, st));
+  const long long P = (long long)N * Ho * Wo;
+  int chunks = (int)((P + 256 * 16 - 1) / (256 * 16));
+  if (chunks < 1) chunks = 1;
+  if (chunks > 64) chunks = 64;
+  MMQG_PROBE(KC_OTHER, 2.0 * P * Cout * Cin * K * K, 4.0 * P * (Cout * Cin + (double)Cin * Cout * K * K));
+  cs::conv_bwd_w_kernel<<<dim3(Cout * Cin, chunks), 256, 0, st>>>(x, in_scale, in_shift, dz, dw, db, N, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmqg_conv_bwd_x(const float* dz, const float* w, float* dxn, int N, int Cin, int Hin, int Win, int Cout, int K, int stride,
+                               void* stream) {
+  MMQG_REQUIRE(dz && w && dxn && N > 0 && Cin > 0 && Cin <= cs::MAXC && Cout > 0 && Cout <= cs::MAXC && K >= 1 && K <= 5 && stride >= 1 &&
+                   Hin >= K && Win >= K && Cout * Cin * K * K <= cs::MAXW, "conv_bwd_x: unsupported shape");
+  cudaStream_t st = as_stream(stream);
+  const int Ho = cs::conv_out(Hin, K, stride), Wo = cs::conv_out(Win, K, stride);
+  MMQG_PROBE(KC_OTHER, 2.0 * N * Ho * Wo * Cout * Cin * K * K, 4.0 * N * ((double)Cin * Hin * Win + (double)Cout * Ho * Wo));
+  cs::conv_bwd_x_kernel<<<dim3(ceil_div(Hin * Win, 256), N), 256, 0, st>>>(dz, w, dxn, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}

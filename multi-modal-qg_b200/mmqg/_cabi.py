@@ -87,6 +87,13 @@ SYMBOLS = {
     "mmqg_argmax_rows": (_i, [_fp, _i, _fp, _ll, _i, _i, _fp]),
     "mmqg_colsum": (_i, [_fp, _i, _fp, _i, _i, _f, _fp]),
     "mmqg_pack_bf16": (_i, [_fp, _fp, _ll, _fp]),
+    "mmqg_conv_relu_fwd": (_i, [_fp] * 7 + [_i] * 7 + [_fp]),
+    "mmqg_bn_finalize": (_i, [_fp, _ll, _fp, _fp, _f, _f] + [_fp] * 6 + [_i, _fp]),
+    "mmqg_bn_maxpool_fwd": (_i, [_fp] * 5 + [_i] * 5 + [_fp]),
+    "mmqg_maxpool_bwd": (_i, [_fp] * 3 + [_i] * 5 + [_fp]),
+    "mmqg_bn_relu_bwd": (_i, [_fp] * 7 + [_i] * 4 + [_fp]),
+    "mmqg_conv_bwd_w": (_i, [_fp] * 6 + [_i] * 7 + [_fp]),
+    "mmqg_conv_bwd_x": (_i, [_fp] * 3 + [_i] * 7 + [_fp]),
     "mmqg_unpack_bf16": (_i, [_fp, _fp, _ll, _fp]),
     "mmqg_lstm_seq_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mmqg_lstm_seq_fwd": (_i, [_fp] * 7 + [_i] * 4 + [_fp, _sz, _fp, _fp, _fp, _fp]),

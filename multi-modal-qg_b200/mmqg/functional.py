@@ -184,6 +184,101 @@ class LSTMLayerSeq(Function):
 _mask_calls = 0
 
 
+class ConvStack(Function):
+    """f2: the conv stack of VideoConvLstmEncoder (reference model/encoder.py:62-64): four Conv2d -> ReLU -> BatchNorm2d
+    blocks with a MaxPool2d(k, k) behind the second and the fourth, on the CUDA kernels of csrc/convstack.cu.
+    Train mode uses batch statistics and updates the running buffers like torch.nn.BatchNorm2d; eval mode uses the
+    running statistics.  Inputs: x (N,C,H,W); per layer conv weight, conv bias, bn weight, bn bias; `state`: per layer
+    (running_mean, running_var, eps, momentum) (buffers, updated in place) and (K, stride, training)."""
+
+    POOL_AFTER = (1, 3)
+
+    @staticmethod
+    def forward(ctx, x, state, *params):
+        bn_state, K, stride, training = state
+        x = _c(x)
+        n_layers = len(params) // 4
+        saved, meta = [], []
+        inp, sc, sh = x, None, None
+        for l in range(n_layers):
+            w, b, gamma, beta = [_c(p) for p in params[4 * l:4 * l + 4]]
+            rm, rv, eps, mom = bn_state[l]
+            y, stats = ops.conv_relu_fwd(inp, w, b, sc, sh, stride, want_stats=training)
+            if training:
+                count = y.shape[0] * y.shape[2] * y.shape[3]
+                scale, shift, mean, invstd = ops.bn_finalize(stats, count, gamma, beta, eps, mom, rm, rv)
+            else:
+                invstd = torch.rsqrt(rv + eps)
+                mean = rm
+                scale = gamma * invstd
+                shift = beta - rm * scale
+            saved += [inp, sc, sh, y, mean, invstd]
+            if l in ConvStack.POOL_AFTER:
+                pooled, idx = ops.bn_maxpool_fwd(y, scale, shift, K)
+                saved.append(idx)
+                meta.append((True, y.shape[2], y.shape[3]))
+                inp, sc, sh = pooled, None, None
+            else:
+                saved.append(None)
+                meta.append((False, y.shape[2], y.shape[3]))
+                inp, sc, sh = y, scale, shift
+        if sc is not None:      # stack that does not end in a pool: materialise the last BatchNorm
+            inp = inp * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+        ctx.meta = (meta, K, stride, training, n_layers)
+        ctx.save_for_backward(*[t for t in saved if t is not None], *params)
+        ctx.mask = [t is not None for t in saved]
+        return inp
+
+    @staticmethod
+    def backward(ctx, dout):
+        meta, K, stride, training, n_layers = ctx.meta
+        it = iter(ctx.saved_tensors)
+        saved = [next(it) if m else None for m in ctx.mask]
+        params = list(it)
+        grads = [None] * (4 * n_layers)
+        d = _c(dout)
+        for l in range(n_layers - 1, -1, -1):
+            inp, sc, sh, y, mean, invstd, idx = saved[7 * l:7 * l + 7]
+            w, gamma = _c(params[4 * l]), _c(params[4 * l + 2])
+            pooled, H, W = meta[l]
+            if pooled:
+                dbn = ops.maxpool_bwd(d, idx, H, W, K)
+            else:      # d is ours (conv_bwd_x of the layer above) unless it is autograd's own dout
+                dbn = d.clone() if l == n_layers - 1 else d
+            C_ = y.shape[1]
+            if not training:      # eval-mode BatchNorm: d beta = sum d, d gamma = sum d * xhat over the fixed statistics
+                xhat = (y - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+                grads[4 * l + 3], grads[4 * l + 2] = dbn.sum((0, 2, 3)), (dbn * xhat).sum((0, 2, 3))
+            dz, sums = ops.bn_relu_bwd(y, mean, invstd, gamma, dbn, train=training)      # in place: dz aliases dbn
+            if training:
+                grads[4 * l + 3], grads[4 * l + 2] = sums[:C_].clone(), sums[C_:].clone()
+            grads[4 * l], grads[4 * l + 1] = ops.conv_bwd_w(inp, dz, K, stride, sc, sh)
+            if l > 0:
+                d = ops.conv_bwd_x(dz, w, inp.shape[2], inp.shape[3], stride)
+        return (None, None, *grads)
+
+
+def conv_stack(x, module):
+    """Run module.conv1..4 / bn1..4 / maxpool1..2 of a VideoConvLstmEncoder on (N,C,H,W) frames -> (N, 10, h, w)."""
+    convs = [module.conv1, module.conv2, module.conv3, module.conv4]
+    bns = [module.bn1, module.bn2, module.bn3, module.bn4]
+    K = convs[0].kernel_size[0]
+    stride = convs[0].stride[0]
+    for c in convs:
+        assert c.kernel_size == (K, K) and c.stride == (stride, stride) and c.padding == (0, 0) and c.dilation == (1, 1) and c.groups == 1
+    assert module.maxpool1.kernel_size == K and module.maxpool1.stride == K and module.maxpool2.kernel_size == K
+    training = module.training
+    bn_state = []
+    params = []
+    for c, bn in zip(convs, bns):
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        bn_state.append((bn.running_mean, bn.running_var, bn.eps, mom))
+        params += [c.weight, c.bias, bn.weight, bn.bias]
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+    return ConvStack.apply(x, (bn_state, K, stride, training), *params)
+
+
 def _dropout_masks(L, T, B, H, p, device):
     """(L-1,T,B,H) inter-layer dropout masks (0 or 1/(1-p)) drawn by the library's counter-based generator
     (mmqg_dropout_mask), a fresh stream per call; torch.manual_seed() reseeds it through torch.initial_seed()."""

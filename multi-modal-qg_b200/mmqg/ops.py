@@ -260,3 +260,74 @@ def lstm_seq_bwd(dy, dhn, dcn, w_hh, ws, T, B, I, H, want_dx=True):
                                   ws.numel(), _cabi.ptr(g["dx"]), g["dw_ih"].data_ptr(), g["dw_hh"].data_ptr(),
                                   g["db_ih"].data_ptr(), g["db_hh"].data_ptr(), g["dh0"].data_ptr(), g["dc0"].data_ptr(), _st()))
     return g
+
+
+# ---- f2: conv stack building blocks (csrc/convstack.cu) --------------------------------------------------------------
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def conv_relu_fwd(x, w, b, in_scale=None, in_shift=None, stride=1, want_stats=True):
+    """y = relu(conv2d(x * in_scale + in_shift, w) + b) on (N,Cin,H,W) fp32; returns (y, stats) with stats = per-channel
+    (sum, sum of squares) of y, 2*Cout floats (None when want_stats is False)."""
+    _chk(x, w, b, in_scale, in_shift)
+    N, Cin, H, W = x.shape
+    Cout, _, K, _ = w.shape
+    Ho, Wo = (H - K) // stride + 1, (W - K) // stride + 1
+    y = torch.empty(N, Cout, Ho, Wo, device=x.device, dtype=torch.float32)
+    stats = torch.empty(2 * Cout, device=x.device, dtype=torch.float32) if want_stats else None
+    check(lib().mmqg_conv_relu_fwd(x.data_ptr(), _p(in_scale), _p(in_shift), w.data_ptr(), _p(b), y.data_ptr(), _p(stats),
+                                   N, Cin, H, W, Cout, K, stride, _st()))
+    return y, stats
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var):
+    """Train-mode BatchNorm2d statistics -> (scale, shift, mean, invstd); running stats updated in place (None = skip)."""
+    C_ = stats.numel() // 2
+    out = [torch.empty(C_, device=stats.device, dtype=torch.float32) for _ in range(4)]
+    check(lib().mmqg_bn_finalize(stats.data_ptr(), int(count), _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
+                                 _p(running_var), *[o.data_ptr() for o in out], C_, _st()))
+    return out
+
+
+def bn_maxpool_fwd(y, scale, shift, K):
+    N, C_, H, W = y.shape
+    Hp, Wp = (H - K) // K + 1, (W - K) // K + 1
+    out = torch.empty(N, C_, Hp, Wp, device=y.device, dtype=torch.float32)
+    idx = torch.empty(N, C_, Hp, Wp, device=y.device, dtype=torch.uint8)
+    check(lib().mmqg_bn_maxpool_fwd(y.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(), idx.data_ptr(), N, C_, H, W, K, _st()))
+    return out, idx
+
+
+def maxpool_bwd(dpool, idx, H, W, K):
+    N, C_ = dpool.shape[:2]
+    dbn = torch.empty(N, C_, H, W, device=dpool.device, dtype=torch.float32)
+    check(lib().mmqg_maxpool_bwd(dpool.data_ptr(), idx.data_ptr(), dbn.data_ptr(), N, C_, H, W, K, _st()))
+    return dbn
+
+
+def bn_relu_bwd(y, mean, invstd, gamma, dbn, train=True):
+    """Gradient w.r.t. the conv output (in place of dbn) and, in train mode, sums = (d beta | d gamma)."""
+    N, C_, H, W = y.shape
+    sums = torch.empty(2 * C_, device=y.device, dtype=torch.float32) if train else None
+    check(lib().mmqg_bn_relu_bwd(y.data_ptr(), _p(mean), invstd.data_ptr(), _p(gamma), dbn.data_ptr(), dbn.data_ptr(), _p(sums),
+                                 N, C_, H, W, _st()))
+    return dbn, sums
+
+
+def conv_bwd_w(x, dz, K, stride=1, in_scale=None, in_shift=None):
+    N, Cin, H, W = x.shape
+    Cout = dz.shape[1]
+    dw = torch.empty(Cout, Cin, K, K, device=x.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32)
+    check(lib().mmqg_conv_bwd_w(x.data_ptr(), _p(in_scale), _p(in_shift), dz.data_ptr(), dw.data_ptr(), db.data_ptr(), N, Cin, H, W,
+                                Cout, K, stride, _st()))
+    return dw, db
+
+
+def conv_bwd_x(dz, w, H, W, stride=1):
+    N, Cout = dz.shape[:2]
+    _, Cin, K, _ = w.shape
+    dxn = torch.empty(N, Cin, H, W, device=dz.device, dtype=torch.float32)
+    check(lib().mmqg_conv_bwd_x(dz.data_ptr(), w.data_ptr(), dxn.data_ptr(), N, Cin, H, W, Cout, K, stride, _st()))
+    return dxn

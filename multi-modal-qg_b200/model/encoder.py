@@ -7,7 +7,6 @@ runs in libmmqg.so.  torch.nn.LSTM objects are kept purely as parameter containe
 never called.  CUDA only: CPU tensors raise (no fallback).
 """
 import torch
-import torch.nn.functional as F
 from torch.nn import Module, LSTM, Conv2d, MaxPool2d, AdaptiveAvgPool1d, BatchNorm2d, Flatten
 from torch.nn.init import orthogonal_, normal_
 
@@ -36,8 +35,9 @@ class AudioEncoder(Module):
 
 
 class VideoConvLstmEncoder(Module):
-    """reference encoder.py:31-78.  The conv stack stays on stock torch modules (SURVEY section 8 f2,
-    out of scope this round); the LSTM over the per-frame features runs on the CUDA kernels."""
+    """reference encoder.py:31-78.  Conv2d / BatchNorm2d / MaxPool2d objects are parameter and buffer containers
+    (same state_dict keys); the conv stack runs on csrc/convstack.cu, the LSTM over the
+    per-frame features on the recurrent kernels."""
 
     def __init__(self, in_channels, kernel_sz, stride, hidden_dim, video_emb_dim):
         super().__init__()
@@ -75,8 +75,10 @@ class VideoConvLstmEncoder(Module):
         width = video_frames.shape[4]
         # `view`, not permute: the reference reinterprets memory here
         x = video_frames.view(batch_sz, channels, height, width)
-        first_block = self.maxpool1(self.bn2(F.relu(self.conv2(self.bn1(F.relu(self.conv1(x)))))))
-        second_block = self.maxpool2(self.bn4(F.relu(self.conv4(self.bn3(F.relu(self.conv3(first_block)))))))
+        # reference encoder.py:62-63: maxpool1(bn2(relu(conv2(bn1(relu(conv1(x))))))) and the same with conv3/4, bn3/4,
+        # maxpool2 -- on the kernels of csrc/convstack.cu (train-mode batch statistics, running-stat updates included)
+        MF.require_cuda(x)
+        second_block = MF.conv_stack(x, self)
         cnn_out = self.flatten(second_block)
         return self.encode_features(cnn_out)
 

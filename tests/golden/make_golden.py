@@ -285,6 +285,51 @@ def run_decoder_case(name, T, V, E, A, H, L, seed, dtype=torch.float64):
     print(name, "loss", float(loss), os.path.getsize(path), "bytes")
 
 
+def run_convstack_case(name, T, HW, hidden, seed, dtype=torch.float64):
+    """f2: the reference's own VideoConvLstmEncoder (model/encoder.py:31-78) on raw frames: conv stack (4 x Conv2d -> ReLU ->
+    BatchNorm2d, two MaxPool2d) + LSTM.  One train-mode forward/backward (batch statistics, running buffers updated) and one
+    eval-mode forward.  Stored: initial state_dict, frames, outputs, the projection that forms the scalar loss, every
+    parameter gradient, the BatchNorm buffers after the train-mode forward."""
+    torch.manual_seed(seed)
+    s = HW
+    for _ in range(2):
+        s = ((s - 2) - 2) // 3
+    feat = 10 * s * s
+    enc = VideoConvLstmEncoder(3, 3, 1, hidden, feat).to(dtype)
+    with torch.no_grad():      # BatchNorm affine parameters and running buffers away from their defaults
+        for bn in (enc.bn1, enc.bn2, enc.bn3, enc.bn4):
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.3, 0.3)
+            bn.running_mean.uniform_(-0.2, 0.2)
+            bn.running_var.uniform_(0.5, 1.5)
+        for v in enc.state_dict().values():      # fp32-representable values: the fixture stores fp32 and loses nothing
+            if v.is_floating_point():
+                v.copy_(v.float().to(dtype))
+    state0 = {k: v.detach().clone().float() for k, v in enc.state_dict().items()}
+    frames = torch.randn(1, 3, T, HW, HW).to(dtype)
+    proj = torch.randn(T, 1, hidden).to(dtype)
+    enc.train()
+    out = enc(frames)
+    loss = (out * proj).sum()
+    loss.backward()
+    grads = {n_: p_.grad.detach().float().clone() for n_, p_ in enc.named_parameters()}
+    state1 = {k: v.detach().clone().float() for k, v in enc.state_dict().items() if "running" in k or "num_batches" in k}
+    enc.eval()
+    with torch.no_grad():
+        out_eval = enc(frames)
+    fx = {"T": T, "HW": HW, "hidden": hidden, "feat": feat, "state0": state0, "frames": frames.float(), "proj": proj.float(),
+          "out_train": out.detach().float(), "loss": float(loss), "grads": grads, "bn_after": state1, "out_eval": out_eval.float()}
+    path = os.path.join(HERE, f"{name}.pt")
+    torch.save(fx, path)
+    print(name, "loss", float(loss), "features", feat, os.path.getsize(path), "bytes")
+
+
+CONVSTACK_CASES = {
+    "convstack_a": dict(T=3, HW=40, hidden=32, seed=51),       # 40 -> 38 -> 36 -> 12 -> 10 -> 8 -> 2: 40 features
+    "convstack_b": dict(T=5, HW=58, hidden=64, seed=52),       # 58 -> ... -> 4: 160 features; hidden on the tensor-core sequence path
+}
+
+
 DECODER_CASES = {
     "decoder_a": dict(T=6, V=37, E=12, A=20, H=32, L=2, seed=41),      # fp32 building blocks (H not a multiple of 64)
     "decoder_b": dict(T=9, V=53, E=12, A=20, H=64, L=3, seed=42),      # shape the tensor-core sequence kernels take
@@ -294,10 +339,13 @@ DECODER_CASES = {
 if __name__ == "__main__":
     torch.manual_seed(0)
     which = sys.argv[1:]
+    for name, c in CONVSTACK_CASES.items():
+        if not which or name in which:
+            run_convstack_case(name, **c)
     for name, c in DECODER_CASES.items():
         if not which or name in which:
             run_decoder_case(name, **c)
-    if which and all(w in DECODER_CASES for w in which):
+    if which and all(w in DECODER_CASES or w in CONVSTACK_CASES for w in which):
         sys.exit(0)
     if not which or "adam_a" in which:
         run_adam_case()

@@ -11,6 +11,10 @@ from oracle import mmqg_oracle as O
 from oracle import ref_loop as R
 
 
+def rel(a, b):
+    return O.rel_err(a, b)
+
+
 @pytest.mark.parametrize("name", ["small_a", "small_b"])
 def test_oracle_matches_reference_small(name):
     fx = load_golden(name)
@@ -200,3 +204,22 @@ def test_oracle_adam_wiring_matches_the_reference_fixture():
         upd_ref = v.double() - fx["params"][k].double()
         upd = p[k].detach() - fx["params"][k].double()
         assert float((upd - upd_ref).norm()) <= 1e-7 * float(upd_ref.norm()) + 1e-15, k
+
+
+@pytest.mark.parametrize("name", ["convstack_a", "convstack_b"])
+def test_convstack_oracle_matches_reference_module(name):
+    """f2: oracle/convstack_oracle.py against the reference's own VideoConvLstmEncoder (train-mode outputs, every gradient,
+    BatchNorm running buffers, eval-mode outputs) at 1e-9."""
+    from oracle import convstack_oracle as CO
+    fx = load_golden(name)
+    out, loss, grads, buffers = CO.loss_and_grads(fx)
+    assert abs(loss - fx["loss"]) < 1e-9 * max(1.0, abs(fx["loss"]))
+    assert rel(out, fx["out_train"].double()) < 1e-6          # fixtures are stored in fp32
+    for k, g in fx["grads"].items():
+        assert rel(grads[k], g.double()) < 1e-6, k
+    for k, v in buffers.items():
+        assert rel(v, fx["bn_after"][k].double()) < 1e-6, k
+    p = {k: v.double() for k, v in fx["state0"].items()}
+    p.update({k: v.double() for k, v in fx["bn_after"].items() if "running" in k})
+    out_eval, _ = CO.video_conv_lstm(fx["frames"].double(), p, False)
+    assert rel(out_eval, fx["out_eval"].double()) < 1e-6
