@@ -343,8 +343,9 @@ int mmqg_decode_step_argmax(const void* h_bf16, const void* w_bf16, const float*
  * 4 x [Conv2d(k, stride) -> ReLU -> BatchNorm2d], MaxPool2d(k, k) behind the 2nd and 4th; NCHW fp32, channels <= 16, k <= 5.
  * Train-mode BatchNorm is split and folded into its neighbours (see csrc/convstack.cu):
  *   conv_relu_fwd : y = relu(conv2d(x * in_scale[c] + in_shift[c], w) + b)  (in_scale/in_shift = the previous BatchNorm, NULL = none);
- *                   stats (2*Cout floats, zeroed here, NULL = skip) receives per-channel sum and sum of squares of y
- *   bn_finalize   : stats over `count` = N*H*W elements -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd,
+ *                   stats (mmqg_conv_stats_parts() x 2*Cout floats, NULL = skip) receives per-block partial sums and sums of
+ *                   squares of y per channel (no same-address atomics)
+ *   bn_finalize   : the `nparts` partials, `count` = N*H*W elements -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd,
  *                   running_mean / running_var updated like torch.nn.BatchNorm2d (momentum, unbiased variance; NULL = skip)
  *   bn_maxpool_fwd: out = maxpool_K(y * scale + shift) (kernel = stride = K, floor), idx = position of the first maximum in the window
  * Backward:
@@ -355,9 +356,10 @@ int mmqg_decode_step_argmax(const void* h_bf16, const void* w_bf16, const float*
  *   conv_bwd_x    : gradient w.r.t. the normalised layer input = the previous BatchNorm's output */
 int mmqg_conv_relu_fwd(const float* x, const float* in_scale, const float* in_shift, const float* w, const float* b, float* y,
                        float* stats, int N, int Cin, int Hin, int Win, int Cout, int K, int stride, void* stream);
-int mmqg_bn_finalize(const float* stats, long long count, const float* gamma, const float* beta, float eps, float momentum,
-                     float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
-                     void* stream);
+int mmqg_conv_stats_parts(int N, int Hin, int Win, int K, int stride);
+int mmqg_bn_finalize(const float* stats_parts, int nparts, long long count, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                     float* invstd, int C, void* stream);
 int mmqg_bn_maxpool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* idx, int N, int C, int H,
                         int W, int K, void* stream);
 int mmqg_maxpool_bwd(const float* dpool, const unsigned char* idx, float* dbn, int N, int C, int H, int W, int K, void* stream);

@@ -5,7 +5,7 @@
 // activation tensors (HBM/L2-bound), with the small weight set in shared memory.  Train-mode BatchNorm needs the batch
 // statistics of its input before it can normalise, so each BatchNorm is split in two and folded into its neighbours:
 //   conv_relu_fwd   : y = relu(conv(x * in_scale + in_shift) + b)       (the PREVIOUS BatchNorm applied on the load)
-//                     + per-channel sum / sum of squares of y           (statistics of the NEXT BatchNorm, atomics)
+//                     + per-block partial sums / sums of squares of y   (statistics of the NEXT BatchNorm)
 //   bn_finalize     : statistics -> scale / shift, saved mean / invstd, running-stat update (BatchNorm2d, momentum 0.1)
 //   bn_maxpool_fwd  : out = maxpool(y * scale + shift), arg-max kept for the backward pass (first maximum on ties)
 // Backward, per layer: maxpool_bwd (dense gradient w.r.t. the BatchNorm output) -> bn_bwd_stats (sum d, sum d*xhat)
@@ -62,7 +62,9 @@ conv_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ in_s
         }
     }
   }
-  const int lane = threadIdx.x & 31;
+  // per-block partial statistics (no same-address atomics: N * tiles blocks would serialise on 2*Cout words of L2)
+  __shared__ float red[8][2 * MAXC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int co = 0; co < MAXC; ++co) {
     if (co >= Cout) break;
@@ -70,20 +72,42 @@ conv_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ in_s
     if (live) y[(((size_t)n * Cout + co) * Ho + oy) * Wo + ox] = v;
     if (stats) {
       const float s1 = warp_sum(v), s2 = warp_sum(v * v);
-      if (lane == 0) { atomicAdd(stats + co, s1); atomicAdd(stats + Cout + co, s2); }
+      if (lane == 0) { red[warp][co] = s1; red[warp][Cout + co] = s2; }
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    if (threadIdx.x < 2 * Cout) {
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+      stats[((size_t)n * gridDim.x + blockIdx.x) * 2 * Cout + threadIdx.x] = t;
     }
   }
 }
 
-// one block, one thread per channel
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
-  const float mean = stats[c] / count;
-  const float var = fmaxf(stats[C + c] / count - mean * mean, 0.f);     // biased, as BatchNorm normalises with
+// grid C, block 256: block c sums the per-block partial statistics of channel c, thread 0 finishes the BatchNorm bookkeeping
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ parts, int nparts, float count, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
+  __shared__ float r1[8], r2[8];
+  const int c = blockIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    s1 += parts[(size_t)i * 2 * C + c];
+    s2 += parts[(size_t)i * 2 * C + C + c];
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { r1[warp] = s1; r2[warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  s1 = 0.f; s2 = 0.f;
+  for (int wv = 0; wv < 8; ++wv) { s1 += r1[wv]; s2 += r2[wv]; }
+  const float mean = s1 / count;
+  const float var = fmaxf(s2 / count - mean * mean, 0.f);     // biased, as BatchNorm normalises with
   const float invstd = rsqrtf(var + eps);
   const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
   scale[c] = g * invstd;
@@ -223,7 +247,75 @@ conv_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ in_scal
   }
 }
 
+// K = 3 fast path.  grid (chunks, Cin): a block takes ONE input channel and a slice of the N*Ho*Wo positions; a thread keeps the
+// 9 taps x Cout partial sums in registers (x patch read once per position, d z once per output channel), so d z is read Cin
+// times in total instead of Cin * Cout * 9 / ... times through the generic kernel's (co, ci) blocks.
+template <int STRIDE1>
+__global__ void __launch_bounds__(256)
+conv_bwd_w3_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
+                   const float* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db, int N, int Cin, int Hin, int Win,
+                   int Cout, int stride, int Ho, int Wo) {
+  __shared__ float red[8][MAXC * 9 + MAXC];
+  const int ci = blockIdx.y;
+  const float sc = in_scale ? in_scale[ci] : 1.f, sh = in_shift ? in_shift[ci] : 0.f;
+  const long long P = (long long)N * Ho * Wo;
+  const size_t plane = (size_t)Ho * Wo;
+  float acc[MAXC][9], accb[MAXC];
+#pragma unroll
+  for (int co = 0; co < MAXC; ++co) {
+    accb[co] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[co][k] = 0.f;
+  }
+  const int st = STRIDE1 ? 1 : stride;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), n = (int)(p / ((long long)Wo * Ho));
+    const float* xp = x + (((size_t)n * Cin + ci) * Hin + (size_t)oy * st) * Win + (size_t)ox * st;
+    float xv[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) xv[ky * 3 + kx] = fmaf(xp[(size_t)ky * Win + kx], sc, sh);
+    const float* gp = dz + (size_t)n * Cout * plane + (size_t)oy * Wo + ox;
+#pragma unroll
+    for (int co = 0; co < MAXC; ++co) {
+      if (co >= Cout) break;
+      const float g = gp[co * plane];
+      accb[co] += g;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[co][k] = fmaf(g, xv[k], acc[co][k]);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int co = 0; co < MAXC; ++co) {
+    if (co >= Cout) break;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float s = warp_sum(acc[co][k]);
+      if (lane == 0) red[warp][co * 9 + k] = s;
+    }
+    const float sb = warp_sum(accb[co]);
+    if (lane == 0) red[warp][MAXC * 9 + co] = sb;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * 9 + Cout; i += blockDim.x) {
+    const bool is_b = i >= Cout * 9;
+    const int slot = is_b ? MAXC * 9 + (i - Cout * 9) : i;
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][slot];
+    if (is_b) {
+      if (ci == 0 && db) atomicAdd(db + (i - Cout * 9), s);
+    } else {
+      const int co = i / 9, k = i % 9;
+      atomicAdd(dw + ((size_t)(co * Cin + ci)) * 9 + k, s);
+    }
+  }
+}
+
 // grid (ceil(Hin*Win / 256), N).  Thread = one input pixel, all input channels: dxn = sum_{co,ky,kx} dz[oy, ox] * w[co][ci][ky][kx]
+template <int STRIDE1>
 __global__ void __launch_bounds__(256)
 conv_bwd_x_kernel(const float* __restrict__ dz, const float* __restrict__ w, float* __restrict__ dxn, int Cin, int Hin, int Win,
                   int Cout, int K, int stride, int Ho, int Wo) {
@@ -239,21 +331,28 @@ conv_bwd_x_kernel(const float* __restrict__ dz, const float* __restrict__ w, flo
 #pragma unroll
   for (int ci = 0; ci < MAXC; ++ci) acc[ci] = 0.f;
   for (int ky = 0; ky < K; ++ky) {
-    const int ty = iy - ky;
-    if (ty < 0 || ty % stride) continue;
-    const int oy = ty / stride;
+    int oy = iy - ky;
+    if (oy < 0) continue;
+    if (!STRIDE1) {
+      if (oy % stride) continue;
+      oy /= stride;
+    }
     if (oy >= Ho) continue;
     for (int kx = 0; kx < K; ++kx) {
-      const int tx = ix - kx;
-      if (tx < 0 || tx % stride) continue;
-      const int ox = tx / stride;
+      int ox = ix - kx;
+      if (ox < 0) continue;
+      if (!STRIDE1) {
+        if (ox % stride) continue;
+        ox /= stride;
+      }
       if (ox >= Wo) continue;
+      const float* gp = dz + ((size_t)n * Cout * Ho + oy) * Wo + ox;
+      const float* wp = sw + ky * K + kx;
       for (int co = 0; co < Cout; ++co) {
-        const float g = dz[(((size_t)n * Cout + co) * Ho + oy) * Wo + ox];
-        const float* wp = sw + (size_t)co * Cin * K * K + ky * K + kx;
+        const float g = gp[(size_t)co * Ho * Wo];
 #pragma unroll
         for (int ci = 0; ci < MAXC; ++ci)
-          if (ci < Cin) acc[ci] = fmaf(g, wp[ci * K * K], acc[ci]);
+          if (ci < Cin) acc[ci] = fmaf(g, wp[(co * Cin + ci) * K * K], acc[ci]);
       }
     }
   }
@@ -269,6 +368,12 @@ static int conv_out(int in, int K, int stride) { return (in - K) / stride + 1; }
 
 using namespace mmqg;
 
+// stats: (mmqg_conv_stats_parts(...) x 2*Cout) floats of per-block partial sums (sum | sum of squares), or NULL
+extern "C" int mmqg_conv_stats_parts(int N, int Hin, int Win, int K, int stride) {
+  if (N <= 0 || Hin < K || Win < K || K < 1 || stride < 1) return 0;
+  return N * ceil_div(cs::conv_out(Hin, K, stride) * cs::conv_out(Win, K, stride), 256);
+}
+
 extern "C" int mmqg_conv_relu_fwd(const float* x, const float* in_scale, const float* in_shift, const float* w, const float* b, float* y,
                                   float* stats, int N, int Cin, int Hin, int Win, int Cout, int K, int stride, void* stream) {
   MMQG_REQUIRE(x && w && y && N > 0 && Cin > 0 && Cin <= cs::MAXC && Cout > 0 && Cout <= cs::MAXC && K >= 1 && K <= 5 && stride >= 1 &&
@@ -276,7 +381,6 @@ extern "C" int mmqg_conv_relu_fwd(const float* x, const float* in_scale, const f
                "conv_relu_fwd: unsupported shape N=%d Cin=%d Cout=%d K=%d stride=%d H=%d W=%d", N, Cin, Cout, K, stride, Hin, Win);
   cudaStream_t st = as_stream(stream);
   const int Ho = cs::conv_out(Hin, K, stride), Wo = cs::conv_out(Win, K, stride);
-  if (stats) MMQG_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, st));
   MMQG_PROBE(KC_OTHER, 2.0 * N * Ho * Wo * Cout * Cin * K * K, 4.0 * N * ((double)Cin * Hin * Win + (double)Cout * Ho * Wo));
   cs::conv_relu_fwd_kernel<<<dim3(ceil_div(Ho * Wo, 256), N), 256, 0, st>>>(x, in_scale, in_shift, w, b, y, stats, Cin, Hin, Win, Cout, K,
                                                                             stride, Ho, Wo);
@@ -284,13 +388,13 @@ extern "C" int mmqg_conv_relu_fwd(const float* x, const float* in_scale, const f
   return 0;
 }
 
-extern "C" int mmqg_bn_finalize(const float* stats, long long count, const float* gamma, const float* beta, float eps, float momentum,
-                                float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd, int C,
-                                void* stream) {
-  MMQG_REQUIRE(stats && scale && shift && mean && invstd && C > 0 && C <= cs::MAXC && count > 0, "bn_finalize: bad args");
+extern "C" int mmqg_bn_finalize(const float* stats_parts, int nparts, long long count, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                                float* invstd, int C, void* stream) {
+  MMQG_REQUIRE(stats_parts && nparts > 0 && scale && shift && mean && invstd && C > 0 && C <= cs::MAXC && count > 0, "bn_finalize: bad args");
   cudaStream_t st = as_stream(stream);
-  cs::bn_finalize_kernel<<<1, 32, 0, st>>>(stats, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
-                                           invstd, C);
+  cs::bn_finalize_kernel<<<C, 256, 0, st>>>(stats_parts, nparts, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                                            shift, mean, invstd, C);
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -354,8 +458,16 @@ extern "C" int mmqg_conv_bwd_w(const float* x, const float* in_scale, const floa
   int chunks = (int)((P + 256 * 16 - 1) / (256 * 16));
   if (chunks < 1) chunks = 1;
   if (chunks > 64) chunks = 64;
-  MMQG_PROBE(KC_OTHER, 2.0 * P * Cout * Cin * K * K, 4.0 * P * (Cout * Cin + (double)Cin * Cout * K * K));
-  cs::conv_bwd_w_kernel<<<dim3(Cout * Cin, chunks), 256, 0, st>>>(x, in_scale, in_shift, dz, dw, db, N, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
+  MMQG_PROBE(KC_OTHER, 2.0 * P * Cout * Cin * K * K, 4.0 * (N * (double)Cin * Hin * Win + (double)Cin * P * Cout));
+  if (K == 3) {
+    int cx = (int)((P + 256 * 32 - 1) / (256 * 32));
+    if (cx < 1) cx = 1;
+    if (cx > 148 * 2) cx = 148 * 2;
+    if (stride == 1) cs::conv_bwd_w3_kernel<1><<<dim3(cx, Cin), 256, 0, st>>>(x, in_scale, in_shift, dz, dw, db, N, Cin, Hin, Win, Cout, stride, Ho, Wo);
+    else cs::conv_bwd_w3_kernel<0><<<dim3(cx, Cin), 256, 0, st>>>(x, in_scale, in_shift, dz, dw, db, N, Cin, Hin, Win, Cout, stride, Ho, Wo);
+  } else {
+    cs::conv_bwd_w_kernel<<<dim3(Cout * Cin, chunks), 256, 0, st>>>(x, in_scale, in_shift, dz, dw, db, N, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
+  }
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -367,7 +479,8 @@ extern "C" int mmqg_conv_bwd_x(const float* dz, const float* w, float* dxn, int 
   cudaStream_t st = as_stream(stream);
   const int Ho = cs::conv_out(Hin, K, stride), Wo = cs::conv_out(Win, K, stride);
   MMQG_PROBE(KC_OTHER, 2.0 * N * Ho * Wo * Cout * Cin * K * K, 4.0 * N * ((double)Cin * Hin * Win + (double)Cout * Ho * Wo));
-  cs::conv_bwd_x_kernel<<<dim3(ceil_div(Hin * Win, 256), N), 256, 0, st>>>(dz, w, dxn, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
+  if (stride == 1) cs::conv_bwd_x_kernel<1><<<dim3(ceil_div(Hin * Win, 256), N), 256, 0, st>>>(dz, w, dxn, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
+  else cs::conv_bwd_x_kernel<0><<<dim3(ceil_div(Hin * Win, 256), N), 256, 0, st>>>(dz, w, dxn, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
   MMQG_LAUNCH_CHECK();
   return 0;
 }

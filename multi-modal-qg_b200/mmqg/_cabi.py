@@ -88,7 +88,8 @@ SYMBOLS = {
     "mmqg_colsum": (_i, [_fp, _i, _fp, _i, _i, _f, _fp]),
     "mmqg_pack_bf16": (_i, [_fp, _fp, _ll, _fp]),
     "mmqg_conv_relu_fwd": (_i, [_fp] * 7 + [_i] * 7 + [_fp]),
-    "mmqg_bn_finalize": (_i, [_fp, _ll, _fp, _fp, _f, _f] + [_fp] * 6 + [_i, _fp]),
+    "mmqg_conv_stats_parts": (_i, [_i] * 5),
+    "mmqg_bn_finalize": (_i, [_fp, _i, _ll, _fp, _fp, _f, _f] + [_fp] * 6 + [_i, _fp]),
     "mmqg_bn_maxpool_fwd": (_i, [_fp] * 5 + [_i] * 5 + [_fp]),
     "mmqg_maxpool_bwd": (_i, [_fp] * 3 + [_i] * 5 + [_fp]),
     "mmqg_bn_relu_bwd": (_i, [_fp] * 7 + [_i] * 4 + [_fp]),

@@ -268,14 +268,15 @@ def _p(t):
 
 
 def conv_relu_fwd(x, w, b, in_scale=None, in_shift=None, stride=1, want_stats=True):
-    """y = relu(conv2d(x * in_scale + in_shift, w) + b) on (N,Cin,H,W) fp32; returns (y, stats) with stats = per-channel
-    (sum, sum of squares) of y, 2*Cout floats (None when want_stats is False)."""
+    """y = relu(conv2d(x * in_scale + in_shift, w) + b) on (N,Cin,H,W) fp32; returns (y, stats) with stats = per-block partial
+    (sum | sum of squares) of y per channel, (nparts, 2*Cout) floats (None when want_stats is False)."""
     _chk(x, w, b, in_scale, in_shift)
     N, Cin, H, W = x.shape
     Cout, _, K, _ = w.shape
     Ho, Wo = (H - K) // stride + 1, (W - K) // stride + 1
     y = torch.empty(N, Cout, Ho, Wo, device=x.device, dtype=torch.float32)
-    stats = torch.empty(2 * Cout, device=x.device, dtype=torch.float32) if want_stats else None
+    nparts = lib().mmqg_conv_stats_parts(N, H, W, K, stride)
+    stats = torch.empty(nparts, 2 * Cout, device=x.device, dtype=torch.float32) if want_stats else None
     check(lib().mmqg_conv_relu_fwd(x.data_ptr(), _p(in_scale), _p(in_shift), w.data_ptr(), _p(b), y.data_ptr(), _p(stats),
                                    N, Cin, H, W, Cout, K, stride, _st()))
     return y, stats
@@ -283,9 +284,10 @@ def conv_relu_fwd(x, w, b, in_scale=None, in_shift=None, stride=1, want_stats=Tr
 
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var):
     """Train-mode BatchNorm2d statistics -> (scale, shift, mean, invstd); running stats updated in place (None = skip)."""
-    C_ = stats.numel() // 2
+    stats = stats.view(-1, stats.shape[-1]) if stats.dim() > 1 else stats.view(1, -1)
+    C_ = stats.shape[1] // 2
     out = [torch.empty(C_, device=stats.device, dtype=torch.float32) for _ in range(4)]
-    check(lib().mmqg_bn_finalize(stats.data_ptr(), int(count), _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
+    check(lib().mmqg_bn_finalize(stats.data_ptr(), stats.shape[0], int(count), _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
                                  _p(running_var), *[o.data_ptr() for o in out], C_, _st()))
     return out
 
