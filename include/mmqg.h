@@ -49,6 +49,9 @@ typedef enum {
 /* precision modes (SURVEY.md section 8d "Precision modes") */
 #define MMQG_MODE_FP32 0     /* fp32 storage, fp32 FMA accumulation: the parity mode   */
 #define MMQG_MODE_BF16 1     /* bf16 operands on tcgen05 tensor cores, fp32 accumulate */
+#define MMQG_MODE_FP32_TC 2  /* the fp32 parity path with every contraction on the tcgen05 tensor cores: operands split
+                              * into bf16 (hi, lo), three products hi*lo + lo*hi + hi*hi accumulated in fp32 (~2^-16
+                              * relative per product); fp32 storage, pointwise math and reductions as MMQG_MODE_FP32 */
 
 /* Shapes (SURVEY.md section 8 symbol table; reference config.py:64-87). */
 typedef struct {

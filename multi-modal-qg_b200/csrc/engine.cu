@@ -16,11 +16,13 @@
 //                    are never stored (train.py:174 + decoder.py:106 + their backward).
 //   backward       : per step only the pointwise cell gradient and dG W_hh (+ dG W_ih for
 //                    the layer below); all weight gradients are GEMMs over the stored dG.
+#include <algorithm>
 #include "kernels.h"
 
 namespace mmqg {
 
-static const int kSplit = 4;   // split-K slices of the skinny (B x H) per-step backward products
+static const int kSplitMax = 8; // split-K slices of the skinny (B x H) per-step backward products: 4 (SIMT), 8 (tensor-core parity mode)
+static const int kPreSplitMax = 4;
 
 struct Carver {
   char* base; size_t off;
@@ -46,6 +48,9 @@ struct Ws {
   float *dh_rec[MMQG_MAX_LAYERS], *dc[MMQG_MAX_LAYERS], *dx_above, *dq_h, *dctx_all, *dm_txt, *dm_vid, *de_dec;
   float *dh_rec_enc, *dh_rec_vid, *dx_text, *dc_v;
   float *xcat;
+  float* pre_part;                    // split-K partial pre-activations of one recurrent step (tensor-core parity mode)
+  void *x3_arena, *x3_sa, *x3_sb;     // MMQG_MODE_FP32_TC: split copies (gemm_f32x3.cu)
+  size_t x3_arena_bytes, x3_sa_bytes, x3_sb_bytes;
   int S_pad, Rc;
   size_t bytes;
 };
@@ -59,7 +64,7 @@ static int vocab_chunk_rows32(int R, int V) {
 }
 
 // T_q here is the number of decoder steps the buffers must hold (max_len for greedy).
-static Ws carve(const mmqg_dims& d, int T_q, void* base) {
+static Ws carve(const mmqg_dims& d, int T_q, void* base, bool tc = false) {
   Ws w{};
   Carver c{reinterpret_cast<char*>(base), 0};
   const size_t B = d.B, H = d.H, G = 4 * (size_t)d.H, Gv = 4 * (size_t)d.H_v;
@@ -103,19 +108,38 @@ static Ws carve(const mmqg_dims& d, int T_q, void* base) {
   w.logits = c.take<float>((size_t)w.Rc * d.V);
   w.nll = c.take<float>(R);
   w.dhtop = c.take<float>(R * H);
-  for (int l = 0; l < d.L; ++l) { w.dh_rec[l] = c.take<float>(kSplit * B * H); w.dc[l] = c.take<float>(B * H); }
-  w.dx_above = c.take<float>(kSplit * B * H);
-  w.dq_h = c.take<float>(kSplit * B * H);
+  for (int l = 0; l < d.L; ++l) { w.dh_rec[l] = c.take<float>(kSplitMax * B * H); w.dc[l] = c.take<float>(B * H); }
+  w.dx_above = c.take<float>(kSplitMax * B * H);
+  w.dq_h = c.take<float>(kSplitMax * B * H);
   w.dctx_all = c.take<float>(R * C);
   w.dm_txt = c.take<float>(B * d.TM * H);
   w.dm_vid = c.take<float>(B * d.AM * d.H_v);
   w.de_dec = c.take<float>(R * d.E);
-  w.dh_rec_enc = c.take<float>(kSplit * B * H);
-  w.dh_rec_vid = c.take<float>(kSplit * B * d.H_v);
+  w.dh_rec_enc = c.take<float>(kSplitMax * B * H);
+  w.dh_rec_vid = c.take<float>(kSplitMax * B * d.H_v);
   w.dx_text = c.take<float>((size_t)d.T_t * B * (d.E > d.H ? d.E : d.H));
   w.dc_v = c.take<float>(B * d.H_v);
   w.xcat = c.take<float>(B * X0);
   for (int l = 0; l + 1 < d.L; ++l) { w.xdrop_text[l] = c.take<float>((size_t)d.T_t * B * H); w.hdrop_dec[l] = c.take<float>(R * H); }
+  if (tc) {
+    // constant operands: every GEMM weight once per layout (forward (N,K) and backward (K,N) roles), column slices padded
+    auto ent = [](size_t r, size_t cc) { return 4 * (r + 8) * (cc + 16) + 512; };
+    size_t wb = ent(Gv, d.F_v) + ent(Gv, d.H_v) + ent(d.V, H) + ent(w.S_pad, Q) + ent(w.S_pad, 16);
+    for (int l = 0; l < d.L; ++l)
+      wb += ent(G, l == 0 ? d.E : H) + ent(G, H) + ent(G, l == 0 ? X0 + 16 : H) + ent(G, H);
+    w.x3_arena_bytes = 2 * wb + (1u << 20);
+    const long long NB = (long long)d.T_t * B > (long long)R ? (long long)d.T_t * B : (long long)R;
+    const long long Km = std::max<long long>(std::max<long long>(G + w.S_pad, Gv), std::max<long long>(X0, d.F_v + d.H_v));
+    size_t sa = std::max(f32x3_split_bytes(0, NB, Km), f32x3_split_bytes(1, Km, NB));
+    sa = std::max(sa, std::max(f32x3_split_bytes(0, w.Rc, d.V), f32x3_split_bytes(1, d.V, w.Rc)));
+    w.x3_sa_bytes = sa + 4096;
+    size_t sb = std::max(f32x3_split_bytes(1, std::max<long long>(X0, H), NB), f32x3_split_bytes(1, d.F_v, B));
+    w.x3_sb_bytes = sb + 4096;
+    w.pre_part = c.take<float>((size_t)kPreSplitMax * B * std::max(G, Gv));
+    w.x3_arena = c.take<char>(w.x3_arena_bytes);
+    w.x3_sa = c.take<char>(w.x3_sa_bytes);
+    w.x3_sb = c.take<char>(w.x3_sb_bytes);
+  }
   w.bytes = align_up(c.off, 256);
   return w;
 }
@@ -142,8 +166,12 @@ static int check_tensors(const mmqg_dims& d, const mmqg_tensors* t, const char* 
 }
 
 // GEMM call helper ------------------------------------------------------------------------
+// MMQG_MODE_FP32_TC: the contractions of the current call run on the tensor cores (bf16 split, gemm_f32x3.cu)
+static thread_local bool g32_tc = false;
+
 struct GemmCall {
   mmqg_gemm_args a;
+  bool b_const = false;
   GemmCall(const float* A, int lda, bool tA, const float* Bm, int ldb, bool tB, int M, int N, int K, float* C, int ldc) {
     a = mmqg_gemm_args{};
     a.A = A; a.lda = lda; a.transA = tA; a.B = Bm; a.ldb = ldb; a.transB = tB;
@@ -156,8 +184,24 @@ struct GemmCall {
   GemmCall& accumulate(bool on) { if (on) { a.Cin = a.C; a.ldcin = a.ldc; a.beta = 1.f; } return *this; }
   GemmCall& bias(const float* b) { a.bias = b; return *this; }
   GemmCall& split(int s, long long stride) { a.split_k = s; a.c_split_stride = stride; return *this; }
-  int run(cudaStream_t st) { return gemm_f32(a, st); }
+  GemmCall& w() { b_const = true; return *this; }      // B (and B2) are parameters: constant during the call
+  int run(cudaStream_t st) { return g32_tc ? gemm_f32x3(a, b_const, st) : gemm_f32(a, st); }
 };
+
+// Tensor-core parity mode: the (B x 4H) pre-activation product of one recurrent step is issued split-K so that ~128 SMs
+// pull operands instead of ceil(B/128) * 4H/64; the partial sums go to `part` and the cell kernel adds them
+// (to the hoisted input projection already in `gates`, or to `bias`).  Returns the PreSpec for lstm_pointwise_fwd.
+static int step_pre_tc(GemmCall& g, float* part, int M, int N, const float* bias, bool add_gates, PreSpec* ps, cudaStream_t st) {
+  const int base = ceil_div(M, 128) * ceil_div(N, 64);
+  int S = 148 / base;
+  S = S < 1 ? 1 : (S > kPreSplitMax ? kPreSplitMax : S);
+  g.a.C = part; g.a.ldc = N; g.a.Cin = nullptr; g.a.beta = 0.f; g.a.bias = nullptr;
+  g.split(S, (long long)M * N).w();
+  MMQG_TRY(g.run(st));
+  *ps = PreSpec{};
+  ps->part = part; ps->n_part = S; ps->ld = N; ps->stride = (long long)M * N; ps->bias = bias; ps->add_gates = add_gates ? 1 : 0;
+  return 0;
+}
 
 // inter-layer dropout of the current call (0 = off); stream ids as in engine_bf16.cu
 static thread_local float g32_drop_p = 0.f;
@@ -180,14 +224,17 @@ static int encoder_forward(const mmqg_dims& d, const mmqg_tensors& P, const mmqg
   MMQG_TRY(add2(P.vid_b_ih, P.vid_b_hh, w.bsum_vid, Gv, st));
   for (int t = 0; t < d.T_v; ++t) {
     StepGemmScope step_scope;
+    PdlScope pdl_scope(g32_tc && pdl_enabled());
     float* acts = w.acts_v + (size_t)t * B * Gv;
     GemmCall g(bt.frames + (size_t)t * d.F_v, d.T_v * d.F_v, false, P.vid_w_ih, d.F_v, true, B, Gv, d.F_v, acts, Gv);
     g.bias(w.bsum_vid);
     if (t > 0) g.second(w.hs_v + (size_t)t * B * Hv, Hv, P.vid_w_hh, Hv, Hv);
-    MMQG_TRY(g.run(st));
+    PreSpec ps;
+    if (g32_tc) MMQG_TRY(step_pre_tc(g, w.pre_part, B, Gv, w.bsum_vid, false, &ps, st));
+    else MMQG_TRY(g.w().run(st));
     MMQG_TRY(lstm_pointwise_fwd(acts, Gv, t > 0 ? w.cs_v + (size_t)t * B * Hv : nullptr, Hv,
                                 w.cs_v + (size_t)(t + 1) * B * Hv, Hv, w.hs_v + (size_t)(t + 1) * B * Hv, Hv,
-                                w.m_vid + (size_t)t * Hv, d.AM * Hv, B, Hv, st));
+                                w.m_vid + (size_t)t * Hv, d.AM * Hv, B, Hv, st, ps));
   }
   // text LSTM stack
   MMQG_TRY(embedding_gather(P.emb, w.idx_ctx, w.x0_text, d.E, d.T_t * B, d.E, d.V, st));
@@ -199,16 +246,20 @@ static int encoder_forward(const mmqg_dims& d, const mmqg_tensors& P, const mmqg
     const float* X = l == 0 ? w.x0_text : (g32_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);
     const int I = l == 0 ? d.E : H;
     MMQG_TRY(GemmCall(X, I, false, P.text_w_ih[l], I, true, d.T_t * B, G, I, w.acts_text[l], G)
-                 .bias(w.bsum_text[l]).run(st));
+                 .bias(w.bsum_text[l]).w().run(st));
     for (int t = 0; t < d.T_t; ++t) {
       StepGemmScope step_scope;
+      PdlScope pdl_scope(g32_tc && pdl_enabled());
       float* acts = w.acts_text[l] + (size_t)t * B * G;
-      if (t > 0)
-        MMQG_TRY(GemmCall(w.hs_text[l] + (size_t)t * B * H, H, false, P.text_w_hh[l], H, true, B, G, H, acts, G)
-                     .accumulate(true).run(st));
+      PreSpec ps;
+      if (t > 0) {
+        GemmCall g(w.hs_text[l] + (size_t)t * B * H, H, false, P.text_w_hh[l], H, true, B, G, H, acts, G);
+        if (g32_tc) MMQG_TRY(step_pre_tc(g, w.pre_part, B, G, nullptr, true, &ps, st));
+        else MMQG_TRY(g.accumulate(true).w().run(st));
+      }
       MMQG_TRY(lstm_pointwise_fwd(acts, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr, H,
                                   w.cs_text[l] + (size_t)(t + 1) * B * H, H, w.hs_text[l] + (size_t)(t + 1) * B * H, H,
-                                  l == d.L - 1 ? w.m_txt + (size_t)t * H : nullptr, d.TM * H, B, H, st));
+                                  l == d.L - 1 ? w.m_txt + (size_t)t * H : nullptr, d.TM * H, B, H, st, ps));
     }
   }
   return 0;
@@ -246,13 +297,13 @@ extern "C" {
 size_t mmqg_train_workspace_bytes(const mmqg_dims* d, int mode) {
   if (check_dims(d) != 0) return 0;
   if (mode == MMQG_MODE_BF16) return check_dims_bf16(*d) == 0 ? train_workspace_bytes_bf16(*d, d->T_q) : 0;
-  return carve(*d, d->T_q, nullptr).bytes;
+  return carve(*d, d->T_q, nullptr, mode == MMQG_MODE_FP32_TC).bytes;
 }
 
 size_t mmqg_greedy_workspace_bytes(const mmqg_dims* d, int max_len, int mode) {
   if (check_dims(d) != 0 || max_len <= 0) return 0;
   if (mode == MMQG_MODE_BF16) return check_dims_bf16(*d) == 0 ? greedy_workspace_bytes_bf16(*d, max_len) : 0;
-  return carve(*d, max_len, nullptr).bytes;
+  return carve(*d, max_len, nullptr, mode == MMQG_MODE_FP32_TC).bytes;
 }
 
 int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mmqg_batch* batch, void* workspace,
@@ -263,7 +314,7 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   MMQG_TRY(check_tensors(d, params, "params"));
   MMQG_REQUIRE(batch && batch->context && batch->target && batch->frames && batch->audio, "batch: null pointer");
   MMQG_REQUIRE(workspace && loss_out, "null workspace / loss_out");
-  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
+  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16 || mode == MMQG_MODE_FP32_TC, "unknown mode %d", mode);
   MMQG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p=%g not in [0,1)", dropout_p);
   if (want_grads) MMQG_TRY(check_tensors(d, grads, "grads"));
   if (mode == MMQG_MODE_BF16)
@@ -272,7 +323,9 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   g32_drop_p = dropout_p;
   g32_drop_seed = seed;
   MMQG_REQUIRE(!batch->ctx_len && !batch->tgt_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
-  Ws w = carve(d, d.T_q, workspace);
+  g32_tc = mode == MMQG_MODE_FP32_TC;
+  Ws w = carve(d, d.T_q, workspace, g32_tc);
+  if (g32_tc) f32x3_bind(w.x3_arena, w.x3_arena_bytes, w.x3_sa, w.x3_sa_bytes, w.x3_sb, w.x3_sb_bytes);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   cudaStream_t st = as_stream(stream);
@@ -289,29 +342,35 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   // decoder: hoisted embedding-column products over all teacher-forced steps
   MMQG_TRY(embedding_gather(P.emb, w.idx_dec, w.e_dec, E, R, E, d.V, st));
   for (int l = 0; l < d.L; ++l) MMQG_TRY(add2(P.dec_b_ih[l], P.dec_b_hh[l], w.bsum_dec[l], G, st));
-  MMQG_TRY(GemmCall(w.e_dec, E, false, P.dec_w_ih[0], X0, true, R, G, E, w.acts_dec[0], G).bias(w.bsum_dec[0]).run(st));
-  MMQG_TRY(GemmCall(w.e_dec, E, false, w.attn_w_cat, Q, true, R, Sp, E, w.attn_all, Sp).bias(w.attn_b_cat).run(st));
+  MMQG_TRY(GemmCall(w.e_dec, E, false, P.dec_w_ih[0], X0, true, R, G, E, w.acts_dec[0], G).bias(w.bsum_dec[0]).w().run(st));
+  MMQG_TRY(GemmCall(w.e_dec, E, false, w.attn_w_cat, Q, true, R, Sp, E, w.attn_all, Sp).bias(w.attn_b_cat).w().run(st));
   const AttnShape as = attn_shape(d);
   for (int t = 0; t < d.T_q; ++t) {
     StepGemmScope step_scope;
+    PdlScope pdl_scope(g32_tc && pdl_enabled());
     const float* htop_prev = w.hs_dec[d.L - 1] + (size_t)t * B * H;
     float* sc = w.attn_all + (size_t)t * B * Sp;
     float* ctx = w.ctx_all + (size_t)t * B * C;
-    MMQG_TRY(GemmCall(htop_prev, H, false, w.attn_w_cat + E, Q, true, B, Sp, H, sc, Sp).accumulate(true).run(st));
+    MMQG_TRY(GemmCall(htop_prev, H, false, w.attn_w_cat + E, Q, true, B, Sp, H, sc, Sp).accumulate(true).w().run(st));
     MMQG_TRY(attn_fwd(sc, Sp, w.m_txt, w.m_aud, w.m_vid, ctx, C, as, st));
     for (int l = 0; l < d.L; ++l) {
       float* acts = w.acts_dec[l] + (size_t)t * B * G;
       const float* hprev = w.hs_dec[l] + (size_t)t * B * H;
+      PreSpec ps;
       if (l == 0) {
-        MMQG_TRY(GemmCall(ctx, C, false, P.dec_w_ih[0] + E, X0, true, B, G, C, acts, G)
-                     .second(hprev, H, P.dec_w_hh[0], H, H).accumulate(true).run(st));
+        GemmCall g(ctx, C, false, P.dec_w_ih[0] + E, X0, true, B, G, C, acts, G);
+        g.second(hprev, H, P.dec_w_hh[0], H, H);
+        if (g32_tc) MMQG_TRY(step_pre_tc(g, w.pre_part, B, G, nullptr, true, &ps, st));
+        else MMQG_TRY(g.accumulate(true).w().run(st));
       } else {
         const float* xin = g32_drop_p > 0.f ? w.hdrop_dec[l - 1] + (size_t)t * B * H : w.hs_dec[l - 1] + (size_t)(t + 1) * B * H;
-        MMQG_TRY(GemmCall(xin, H, false, P.dec_w_ih[l], H, true, B, G, H, acts, G)
-                     .second(hprev, H, P.dec_w_hh[l], H, H).bias(w.bsum_dec[l]).run(st));
+        GemmCall g(xin, H, false, P.dec_w_ih[l], H, true, B, G, H, acts, G);
+        g.second(hprev, H, P.dec_w_hh[l], H, H);
+        if (g32_tc) MMQG_TRY(step_pre_tc(g, w.pre_part, B, G, w.bsum_dec[l], false, &ps, st));
+        else MMQG_TRY(g.bias(w.bsum_dec[l]).w().run(st));
       }
       MMQG_TRY(lstm_pointwise_fwd(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
-                                  w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st));
+                                  w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st, ps));
       if (g32_drop_p > 0.f && l + 1 < d.L)      // decoder.py:69: dropout between the LSTM layers
         MMQG_TRY(dropout_f32(w.hs_dec[l] + (size_t)(t + 1) * B * H, w.hdrop_dec[l] + (size_t)t * B * H, (long long)B * H, g32_drop_seed,
                              w.seed_ctr, kSidDec32 + l, (unsigned long long)t * B * H, g32_drop_p, st));
@@ -322,10 +381,10 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   const float dscale = want_grads ? grad_scale / (float)B : 0.f;
   for (int r0 = 0, first = 1; r0 < R; r0 += w.Rc, first = 0) {
     const int rc = R - r0 < w.Rc ? R - r0 : w.Rc;
-    MMQG_TRY(GemmCall(htop + (size_t)r0 * H, H, false, P.out_w, H, true, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(st));
+    MMQG_TRY(GemmCall(htop + (size_t)r0 * H, H, false, P.out_w, H, true, rc, d.V, H, w.logits, d.V).bias(P.out_b).w().run(st));
     MMQG_TRY(nll_rows(w.logits, d.V, w.tgt_tm + r0, 1, w.nll + r0, rc, d.V, dscale, st));
     if (want_grads) {
-      MMQG_TRY(GemmCall(w.logits, d.V, false, P.out_w, H, false, rc, H, d.V, w.dhtop + (size_t)r0 * H, H).run(st));
+      MMQG_TRY(GemmCall(w.logits, d.V, false, P.out_w, H, false, rc, H, d.V, w.dhtop + (size_t)r0 * H, H).w().run(st));
       MMQG_TRY(GemmCall(w.logits, d.V, true, htop + (size_t)r0 * H, H, false, d.V, H, rc, grads->out_w, H)
                    .accumulate(!first).run(st));
       MMQG_TRY(colsum(w.logits, d.V, grads->out_b, nullptr, rc, d.V, first ? 0.f : 1.f, st));
@@ -374,7 +433,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   MMQG_TRY(check_tensors(d, grads, "grads"));
   MMQG_REQUIRE(batch && batch->frames, "batch: null pointer");
   MMQG_REQUIRE(workspace, "null workspace");
-  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
+  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16 || mode == MMQG_MODE_FP32_TC, "unknown mode %d", mode);
   MMQG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p=%g not in [0,1)", dropout_p);
   MMQG_REQUIRE(phase >= 0 && phase <= 3, "phase %d not in 0..3", phase);
   if (mode == MMQG_MODE_BF16)
@@ -382,7 +441,9 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   g32_drop_p = dropout_p;
   g32_drop_seed = seed;
   MMQG_REQUIRE(!batch->ctx_len && !batch->tgt_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
-  Ws w = carve(d, d.T_q, workspace);
+  g32_tc = mode == MMQG_MODE_FP32_TC;
+  Ws w = carve(d, d.T_q, workspace, g32_tc);
+  if (g32_tc) f32x3_bind(w.x3_arena, w.x3_arena_bytes, w.x3_sa, w.x3_sa_bytes, w.x3_sb, w.x3_sb_bytes);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   cudaStream_t st = as_stream(stream);
@@ -390,6 +451,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   mmqg_tensors& Gd = *grads;
   const int B = d.B, H = d.H, G = 4 * d.H, E = d.E, Q = d.E + d.H, C = d.H + d.H_a + d.H_v, X0 = E + C;
   const int R = d.T_q * B, Sp = w.S_pad, L = d.L;
+  const int kSplit = g32_tc ? kSplitMax : 4;
   const long long ps = (long long)B * H;       // split-K partial stride for (B,H) products
   const AttnShape as = attn_shape(d);
 
@@ -405,6 +467,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
     if (Sp != d.TM + 2 * d.AM) MMQG_CUDA(cudaMemsetAsync(w.ds_all, 0, sizeof(float) * (size_t)R * Sp, st));
     for (int t = d.T_q - 1; t >= 0; --t) {
       StepGemmScope step_scope;
+      PdlScope pdl_scope(g32_tc && pdl_enabled());
       const bool last = t == d.T_q - 1;
       for (int l = L - 1; l >= 0; --l) {
         float* acts = w.acts_dec[l] + (size_t)t * B * G;
@@ -422,18 +485,18 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
         }
         MMQG_TRY(lstm_pointwise_bwd(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
                                     dh0, H, kSplit, ps, dh1, H, n1, ps, dh2, H, w.dc[l], H, last ? 1 : 0, B, H, st));
-        MMQG_TRY(GemmCall(acts, G, false, P.dec_w_hh[l], H, false, B, H, G, w.dh_rec[l], H).split(kSplit, ps).run(st));
+        MMQG_TRY(GemmCall(acts, G, false, P.dec_w_hh[l], H, false, B, H, G, w.dh_rec[l], H).split(kSplit, ps).w().run(st));
         if (l > 0)
-          MMQG_TRY(GemmCall(acts, G, false, P.dec_w_ih[l], H, false, B, H, G, w.dx_above, H).split(kSplit, ps).run(st));
+          MMQG_TRY(GemmCall(acts, G, false, P.dec_w_ih[l], H, false, B, H, G, w.dx_above, H).split(kSplit, ps).w().run(st));
         else
-          MMQG_TRY(GemmCall(acts, G, false, P.dec_w_ih[0] + E, X0, false, B, C, G, w.dctx_all + (size_t)t * B * C, C).run(st));
+          MMQG_TRY(GemmCall(acts, G, false, P.dec_w_ih[0] + E, X0, false, B, C, G, w.dctx_all + (size_t)t * B * C, C).w().run(st));
       }
       // dS(t) goes to its own buffer: the softmax weights are needed again by the hoisted
       // memory gradients (attn_dmem) after the loop.
       float* ds = w.ds_all + (size_t)t * B * Sp;
       MMQG_TRY(attn_bwd(w.attn_all + (size_t)t * B * Sp, ds, Sp, w.dctx_all + (size_t)t * B * C, C, w.m_txt, w.m_aud,
                         w.m_vid, nullptr, nullptr, as, st));
-      MMQG_TRY(GemmCall(ds, Sp, false, w.attn_w_cat + E, Q, false, B, H, Sp, w.dq_h, H).split(kSplit, ps).run(st));
+      MMQG_TRY(GemmCall(ds, Sp, false, w.attn_w_cat + E, Q, false, B, H, Sp, w.dq_h, H).split(kSplit, ps).w().run(st));
     }
     // ---- hoisted decoder weight gradients over all steps ----
     for (int l = 0; l < L; ++l) {
@@ -461,7 +524,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
     }
     // embedding gradient, decoder side: dE = dG0 W_ih_l0[:, :E] + dS W_attn[:, :E]
     MMQG_TRY(GemmCall(w.acts_dec[0], G, false, P.dec_w_ih[0], X0, false, R, E, G, w.de_dec, E)
-                 .second(w.ds_all, Sp, w.attn_w_cat, Q, Sp).run(st));
+                 .second(w.ds_all, Sp, w.attn_w_cat, Q, Sp).w().run(st));
     MMQG_CUDA(cudaMemsetAsync(Gd.emb, 0, sizeof(float) * (size_t)d.V * E, st));
     MMQG_TRY(embedding_scatter_add(Gd.emb, w.idx_dec, w.de_dec, R, E, d.V, st));
     return 0;
@@ -473,6 +536,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
     const long long pv = (long long)B * Hv;
     for (int t = d.T_v - 1; t >= 0; --t) {
       StepGemmScope step_scope;
+      PdlScope pdl_scope(g32_tc && pdl_enabled());
       const bool last = t == d.T_v - 1;
       float* acts = w.acts_v + (size_t)t * B * Gv;
       MMQG_TRY(lstm_pointwise_bwd(acts, Gv, t > 0 ? w.cs_v + (size_t)t * B * Hv : nullptr, Hv,
@@ -480,7 +544,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
                                   nullptr, 0, 0, 0, w.dm_vid + (size_t)t * Hv, d.AM * Hv, w.dc_v, Hv, last ? 1 : 0, B, Hv,
                                   st));
       if (t > 0)
-        MMQG_TRY(GemmCall(acts, Gv, false, P.vid_w_hh, Hv, false, B, Hv, Gv, w.dh_rec_vid, Hv).split(kSplit, pv).run(st));
+        MMQG_TRY(GemmCall(acts, Gv, false, P.vid_w_hh, Hv, false, B, Hv, Gv, w.dh_rec_vid, Hv).split(kSplit, pv).w().run(st));
     }
     if (d.T_v > 1)
       MMQG_TRY(GemmCall(w.acts_v + (size_t)B * Gv, Gv, true, w.hs_v + (size_t)B * Hv, Hv, false, Gv, Hv, (d.T_v - 1) * B,
@@ -501,6 +565,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
       MMQG_TRY(dropout_scale_f32(w.dx_text, 1, 0, (long long)d.T_t * B * H, g32_drop_seed, w.seed_ctr, kSidText32 + l, 0, g32_drop_p, st));
     for (int t = d.T_t - 1; t >= 0; --t) {
       StepGemmScope step_scope;
+      PdlScope pdl_scope(g32_tc && pdl_enabled());
       const bool last = t == d.T_t - 1;
       float* acts = w.acts_text[l] + (size_t)t * B * G;
       // At the last encoder step the recurrent gradient is the decoder's gradient w.r.t. its
@@ -513,7 +578,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
                                   w.cs_text[l] + (size_t)(t + 1) * B * H, H, dh0, H, kSplit, ps, dh1, H, kSplit, ps, dh2,
                                   ldh2, w.dc[l], H, 0, B, H, st));
       if (t > 0)
-        MMQG_TRY(GemmCall(acts, G, false, P.text_w_hh[l], H, false, B, H, G, w.dh_rec_enc, H).split(kSplit, ps).run(st));
+        MMQG_TRY(GemmCall(acts, G, false, P.text_w_hh[l], H, false, B, H, G, w.dh_rec_enc, H).split(kSplit, ps).w().run(st));
     }
     const float* dG = w.acts_text[l];
     const float* X = l == 0 ? w.x0_text : (g32_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);
@@ -525,7 +590,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
       MMQG_CUDA(cudaMemsetAsync(Gd.text_w_hh[l], 0, sizeof(float) * (size_t)G * H, st));
     MMQG_TRY(colsum(dG, G, Gd.text_b_ih[l], Gd.text_b_hh[l], d.T_t * B, G, 0.f, st));
     // input gradient for the layer below (or the embedding rows)
-    MMQG_TRY(GemmCall(dG, G, false, P.text_w_ih[l], I, false, d.T_t * B, I, G, w.dx_text, I).run(st));
+    MMQG_TRY(GemmCall(dG, G, false, P.text_w_ih[l], I, false, d.T_t * B, I, G, w.dx_text, I).w().run(st));
   }
   MMQG_TRY(embedding_scatter_add(Gd.emb, w.idx_ctx, w.dx_text, d.T_t * B, E, d.V, st));
   return 0;
@@ -554,12 +619,14 @@ static int decode_impl(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   MMQG_TRY(check_tensors(d, params, "params"));
   MMQG_REQUIRE(batch && batch->context && batch->frames && batch->audio, "batch: null pointer");
   MMQG_REQUIRE(workspace && tokens_out && max_len > 0, "greedy: bad args");
-  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16, "unknown mode %d", mode);
+  MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16 || mode == MMQG_MODE_FP32_TC, "unknown mode %d", mode);
   if (mode == MMQG_MODE_BF16)
     return greedy_decode_bf16(d, *params, *batch, workspace, workspace_bytes, tokens_out, max_len, as_stream(stream), sample, seed);
   MMQG_REQUIRE(!batch->ctx_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
   g32_drop_p = 0.f;      // decoding is eval mode: no dropout
-  Ws w = carve(d, max_len, workspace);
+  g32_tc = mode == MMQG_MODE_FP32_TC;
+  Ws w = carve(d, max_len, workspace, g32_tc);
+  if (g32_tc) f32x3_bind(w.x3_arena, w.x3_arena_bytes, w.x3_sa, w.x3_sa_bytes, w.x3_sb, w.x3_sb_bytes);
   if (w.bytes > workspace_bytes)
     return set_err(MMQG_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, w.bytes);
   cudaStream_t st = as_stream(stream);
@@ -580,22 +647,25 @@ static int decode_impl(const mmqg_dims* dp, const mmqg_tensors* params, const mm
     const float* htop_prev = w.hs_dec[d.L - 1] + (size_t)t * B * H;
     float* sc = w.attn_all + (size_t)t * B * Sp;
     MMQG_TRY(GemmCall(w.xcat, X0, false, w.attn_w_cat, Q, true, B, Sp, E, sc, Sp)
-                 .second(htop_prev, H, w.attn_w_cat + E, Q, H).bias(w.attn_b_cat).run(st));
+                 .second(htop_prev, H, w.attn_w_cat + E, Q, H).bias(w.attn_b_cat).w().run(st));
     MMQG_TRY(attn_fwd(sc, Sp, w.m_txt, w.m_aud, w.m_vid, w.xcat + E, X0, as, st));
     for (int l = 0; l < d.L; ++l) {
       float* acts = w.acts_dec[l] + (size_t)t * B * G;
       const float* hprev = w.hs_dec[l] + (size_t)t * B * H;
       const float* x = l == 0 ? w.xcat : w.hs_dec[l - 1] + (size_t)(t + 1) * B * H;
       const int I = l == 0 ? X0 : H;
-      MMQG_TRY(GemmCall(x, I, false, P.dec_w_ih[l], I, true, B, G, I, acts, G)
-                   .second(hprev, H, P.dec_w_hh[l], H, H).bias(w.bsum_dec[l]).run(st));
+      PreSpec ps;
+      GemmCall g(x, I, false, P.dec_w_ih[l], I, true, B, G, I, acts, G);
+      g.second(hprev, H, P.dec_w_hh[l], H, H);
+      if (g32_tc) MMQG_TRY(step_pre_tc(g, w.pre_part, B, G, w.bsum_dec[l], false, &ps, st));
+      else MMQG_TRY(g.bias(w.bsum_dec[l]).w().run(st));
       MMQG_TRY(lstm_pointwise_fwd(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
-                                  w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st));
+                                  w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st, ps));
     }
     const float* htop = w.hs_dec[d.L - 1] + (size_t)(t + 1) * B * H;
     for (int r0 = 0; r0 < B; r0 += w.Rc) {
       const int rc = B - r0 < w.Rc ? B - r0 : w.Rc;
-      MMQG_TRY(GemmCall(htop + (size_t)r0 * H, H, false, P.out_w, H, true, rc, d.V, H, w.logits, d.V).bias(P.out_b).run(st));
+      MMQG_TRY(GemmCall(htop + (size_t)r0 * H, H, false, P.out_w, H, true, rc, d.V, H, w.logits, d.V).bias(P.out_b).w().run(st));
       if (sample)
         MMQG_TRY(sample_rows(w.logits, d.V, tokens_out + (size_t)r0 * max_len + t, max_len, w.idx_cur + r0, rc, d.V, seed,
                              (unsigned long long)t, r0, B, st));

@@ -6,9 +6,23 @@ namespace mmqg {
 
 int gemm_f32(const mmqg_gemm_args& a, cudaStream_t st);
 int gemm_bf16(const mmqg_gemm_bf16_args& a, cudaStream_t st);
+// fp32 contraction on the tensor cores by bf16 splitting (gemm_f32x3.cu); b_const: B/B2 are constant during the current
+// C-ABI call and their split copy is cached in the arena bound by f32x3_bind (which also forgets the previous call's copies)
+int gemm_f32x3(const mmqg_gemm_args& a, bool b_const, cudaStream_t st);
+void f32x3_bind(void* arena, size_t arena_bytes, void* sa, size_t sa_bytes, void* sb, size_t sb_bytes);
+size_t f32x3_split_bytes(int mn, long long n, long long K);
 
+// Pre-activations handed to the forward cell kernel as split-K partial sums: pre = (gates if
+// add_gates) + bias + sum_k part[k*stride + b*ld + .]; the activated gates still land in `gates`.
+struct PreSpec {
+  const float* part = nullptr;
+  int n_part = 0, ld = 0;
+  long long stride = 0;
+  const float* bias = nullptr;
+  int add_gates = 0;
+};
 int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
-                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st);
+                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, PreSpec ps = PreSpec());
 int lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                        const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,
                        const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, int B, int H,
@@ -60,15 +74,6 @@ struct DropSpec {
   const unsigned long long* ctr = nullptr;   // device call counter added to seed (fresh masks per step, also under graph replay)
   int sid = 0;
   float p = 0.f;
-};
-// Pre-activations handed to the forward cell kernel as split-K partial sums: pre = (gates if
-// add_gates) + bias + sum_k part[k*stride + b*ld + .]; the activated gates still land in `gates`.
-struct PreSpec {
-  const float* part = nullptr;
-  int n_part = 0, ld = 0;
-  long long stride = 0;
-  const float* bias = nullptr;
-  int add_gates = 0;
 };
 int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, void* h_out,
                             int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, DropSpec dr = DropSpec(),

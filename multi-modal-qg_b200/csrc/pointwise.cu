@@ -3,7 +3,7 @@
 //   embedding gather/scatter  : encoder.py:96, decoder.py:75 and embedding_dense_backward
 //   nll_rows / argmax_rows    : train.py:174 (CrossEntropyLoss), train.py:107-108 (greedy)
 //   colsum                    : bias gradients
-#include "common.cuh"
+#include "kernels.h"
 
 namespace mmqg {
 
@@ -21,15 +21,27 @@ int set_err(int code, const char* fmt, ...) {
 // ----------------------------------------------------------------------------------------
 __global__ void lstm_pointwise_fwd_kernel(float* __restrict__ gates, int ldg, const float* __restrict__ c_prev,
                                           int ldcp, float* __restrict__ c_out, int ldc, float* __restrict__ h_out,
-                                          int ldh, float* __restrict__ h2, int ldh2, int B, int H) {
+                                          int ldh, float* __restrict__ h2, int ldh2, int B, int H, PreSpec ps) {
+  pdl_launch_dependents();
+  pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, j = idx % H;
   float* g = gates + (size_t)b * ldg;
-  float i = sigmoidf_acc(g[j]);
-  float f = sigmoidf_acc(g[H + j]);
-  float gg = tanhf(g[2 * H + j]);
-  float o = sigmoidf_acc(g[3 * H + j]);
+  float pre[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pre[q] = (ps.n_part == 0 || ps.add_gates) ? g[q * H + j] : 0.f;
+  if (ps.n_part > 0) {      // pre-activations arrive (partly) as split-K partial sums
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (ps.bias) pre[q] += ps.bias[q * H + j];
+      for (int s = 0; s < ps.n_part; ++s) pre[q] += ps.part[(size_t)s * ps.stride + (size_t)b * ps.ld + q * H + j];
+    }
+  }
+  float i = sigmoidf_acc(pre[0]);
+  float f = sigmoidf_acc(pre[1]);
+  float gg = tanhf(pre[2]);
+  float o = sigmoidf_acc(pre[3]);
   float cp = c_prev ? c_prev[(size_t)b * ldcp + j] : 0.f;
   float c = f * cp + i * gg;
   float h = o * tanhf(c);
@@ -44,6 +56,8 @@ __global__ void lstm_pointwise_bwd_kernel(float* __restrict__ acts, int ldg, con
                                           const float* __restrict__ dh0, int ldh0, int n0, long long s0,
                                           const float* __restrict__ dh1, int ldh1, int n1, long long s1, const float* __restrict__ dh2,
                                           int ldh2, float* __restrict__ dc, int lddc, int dc_is_zero, int B, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, j = idx % H;
@@ -305,12 +319,12 @@ __global__ void __launch_bounds__(256) sum_scale_kernel(const float* __restrict_
 
 // ---------------------------------------------------------------------------- host wrappers
 int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
-                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st) {
+                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, PreSpec ps) {
   MMQG_REQUIRE(gates && c_out && h_out && B > 0 && H > 0, "lstm_pointwise_fwd: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (c_prev ? 11 : 10) + (h2 ? 4.0 * n : 0));
-  lstm_pointwise_fwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(gates, ldg, c_prev, ldcp, c_out, ldc, h_out, ldh, h2,
-                                                               ldh2, B, H);
+  MMQG_CUDA(launch_k(lstm_pointwise_fwd_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, gates, ldg, c_prev, ldcp, c_out, ldc, h_out, ldh, h2,
+                     ldh2, B, H, ps));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -322,8 +336,8 @@ int lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, cons
   MMQG_REQUIRE(acts && c_new && dc && B > 0 && H > 0, "lstm_pointwise_bwd: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (10 + (c_prev ? 1 : 0) + (dh0 ? n0 : 0) + (dh1 ? n1 : 0) + (dh2 ? 1 : 0)));
-  lstm_pointwise_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(acts, ldg, c_prev, ldcp, c_new, ldc, dh0, ldh0, n0, s0,
-                                                               dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, B, H);
+  MMQG_CUDA(launch_k(lstm_pointwise_bwd_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, acts, ldg, c_prev, ldcp, c_new, ldc, dh0, ldh0, n0, s0,
+                     dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, B, H));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -431,7 +445,7 @@ int mmqg_embedding_scatter_add(float* demb, const int64_t* idx, const float* dx,
 }
 int mmqg_lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
                             int ldh, float* h2, int ldh2, int B, int H, void* stream) {
-  return lstm_pointwise_fwd(gates, ldg, c_prev, ldcp, c_out, ldc, h_out, ldh, h2, ldh2, B, H, as_stream(stream));
+  return lstm_pointwise_fwd(gates, ldg, c_prev, ldcp, c_out, ldc, h_out, ldh, h2, ldh2, B, H, as_stream(stream), PreSpec());
 }
 int mmqg_lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                             const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,

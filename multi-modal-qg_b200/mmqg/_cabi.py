@@ -8,7 +8,7 @@ from .dims import Dims
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmmqg.so")
 MAX_LAYERS = 4
-MODE_FP32, MODE_BF16 = 0, 1
+MODE_FP32, MODE_BF16, MODE_FP32_TC = 0, 1, 2
 
 _fp = C.c_void_p      # device pointers travel as integers (tensor.data_ptr())
 

@@ -28,7 +28,7 @@ class TrainEngine:
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _cabi.check(self.lib.mmqg_device_ok(idx))
         self.d = dims
-        self.mode = {"fp32": _cabi.MODE_FP32, "bf16": _cabi.MODE_BF16}[mode]
+        self.mode = {"fp32": _cabi.MODE_FP32, "bf16": _cabi.MODE_BF16, "fp32_tc": _cabi.MODE_FP32_TC}[mode]
         self.dropout_p = float(dropout_p)
         shapes = param_shapes(dims)
         for name, shape in shapes.items():

@@ -79,6 +79,33 @@ def test_cfg2_bf16_step_matches_oracle(eng_mod, cfg2):
         assert rel(eng.grads[k], eager[k]) < 1e-4, k
 
 
+def test_cfg2_fp32_tc_step_matches_oracle(eng_mod):
+    """The parity mode on the tensor cores (MMQG_MODE_FP32_TC: fp32 operands split into bf16 hi/lo, three tcgen05
+    products per contraction) at the benchmarked shape, UNROUNDED weights, north_star's 1e-3 bar on the loss and on
+    every gradient tensor; also reports its step time."""
+    from oracle import mmqg_oracle as O
+    d = config(2)
+    params = make_params(d, seed=0)
+    batch = make_batch(d, seed=1234)
+    loss_ref, grads_ref = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
+    eng = eng_mod.TrainEngine(d, params, mode="fp32_tc")
+    db = eng.to_device(batch)
+    loss = float(eng.step(db))
+    torch.cuda.synchronize()
+    errs = {k: rel(eng.grads[k], g) for k, g in grads_ref.items()}
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        eng.step(db)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"cfg-2 fp32_tc: loss {loss:.6f} vs oracle {float(loss_ref):.6f} (rel {abs(loss - float(loss_ref)) / abs(float(loss_ref)):.2e}); "
+          f"worst grad rel err {worst[1]:.3e} ({worst[0]}); {e0.elapsed_time(e1) / 3:.2f} ms per eager step")
+    assert abs(loss - float(loss_ref)) < 1e-3 * abs(float(loss_ref))
+    assert worst[1] < 1e-3, errs
+
+
 def test_cfg2_chunked_schedule_equals_unchunked(eng_mod, cfg2, monkeypatch):
     """MMQG_CHUNKS=6 (three layer streams, six time chunks -- the default) against one launch per layer."""
     d, params, batch, loss_ref, grads_ref = cfg2

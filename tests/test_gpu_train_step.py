@@ -27,21 +27,26 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def run_step(engine, d, params, batch):
-    eng = engine.TrainEngine(d, params, mode="fp32")
+MODES32 = ["fp32", "fp32_tc"]       # SIMT fp32 FMA / the same path with every contraction on tcgen05 (bf16 split x3)
+
+
+def run_step(engine, d, params, batch, mode="fp32"):
+    eng = engine.TrainEngine(d, params, mode=mode)
     db = eng.to_device(batch)
     loss = eng.step(db)
     torch.cuda.synchronize()
     return eng, float(loss), {k: v.clone() for k, v in eng.grads.items()}
 
 
+@pytest.mark.parametrize("mode", MODES32)
 @pytest.mark.parametrize("name", ["small_a", "small_b"])
-def test_step_matches_reference_golden(eng_mod, name):
+def test_step_matches_reference_golden(eng_mod, name, mode):
     fx = load_golden(name)
     d = Dims(**fx["dims"])
-    eng, loss, grads = run_step(eng_mod, d, fx["params"], fx["batch"])
+    eng, loss, grads = run_step(eng_mod, d, fx["params"], fx["batch"], mode)
     assert abs(loss - float(fx["loss"])) < TOL * abs(float(fx["loss"]))
     worst = max((rel(grads[k], g), k) for k, g in fx["grads"].items())
+    print(f"{name} {mode}: loss rel err {abs(loss - float(fx['loss'])) / abs(float(fx['loss'])):.2e}; worst grad {worst}")
     assert worst[0] < TOL, worst
     # a second step on the same engine reproduces the first (grads overwritten, not accumulated)
     loss2 = float(eng.step(eng.to_device(fx["batch"])))
@@ -51,12 +56,13 @@ def test_step_matches_reference_golden(eng_mod, name):
         assert rel(eng.grads[k], grads[k]) < 1e-5, k
 
 
-def test_step_matches_reference_full_dim_fingerprint(eng_mod):
+@pytest.mark.parametrize("mode", MODES32)
+def test_step_matches_reference_full_dim_fingerprint(eng_mod, mode):
     fx = load_golden("full_dim")
     d = Dims(**fx["dims"])
     params = make_params(d, seed=fx["seed"])
     batch = make_batch(d, seed=fx["seed"] + 1000)
-    _, loss, grads = run_step(eng_mod, d, params, batch)
+    _, loss, grads = run_step(eng_mod, d, params, batch, mode)
     assert abs(loss - float(fx["loss"])) < TOL * abs(float(fx["loss"]))
     for k, fp in fx["grad_fingerprint"].items():
         g = grads[k].double().cpu()
@@ -73,22 +79,25 @@ def test_step_matches_reference_full_dim_fingerprint(eng_mod):
     dict(B=5, T_t=9, T_v=3, T_q=4, V=211, E=52, H=64, L=2, H_a=20, H_v=48, F_v=36, TM=11, AM=6),
     dict(B=70, T_t=6, T_v=2, T_q=3, V=4100, E=20, H=128, L=1, H_a=8, H_v=64, F_v=12, TM=8, AM=3),
 ])
-def test_step_matches_oracle(eng_mod, cfg):
+@pytest.mark.parametrize("mode", MODES32)
+def test_step_matches_oracle(eng_mod, cfg, mode):
     from oracle import mmqg_oracle as O
     d = Dims(**cfg)
     params = make_params(d, seed=21)
     batch = make_batch(d, seed=22)
     loss_ref, grads_ref = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
-    _, loss, grads = run_step(eng_mod, d, params, batch)
+    _, loss, grads = run_step(eng_mod, d, params, batch, mode)
     assert abs(loss - float(loss_ref)) < TOL * abs(float(loss_ref))
     worst = max((rel(grads[k], g), k) for k, g in grads_ref.items())
+    print(f"B={d.B} H={d.H} {mode}: loss rel err {abs(loss - float(loss_ref)) / abs(float(loss_ref)):.2e}; worst grad {worst}")
     assert worst[0] < TOL, worst
 
 
-def test_grad_scale_and_loss_only(eng_mod):
+@pytest.mark.parametrize("mode", MODES32)
+def test_grad_scale_and_loss_only(eng_mod, mode):
     fx = load_golden("small_a")
     d = Dims(**fx["dims"])
-    eng = eng_mod.TrainEngine(d, fx["params"], mode="fp32")
+    eng = eng_mod.TrainEngine(d, fx["params"], mode=mode)
     db = eng.to_device(fx["batch"])
     loss = float(eng.forward(db, want_grads=False))
     assert abs(loss - float(fx["loss"])) < TOL * abs(float(fx["loss"]))
@@ -98,13 +107,14 @@ def test_grad_scale_and_loss_only(eng_mod):
         assert rel(eng.grads[k], 0.25 * g) < TOL, k
 
 
+@pytest.mark.parametrize("mode", MODES32)
 @pytest.mark.parametrize("name", ["small_a", "small_b", "full_dim"])
-def test_greedy_matches_reference_golden(eng_mod, name):
+def test_greedy_matches_reference_golden(eng_mod, name, mode):
     fx = load_golden(name)
     d = Dims(**fx["dims"])
     gp = make_params(d, seed=fx["seed"], bias_scale=0.1, out_weight_scale=10.0)
     batch = make_batch(d, seed=fx["seed"] + 1000)
-    eng = eng_mod.TrainEngine(d, gp, mode="fp32")
+    eng = eng_mod.TrainEngine(d, gp, mode=mode)
     toks = eng.greedy(eng.to_device(batch), fx["greedy_max_len"]).cpu()
     want = fx["greedy_tokens"]
     # a token may legitimately differ only where the reference's own top-1/top-2 margin is
@@ -113,13 +123,14 @@ def test_greedy_matches_reference_golden(eng_mod, name):
     assert torch.equal(toks, want), (toks.tolist(), want.tolist())
 
 
-def test_greedy_matches_oracle_larger_batch(eng_mod):
+@pytest.mark.parametrize("mode", MODES32)
+def test_greedy_matches_oracle_larger_batch(eng_mod, mode):
     from oracle import mmqg_oracle as O
     d = Dims(B=24, T_t=15, T_v=4, T_q=1, V=997, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101)
     gp = make_params(d, seed=31, bias_scale=0.1, out_weight_scale=10.0)
     batch = make_batch(d, seed=32)
     want, margins = O.greedy_decode(gp, batch, d.L, d.TM, d.AM, 12, return_margins=True)
-    eng = eng_mod.TrainEngine(d, gp, mode="fp32")
+    eng = eng_mod.TrainEngine(d, gp, mode=mode)
     toks = eng.greedy(eng.to_device(batch), 12).cpu()
     # compare each row up to the first step whose oracle margin is within fp32 noise
     safe = (margins > 1e-4).long().cumprod(1).bool()
@@ -144,7 +155,8 @@ def test_errors_are_loud(eng_mod):
     dict(B=6, T_t=11, T_v=4, T_q=6, V=703, E=300, H=512, L=3, H_a=128, H_v=512, F_v=2048, TM=283, AM=101),
     dict(B=9, T_t=5, T_v=2, T_q=4, V=120, E=20, H=32, L=2, H_a=8, H_v=16, F_v=24, TM=9, AM=5),
 ])
-def test_fp32_step_with_dropout_matches_oracle_with_same_masks(eng_mod, cfg):
+@pytest.mark.parametrize("mode", MODES32)
+def test_fp32_step_with_dropout_matches_oracle_with_same_masks(eng_mod, cfg, mode):
     """The reference trains with torch.nn.LSTM's inter-layer dropout p = 0.2 (encoder.py:91, decoder.py:69).  The fp32
     parity mode applies the same counter-based masks as the bf16 mode; they are exported (mmqg_dropout_mask) and fed
     to the oracle, so the north-star bar holds with dropout on: loss and every gradient tensor <= 1e-3 relative."""
@@ -152,7 +164,7 @@ def test_fp32_step_with_dropout_matches_oracle_with_same_masks(eng_mod, cfg):
     d = Dims(**cfg)
     params = make_params(d, seed=71)
     batch = make_batch(d, seed=72)
-    eng = eng_mod.TrainEngine(d, params, mode="fp32", dropout_p=0.2)
+    eng = eng_mod.TrainEngine(d, params, mode=mode, dropout_p=0.2)
     eng.seed = 2024
     for _ in range(2):                      # second step: the device-side call counter has advanced, masks are fresh
         masks = {k: v.cpu() for k, v in eng.dropout_masks().items()}
@@ -161,7 +173,7 @@ def test_fp32_step_with_dropout_matches_oracle_with_same_masks(eng_mod, cfg):
         torch.cuda.synchronize()
         assert abs(loss - float(loss_ref)) < TOL * abs(float(loss_ref)), (loss, float(loss_ref))
         worst = max((rel(eng.grads[k], g), k) for k, g in grads_ref.items())
-        print("fp32 + dropout: worst grad rel err", worst)
+        print(f"{mode} + dropout: worst grad rel err", worst)
         assert worst[0] < TOL, worst
     loss_nodrop, _ = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
     assert abs(loss - float(loss_nodrop)) > 1e-4 * abs(loss)      # the masks do act
