@@ -349,7 +349,9 @@ int mmqg_decode_step_argmax(const void* h_bf16, const void* w_bf16, const float*
  *                   stats (mmqg_conv_stats_parts() x 2*Cout floats, NULL = skip) receives per-block partial sums and sums of
  *                   squares of y per channel (no same-address atomics)
  *   bn_finalize   : the `nparts` partials, `count` = N*H*W elements -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd,
- *                   running_mean / running_var updated like torch.nn.BatchNorm2d (momentum, unbiased variance; NULL = skip)
+ *                   running_mean / running_var updated like torch.nn.BatchNorm2d (momentum, unbiased variance; NULL = skip);
+ *                   with nparts > 1, scale and shift must be ONE contiguous (2, C) buffer (shift == scale + C): it holds the
+ *                   partial sums while they are reduced
  *   bn_maxpool_fwd: out = maxpool_K(y * scale + shift) (kernel = stride = K, floor), idx = position of the first maximum in the window
  * Backward:
  *   maxpool_bwd   : dense gradient w.r.t. the BatchNorm output from the pooled gradient
@@ -366,6 +368,10 @@ int mmqg_bn_finalize(const float* stats_parts, int nparts, long long count, cons
 int mmqg_bn_maxpool_fwd(const float* y, const float* scale, const float* shift, float* out, unsigned char* idx, int N, int C, int H,
                         int W, int K, void* stream);
 int mmqg_maxpool_bwd(const float* dpool, const unsigned char* idx, float* dbn, int N, int C, int H, int W, int K, void* stream);
+/* mmqg_maxpool_bwd followed by mmqg_bn_relu_bwd in one pass: the gradient w.r.t. the BatchNorm output is taken from the pooled
+ * gradient and the saved arg-max on the fly, the dense (N,C,H,W) intermediate is never written (layers followed by a MaxPool2d). */
+int mmqg_bn_relu_pool_bwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* dpool,
+                          const unsigned char* idx, int K, float* dz, float* sums, int N, int C, int H, int W, void* stream);
 int mmqg_bn_relu_bwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* dbn, float* dz,
                      float* sums, int N, int C, int H, int W, void* stream);
 int mmqg_conv_bwd_w(const float* x, const float* in_scale, const float* in_shift, const float* dz, float* dw, float* db, int N,

@@ -86,26 +86,32 @@ conv_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ in_s
   }
 }
 
-// grid C, block 256: block c sums the per-block partial statistics of channel c, thread 0 finishes the BatchNorm bookkeeping
+// Partial statistics (nparts, 2C) -> acc[2C] (zeroed by the caller): rows are read coalesced, thread t owns column t % 2C.
 __global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float* __restrict__ parts, int nparts, float count, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
-                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
-                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
-  __shared__ float r1[8], r2[8];
-  const int c = blockIdx.x;
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
-    s1 += parts[(size_t)i * 2 * C + c];
-    s2 += parts[(size_t)i * 2 * C + C + c];
-  }
-  s1 = warp_sum(s1); s2 = warp_sum(s2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { r1[warp] = s1; r2[warp] = s2; }
+bn_reduce_parts_kernel(const float* __restrict__ parts, int nparts, int C2, float* __restrict__ acc) {
+  __shared__ float red[256];
+  const int rows_per_pass = 256 / C2;
+  const int col = threadIdx.x % C2, rl = threadIdx.x / C2;
+  float s = 0.f;
+  if (rl < rows_per_pass)
+    for (int r = blockIdx.x * rows_per_pass + rl; r < nparts; r += gridDim.x * rows_per_pass) s += parts[(size_t)r * C2 + col];
+  red[threadIdx.x] = rl < rows_per_pass ? s : 0.f;
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  s1 = 0.f; s2 = 0.f;
-  for (int wv = 0; wv < 8; ++wv) { s1 += r1[wv]; s2 += r2[wv]; }
+  if (threadIdx.x < C2) {
+    float t = 0.f;
+    for (int k = 0; k < rows_per_pass; ++k) t += red[k * C2 + threadIdx.x];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
+// one thread per channel: acc = (sum | sum of squares) -> the BatchNorm bookkeeping.  acc may alias mean_out / invstd_out storage.
+__global__ void bn_finalize_kernel(const float* __restrict__ acc, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const float s1 = acc[c], s2 = acc[C + c];
   const float mean = s1 / count;
   const float var = fmaxf(s2 / count - mean * mean, 0.f);     // biased, as BatchNorm normalises with
   const float invstd = rsqrtf(var + eps);
@@ -156,20 +162,70 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dpool, const unsign
   dbn[i] = g;
 }
 
-// sums[c] += sum d, sums[C + c] += sum d * xhat over (n, h, w); grid (blocks per plane, N*C)
+// Gradient w.r.t. the BatchNorm output when a MaxPool2d(K, K) follows: the pooled gradient of the window that holds the
+// element if the element was the window's (first) maximum, else 0 -- maxpool_bwd_kernel on the fly, so the dense (N,C,H,W)
+// gradient is never written or re-read.  KC = 3: compile-time window (the reference's); KC = 0: pg.K at run time.
+struct PoolGrad {
+  const float* dpool; const unsigned char* idx; int W, K, Hp, Wp;
+};
+template <int KC>
+__device__ __forceinline__ float pool_grad(const PoolGrad& pg, long long nc, int yh, int xw) {
+  const int K = KC ? KC : pg.K;
+  const int py = yh / K, px = xw / K;
+  if (py >= pg.Hp || px >= pg.Wp) return 0.f;
+  const long long o = (nc * pg.Hp + py) * pg.Wp + px;
+  return pg.idx[o] == (unsigned char)((yh - py * K) * K + (xw - px * K)) ? pg.dpool[o] : 0.f;
+}
+
+// Four consecutive elements i0 .. i0+3 of plane nc: y values and the gradient w.r.t. the BatchNorm output.
+// MODE -1: dense gradient dbn; 0 / 3: pooled gradient (run-time / compile-time window).  vec: float4 accesses are legal.
+template <int MODE>
+__device__ __forceinline__ void load_y_d(const float* __restrict__ yp, const float* __restrict__ dp, const PoolGrad& pg, long long nc,
+                                         int i0, int HW, bool vec, float (&yv)[4], float (&d)[4]) {
+  if (vec) {
+    const float4 t = *reinterpret_cast<const float4*>(yp + i0);
+    yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
+    if (MODE < 0) {
+      const float4 u = *reinterpret_cast<const float4*>(dp + i0);
+      d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      yv[q] = i0 + q < HW ? yp[i0 + q] : 0.f;
+      if (MODE < 0) d[q] = i0 + q < HW ? dp[i0 + q] : 0.f;
+    }
+  }
+  if (MODE >= 0) {
+    int yh = i0 / pg.W, xw = i0 - yh * pg.W;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      d[q] = i0 + q < HW ? pool_grad<(MODE > 0 ? MODE : 0)>(pg, nc, yh, xw) : 0.f;
+      if (++xw == pg.W) { xw = 0; ++yh; }
+    }
+  }
+}
+
+// sums[c] += sum d, sums[C + c] += sum d * xhat over (n, h, w); grid (N*C, blocks per plane)
+template <int MODE>
 __global__ void __launch_bounds__(256)
 bn_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ dbn, float* __restrict__ sums, int C, int HW) {
+                    const float* __restrict__ dbn, PoolGrad pg, float* __restrict__ sums, int C, int HW, bool vec) {
   __shared__ float r1[8], r2[8];
-  const int nc = blockIdx.y, c = nc % C;
+  const long long nc = blockIdx.x;
+  const int c = (int)(nc % C);
   const float m = mean[c], is = invstd[c];
-  const float* yp = y + (size_t)nc * HW;
-  const float* dp = dbn + (size_t)nc * HW;
+  const float* yp = y + nc * HW;
+  const float* dp = MODE < 0 ? dbn + nc * HW : nullptr;
   float s1 = 0.f, s2 = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    const float d = dp[i];
-    s1 += d;
-    s2 = fmaf(d, (yp[i] - m) * is, s2);
+  for (int i0 = (blockIdx.y * 256 + threadIdx.x) * 4; i0 < HW; i0 += gridDim.y * 1024) {
+    float yv[4], d[4];
+    load_y_d<MODE>(yp, dp, pg, nc, i0, HW, vec, yv, d);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s1 += d[q];
+      s2 = fmaf(d[q], (yv[q] - m) * is, s2);
+    }
   }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,22 +239,30 @@ bn_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ mean,
 }
 
 // dz = gamma * invstd * (d - sum_d / M - xhat * sum_dxhat / M) * (y > 0)     (sums == NULL: eval-mode BatchNorm, dz = d * scale * (y > 0))
-__global__ void bn_relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                   const float* __restrict__ gamma, const float* __restrict__ sums, const float* __restrict__ dbn,
-                                   float* __restrict__ dz, int C, int HW, float inv_count, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)((i / HW) % C);
-  const float yv = y[i];
-  const float g = gamma ? gamma[c] : 1.f;
-  float v;
-  if (sums) {
-    const float xhat = (yv - mean[c]) * invstd[c];
-    v = g * invstd[c] * (dbn[i] - sums[c] * inv_count - xhat * sums[C + c] * inv_count);
+// grid (N*C, ceil(HW / 1024)): four consecutive elements per thread
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
+                   const float* __restrict__ gamma, const float* __restrict__ sums, const float* __restrict__ dbn, PoolGrad pg,
+                   float* __restrict__ dz, int C, int HW, float inv_count, bool vec) {
+  const int i0 = (blockIdx.y * 256 + threadIdx.x) * 4;
+  if (i0 >= HW) return;
+  const long long nc = blockIdx.x;
+  const int c = (int)(nc % C);
+  const float is = invstd[c], gi = (gamma ? gamma[c] : 1.f) * is;
+  const float m = sums ? mean[c] : 0.f, a = sums ? sums[c] * inv_count : 0.f, b = sums ? sums[C + c] * inv_count * is : 0.f;
+  float yv[4], d[4], v[4];
+  load_y_d<MODE>(y + nc * HW, MODE < 0 ? dbn + nc * HW : nullptr, pg, nc, i0, HW, vec, yv, d);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) v[q] = yv[q] > 0.f ? gi * (d[q] - a - (yv[q] - m) * b) : 0.f;
+  float* op = dz + nc * HW + i0;
+  if (vec) {
+    *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
-    v = dbn[i] * g * invstd[c];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (i0 + q < HW) op[q] = v[q];
   }
-  dz[i] = yv > 0.f ? v : 0.f;
 }
 
 // grid (Cout * Cin, chunks).  Block = one (co, ci) pair over a chunk of the N*Ho*Wo positions; thread accumulates the K*K taps.
@@ -382,6 +446,8 @@ extern "C" int mmqg_conv_relu_fwd(const float* x, const float* in_scale, const f
   cudaStream_t st = as_stream(stream);
   const int Ho = cs::conv_out(Hin, K, stride), Wo = cs::conv_out(Win, K, stride);
   MMQG_PROBE(KC_OTHER, 2.0 * N * Ho * Wo * Cout * Cin * K * K, 4.0 * N * ((double)Cin * Hin * Win + (double)Cout * Ho * Wo));
+  if (b && conv3_fast_ok(Cin, Cout, K, stride, Win, 0) && ((uintptr_t)x % 8 == 0) && ((uintptr_t)y % 8 == 0))
+    return conv3_relu_fwd(x, in_scale, in_shift, w, b, y, stats, N, Cin, Hin, Win, Cout, mmqg_conv_stats_parts(N, Hin, Win, K, stride) / N, st);
   cs::conv_relu_fwd_kernel<<<dim3(ceil_div(Ho * Wo, 256), N), 256, 0, st>>>(x, in_scale, in_shift, w, b, y, stats, Cin, Hin, Win, Cout, K,
                                                                             stride, Ho, Wo);
   MMQG_LAUNCH_CHECK();
@@ -393,8 +459,23 @@ extern "C" int mmqg_bn_finalize(const float* stats_parts, int nparts, long long 
                                 float* invstd, int C, void* stream) {
   MMQG_REQUIRE(stats_parts && nparts > 0 && scale && shift && mean && invstd && C > 0 && C <= cs::MAXC && count > 0, "bn_finalize: bad args");
   cudaStream_t st = as_stream(stream);
-  cs::bn_finalize_kernel<<<C, 256, 0, st>>>(stats_parts, nparts, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale,
-                                            shift, mean, invstd, C);
+  // the sums are accumulated in `scale` | `shift` (2C floats when contiguous, else in two steps) -- the outputs double as scratch
+  float* acc = scale;
+  const bool contig = shift == scale + C;
+  if (contig && nparts > 1) {
+    MMQG_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 2 * C, st));
+    int blocks = ceil_div(nparts, (256 / (2 * C)) * 8);
+    blocks = blocks > 296 ? 296 : blocks;
+    cs::bn_reduce_parts_kernel<<<blocks, 256, 0, st>>>(stats_parts, nparts, 2 * C, acc);
+    MMQG_LAUNCH_CHECK();
+    cs::bn_finalize_kernel<<<1, 32, 0, st>>>(acc, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift,
+                                             mean, invstd, C);
+  } else if (nparts == 1) {
+    cs::bn_finalize_kernel<<<1, 32, 0, st>>>(stats_parts, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                                             shift, mean, invstd, C);
+  } else {
+    return set_err(MMQG_ERR_BAD_ARG, "bn_finalize: scale and shift must be one contiguous (2, C) buffer when nparts > 1");
+  }
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -426,24 +507,42 @@ extern "C" int mmqg_maxpool_bwd(const float* dpool, const unsigned char* idx, fl
 // Backward of train-mode BatchNorm + ReLU: y = relu output (the BatchNorm's input), dbn = gradient w.r.t. the BatchNorm output,
 // dz = gradient w.r.t. the conv output (may alias dbn).  sums (2*C floats: sum d = d beta, sum d*xhat = d gamma) is filled here.
 // sums == NULL: eval-mode BatchNorm (fixed affine map, invstd = 1/sqrt(running_var + eps)).
+template <int MODE>
+static int bn_relu_bwd_impl(const float* y, const float* mean, const float* invstd, const float* gamma, const float* dbn, cs::PoolGrad pg,
+                            float* dz, float* sums, int N, int C, int H, int W, cudaStream_t st) {
+  const int HW = H * W;
+  const long long total = (long long)N * C * HW;
+  const bool vec = HW % 4 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)dz % 16 == 0 && (MODE >= 0 || (uintptr_t)dbn % 16 == 0);
+  if (sums) {
+    MMQG_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
+    int by = ceil_div(HW, 1024 * 4);
+    if (by > 16) by = 16;
+    MMQG_PROBE(KC_OTHER, 0, (MODE >= 0 ? 4.0 : 8.0) * total);
+    cs::bn_bwd_stats_kernel<MODE><<<dim3(N * C, by), 256, 0, st>>>(y, mean, invstd, dbn, pg, sums, C, HW, vec);
+    MMQG_LAUNCH_CHECK();
+  }
+  MMQG_PROBE(KC_OTHER, 0, (MODE >= 0 ? 8.0 : 12.0) * total);
+  cs::bn_relu_bwd_kernel<MODE><<<dim3(N * C, ceil_div(HW, 1024)), 256, 0, st>>>(y, mean, invstd, gamma, sums, dbn, pg, dz, C, HW,
+                                                                                1.0f / ((float)N * HW), vec);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mmqg_bn_relu_bwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* dbn, float* dz,
                                 float* sums, int N, int C, int H, int W, void* stream) {
   MMQG_REQUIRE(y && invstd && dbn && dz && N > 0 && C > 0 && C <= cs::MAXC && H > 0 && W > 0 && (!sums || mean), "bn_relu_bwd: bad args");
-  cudaStream_t st = as_stream(stream);
-  const int HW = H * W;
-  const long long total = (long long)N * C * HW;
-  if (sums) {
-    MMQG_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st));
-    int bx = ceil_div(HW, 256 * 4);
-    if (bx > 64) bx = 64;
-    cs::bn_bwd_stats_kernel<<<dim3(bx, N * C), 256, 0, st>>>(y, mean, invstd, dbn, sums, C, HW);
-    MMQG_LAUNCH_CHECK();
-  }
-  MMQG_PROBE(KC_OTHER, 0, 12.0 * total);
-  cs::bn_relu_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, mean, invstd, gamma, sums, dbn, dz, C, HW,
-                                                                          1.0f / ((float)N * HW), total);
-  MMQG_LAUNCH_CHECK();
-  return 0;
+  return bn_relu_bwd_impl<-1>(y, mean, invstd, gamma, dbn, cs::PoolGrad{}, dz, sums, N, C, H, W, as_stream(stream));
+}
+
+// The same with a MaxPool2d(K, K) between the BatchNorm and the incoming gradient: dpool / idx are the pooled gradient and the
+// arg-max saved by mmqg_bn_maxpool_fwd; equals mmqg_maxpool_bwd followed by mmqg_bn_relu_bwd without the dense intermediate.
+extern "C" int mmqg_bn_relu_pool_bwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* dpool,
+                                     const unsigned char* idx, int K, float* dz, float* sums, int N, int C, int H, int W, void* stream) {
+  MMQG_REQUIRE(y && invstd && dpool && idx && dz && N > 0 && C > 0 && C <= cs::MAXC && K >= 1 && K <= 15 && H >= K && W >= K &&
+                   (!sums || mean), "bn_relu_pool_bwd: bad args");
+  cs::PoolGrad pg{dpool, idx, W, K, (H - K) / K + 1, (W - K) / K + 1};
+  if (K == 3) return bn_relu_bwd_impl<3>(y, mean, invstd, gamma, nullptr, pg, dz, sums, N, C, H, W, as_stream(stream));
+  return bn_relu_bwd_impl<0>(y, mean, invstd, gamma, nullptr, pg, dz, sums, N, C, H, W, as_stream(stream));
 }
 
 extern "C" int mmqg_conv_bwd_w(const float* x, const float* in_scale, const float* in_shift, const float* dz, float* dw, float* db, int N,
@@ -458,6 +557,10 @@ extern "C" int mmqg_conv_bwd_w(const float* x, const float* in_scale, const floa
   int chunks = (int)((P + 256 * 16 - 1) / (256 * 16));
   if (chunks < 1) chunks = 1;
   if (chunks > 64) chunks = 64;
+  if (conv3_fast_ok(Cin, Cout, K, stride, Win, 112) && ((uintptr_t)x % 8 == 0) && ((uintptr_t)dz % 8 == 0)) {
+    MMQG_PROBE(KC_OTHER, 2.0 * P * Cout * Cin * K * K, 4.0 * (N * (double)Cin * Hin * Win + (double)P * Cout));
+    return conv3_bwd_w(x, in_scale, in_shift, dz, dw, db, N, Cin, Hin, Win, Cout, st);
+  }
   MMQG_PROBE(KC_OTHER, 2.0 * P * Cout * Cin * K * K, 4.0 * (N * (double)Cin * Hin * Win + (double)Cin * P * Cout));
   if (K == 3) {
     int cx = (int)((P + 256 * 32 - 1) / (256 * 32));
@@ -479,6 +582,8 @@ extern "C" int mmqg_conv_bwd_x(const float* dz, const float* w, float* dxn, int 
   cudaStream_t st = as_stream(stream);
   const int Ho = cs::conv_out(Hin, K, stride), Wo = cs::conv_out(Win, K, stride);
   MMQG_PROBE(KC_OTHER, 2.0 * N * Ho * Wo * Cout * Cin * K * K, 4.0 * N * ((double)Cin * Hin * Win + (double)Cout * Ho * Wo));
+  if (conv3_fast_ok(Cin, Cout, K, stride, Win, 0) && ((uintptr_t)dz % 8 == 0) && ((uintptr_t)dxn % 8 == 0))
+    return conv3_bwd_x(dz, w, dxn, N, Cin, Hin, Win, Cout, st);
   if (stride == 1) cs::conv_bwd_x_kernel<1><<<dim3(ceil_div(Hin * Win, 256), N), 256, 0, st>>>(dz, w, dxn, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
   else cs::conv_bwd_x_kernel<0><<<dim3(ceil_div(Hin * Win, 256), N), 256, 0, st>>>(dz, w, dxn, Cin, Hin, Win, Cout, K, stride, Ho, Wo);
   MMQG_LAUNCH_CHECK();

@@ -160,6 +160,13 @@ int dec_seq_bwd_persist(const DecPersistBwdArgs& a, int t_lo, int t_hi, cudaStre
 int transpose_f32_bf16(const float* src, long long ld_src, int R, int Cc, void* dst, long long ld_dst, cudaStream_t st);
 size_t dec_bwd_weight_rows(int H, int l);
 int pack_decb_weights(const float* w_hh, int H, const float* w_in, long long ld_in, int n_in_total, int l, void* out, cudaStream_t st);
+// 3x3 / stride-1 fast path of the conv stack for the reference's channel chain (convstack3.cu)
+bool conv3_fast_ok(int Cin, int Cout, int K, int stride, int Win, int max_win);      // max_win <= 0: any width
+int conv3_relu_fwd(const float* x, const float* in_scale, const float* in_shift, const float* w, const float* b, float* y, float* stats,
+                   int N, int Cin, int Hin, int Win, int Cout, int parts, cudaStream_t st);
+int conv3_bwd_x(const float* dz, const float* w, float* dxn, int N, int Cin, int Hin, int Win, int Cout, cudaStream_t st);
+int conv3_bwd_w(const float* x, const float* in_scale, const float* in_shift, const float* dz, float* dw, float* db, int N, int Cin,
+                int Hin, int Win, int Cout, cudaStream_t st);
 // bf16-mode orchestration (engine_bf16.cu)
 size_t train_workspace_bytes_bf16(const mmqg_dims& d, int T_q);
 int check_dims_bf16(const mmqg_dims& d);

@@ -241,15 +241,18 @@ class ConvStack(Function):
             inp, sc, sh, y, mean, invstd, idx = saved[7 * l:7 * l + 7]
             w, gamma = _c(params[4 * l]), _c(params[4 * l + 2])
             pooled, H, W = meta[l]
-            if pooled:
-                dbn = ops.maxpool_bwd(d, idx, H, W, K)
-            else:      # d is ours (conv_bwd_x of the layer above) unless it is autograd's own dout
-                dbn = d.clone() if l == n_layers - 1 else d
             C_ = y.shape[1]
-            if not training:      # eval-mode BatchNorm: d beta = sum d, d gamma = sum d * xhat over the fixed statistics
-                xhat = (y - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
-                grads[4 * l + 3], grads[4 * l + 2] = dbn.sum((0, 2, 3)), (dbn * xhat).sum((0, 2, 3))
-            dz, sums = ops.bn_relu_bwd(y, mean, invstd, gamma, dbn, train=training)      # in place: dz aliases dbn
+            if pooled and training:      # pooled gradient -> d z in one pass, no dense gradient w.r.t. the BatchNorm output
+                dz, sums = ops.bn_relu_pool_bwd(y, mean, invstd, gamma, _c(d), idx, K, train=True)
+            else:
+                if pooled:
+                    dbn = ops.maxpool_bwd(d, idx, H, W, K)
+                else:      # d is ours (conv_bwd_x of the layer above) unless it is autograd's own dout
+                    dbn = d.clone() if l == n_layers - 1 else d
+                if not training:      # eval-mode BatchNorm: d beta = sum d, d gamma = sum d * xhat over the fixed statistics
+                    xhat = (y - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+                    grads[4 * l + 3], grads[4 * l + 2] = dbn.sum((0, 2, 3)), (dbn * xhat).sum((0, 2, 3))
+                dz, sums = ops.bn_relu_bwd(y, mean, invstd, gamma, dbn, train=training)      # in place: dz aliases dbn
             if training:
                 grads[4 * l + 3], grads[4 * l + 2] = sums[:C_].clone(), sums[C_:].clone()
             grads[4 * l], grads[4 * l + 1] = ops.conv_bwd_w(inp, dz, K, stride, sc, sh)

@@ -286,7 +286,8 @@ def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_
     """Train-mode BatchNorm2d statistics -> (scale, shift, mean, invstd); running stats updated in place (None = skip)."""
     stats = stats.view(-1, stats.shape[-1]) if stats.dim() > 1 else stats.view(1, -1)
     C_ = stats.shape[1] // 2
-    out = [torch.empty(C_, device=stats.device, dtype=torch.float32) for _ in range(4)]
+    buf = torch.empty(4, C_, device=stats.device, dtype=torch.float32)      # scale | shift contiguous: they double as the reduction scratch
+    out = [buf[i] for i in range(4)]
     check(lib().mmqg_bn_finalize(stats.data_ptr(), stats.shape[0], int(count), _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
                                  _p(running_var), *[o.data_ptr() for o in out], C_, _st()))
     return out
@@ -315,6 +316,17 @@ def bn_relu_bwd(y, mean, invstd, gamma, dbn, train=True):
     check(lib().mmqg_bn_relu_bwd(y.data_ptr(), _p(mean), invstd.data_ptr(), _p(gamma), dbn.data_ptr(), dbn.data_ptr(), _p(sums),
                                  N, C_, H, W, _st()))
     return dbn, sums
+
+
+def bn_relu_pool_bwd(y, mean, invstd, gamma, dpool, idx, K, train=True):
+    """maxpool_bwd + bn_relu_bwd in one pass (no dense gradient w.r.t. the BatchNorm output): returns (dz, sums)."""
+    N, C_, H, W = y.shape
+    _chk(y, dpool)
+    dz = torch.empty_like(y)
+    sums = torch.empty(2 * C_, device=y.device, dtype=torch.float32) if train else None
+    check(lib().mmqg_bn_relu_pool_bwd(y.data_ptr(), _p(mean), invstd.data_ptr(), _p(gamma), dpool.data_ptr(), idx.data_ptr(), K,
+                                      dz.data_ptr(), _p(sums), N, C_, H, W, _st()))
+    return dz, sums
 
 
 def conv_bwd_w(x, dz, K, stride=1, in_scale=None, in_shift=None):

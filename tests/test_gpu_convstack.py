@@ -34,7 +34,10 @@ def rel(a, b):
 
 @pytest.mark.parametrize("shape", [
     dict(N=3, Cin=3, Cout=4, H=20, W=17, K=3, stride=1),
-    dict(N=2, Cin=8, Cout=10, H=34, W=34, K=3, stride=1),
+    dict(N=2, Cin=8, Cout=10, H=34, W=34, K=3, stride=1),       # fast path (convstack3.cu): even width, reference channels
+    dict(N=3, Cin=3, Cout=4, H=21, W=30, K=3, stride=1),         # fast path, ragged 4-pixel groups (Wo = 28 + edge), 3 tiles of rows
+    dict(N=5, Cin=4, Cout=6, H=110, W=110, K=3, stride=1),       # fast path at the reference's layer-2 size: several blocks per image
+    dict(N=2, Cin=6, Cout=8, H=36, W=36, K=3, stride=1),
     dict(N=1, Cin=1, Cout=1, H=3, W=3, K=3, stride=1),            # single output pixel
     dict(N=2, Cin=5, Cout=7, H=23, W=19, K=5, stride=2),
 ])
@@ -91,9 +94,12 @@ def test_batchnorm_pool_blocks_match_oracle(ops, shape):
     gy, gg, gb = torch.autograd.grad(pooled_ref, [yr, gr, br], dpool.double())
     dbn = ops.maxpool_bwd(dpool.cuda(), idx, H, W, K)
     dz, sums = ops.bn_relu_bwd(yc, mean, invstd, gamma.cuda(), dbn, train=True)
+    dz2, sums2 = ops.bn_relu_pool_bwd(yc, mean, invstd, gamma.cuda(), dpool.cuda(), idx, K, train=True)     # the same in one pass
     torch.cuda.synchronize()
     assert rel(dz, gy * (y.double() > 0)) < 1e-4
     assert rel(sums[:C_], gb) < 1e-4 and rel(sums[C_:], gg) < 1e-4
+    assert rel(dz2, gy * (y.double() > 0)) < 1e-4
+    assert rel(sums2[:C_], gb) < 1e-4 and rel(sums2[C_:], gg) < 1e-4
 
 
 @pytest.mark.parametrize("name", ["convstack_a", "convstack_b"])
