@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16", "auto"],
                     help="N > 1: element type of the gradient all-reduce (fp32 = exact sums; bf16 = buckets rounded to bf16 for the "
                          "exchange, half the NVLink bytes; auto = bf16 in bf16 mode)")
+    ap.add_argument("--reduce", default=os.environ.get("MMQG_REDUCE", "overlap"), choices=["overlap", "late"],
+                    help="N > 1: overlap = one all-reduce per gradient group under the rest of the backward; late = one all-reduce "
+                         "of the flat gradient buffer after the backward")
     return ap.parse_args()
 
 
@@ -193,8 +196,8 @@ def workload_config(d, args, world):
             "dropout_p": 0.0 if args.greedy else args.dropout,
             "optimizer": "fused adam" if args.adam else "none (metric is fwd+bwd)",
             "mode": args.mode, "cuda_graph": not args.no_graph,
-            **({"grad_comm": ("bf16" if args.grad_comm == "bf16" or (args.grad_comm == "auto" and args.mode == "bf16") else "fp32")}
-               if world > 1 else {}),
+            **({"grad_comm": ("bf16" if args.grad_comm == "bf16" or (args.grad_comm == "auto" and args.mode == "bf16") else "fp32"),
+                "grad_reduce": args.reduce} if world > 1 else {}),
             "l2": "working set (2 GB activations + 111 MB weights per step) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -453,7 +456,7 @@ def main():
     pinned = {k: v.pin_memory() for k, v in host.items()}
     dbatch = eng.to_device(host)
     comm_bf16 = args.grad_comm == "bf16" or (args.grad_comm == "auto" and args.mode == "bf16")
-    reducer = GradReducer(eng, world, comm_dtype=torch.bfloat16 if comm_bf16 else torch.float32) if world > 1 else None
+    reducer = GradReducer(eng, world, comm_dtype=torch.bfloat16 if comm_bf16 else torch.float32, schedule=args.reduce) if world > 1 else None
     gscale = 1.0 / world
 
     if args.adam:

@@ -275,9 +275,9 @@ static int pack_rec(const float* w_hh, void* fwd, void* bwd, int B, int H, cudaS
   (void)B;
   return pack_whh(w_hh, fwd, bwd, H, st);
 }
-static int rec_fwd(float* gates, float* cs, void* hs, const void* wp, float* mem, long long mem_ld, uint32_t* flags, int T, int B,
-                   int H, cudaStream_t st, LenSpec len = LenSpec()) {
-  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, nullptr, mem_ld, flags, T, B, H, 0, st, DropSpec(), true, len);
+static int rec_fwd(float* gates, float* cs, void* hs, const void* wp, float* mem, void* mem16, long long mem_ld, uint32_t* flags, int T,
+                   int B, int H, cudaStream_t st, LenSpec len = LenSpec()) {
+  return lstm_seq_fwd_persist(gates, cs, hs, wp, mem, mem16, mem_ld, flags, T, B, H, 0, st, DropSpec(), true, len);
 }
 static int rec_bwd(const float* acts, const float* cs, void* dg, const void* wp, const float* ext, long long ts, long long ld,
                    const float* dh_last, const float* dc_last, uint32_t* flags, int T, int B, int H, cudaStream_t st,
@@ -491,6 +491,7 @@ static int video_forward16(const mmqg_dims& d, const mmqg_batch& bt, Ws16& w, cu
     MMQG_REQUIRE(persist_video(d), "variable-length batches need the persistent recurrent kernels (B=%d H_v=%d)", B, Hv);
     MMQG_TRY(audio_pad(bt.audio, w.m_aud, bt.n_frames, B, d.T_v, d.AM, d.H_a, st));
     MMQG_CUDA(cudaMemsetAsync(w.m_vid, 0, sizeof(float) * (size_t)B * d.AM * Hv, st));      // rows >= n_frames stay zero
+    MMQG_CUDA(cudaMemsetAsync(w.m_vid16, 0, sizeof(b16) * (size_t)B * d.AM * Hv, st));
   } else {
     MMQG_CUDA(cudaMemcpy2DAsync(w.m_aud, sizeof(float) * (size_t)d.AM * d.H_a, bt.audio,
                                 sizeof(float) * (size_t)d.T_v * d.H_a, sizeof(float) * (size_t)d.T_v * d.H_a, B,
@@ -504,8 +505,9 @@ static int video_forward16(const mmqg_dims& d, const mmqg_batch& bt, Ws16& w, cu
     MMQG_CUDA(cudaMemsetAsync(w.hs_v, 0, sizeof(b16) * (size_t)B * Hv, st));
     MMQG_CUDA(cudaMemsetAsync(w.cs_v, 0, sizeof(float) * (size_t)B * Hv, st));
     tl_ktag = 900;
-    MMQG_TRY(rec_fwd(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, (long long)d.AM * Hv, w.flags_v, d.T_v, B, Hv, st, len_video()));
-  } else
+    // the kernel writes the fp32 memory rows and their bf16 copy itself: no conversion pass over the padded (B, AM, H_v) tensor
+    return rec_fwd(w.acts_v, w.cs_v, w.hs_v, w.wvp_f, w.m_vid, w.m_vid16, (long long)d.AM * Hv, w.flags_v, d.T_v, B, Hv, st, len_video());
+  }
   for (int t = 0; t < d.T_v; ++t) {
     StepGemmScope step_scope;
     float* acts = w.acts_v + (size_t)t * B * Gv;
@@ -527,8 +529,8 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
   const int NC = text_chunks(d);
   if (g_len.on) {     // memory rows beyond a sample's length are the zero padding of train.py:160
     MMQG_REQUIRE(persist_text(d), "variable-length batches need the persistent recurrent kernels (B=%d H=%d)", B, H);
-    if (NC > 1) MMQG_CUDA(cudaMemsetAsync(w.m_txt16, 0, sizeof(b16) * (size_t)B * d.TM * H, st));
-    else MMQG_CUDA(cudaMemsetAsync(w.m_txt, 0, sizeof(float) * (size_t)B * d.TM * H, st));
+    MMQG_CUDA(cudaMemsetAsync(w.m_txt16, 0, sizeof(b16) * (size_t)B * d.TM * H, st));
+    if (NC <= 1) MMQG_CUDA(cudaMemsetAsync(w.m_txt, 0, sizeof(float) * (size_t)B * d.TM * H, st));
   }
   if (NC > 1) {
     // layers pipelined over NC time chunks, one stream per layer
@@ -585,7 +587,8 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
     if (persist_text(d)) {
       MMQG_CUDA(cudaMemsetAsync(w.hs_text[l], 0, sizeof(b16) * (size_t)B * H, st));
       MMQG_CUDA(cudaMemsetAsync(w.cs_text[l], 0, sizeof(float) * (size_t)B * H, st));
-      MMQG_TRY(rec_fwd(w.acts_text[l], w.cs_text[l], w.hs_text[l], w.wtp_f[l], l == d.L - 1 ? w.m_txt : nullptr,
+      // the top layer writes the fp32 memory rows and their bf16 copy itself (no conversion pass over the padded (B, TM, H) tensor)
+      MMQG_TRY(rec_fwd(w.acts_text[l], w.cs_text[l], w.hs_text[l], w.wtp_f[l], l == d.L - 1 ? w.m_txt : nullptr, l == d.L - 1 ? w.m_txt16 : nullptr,
                        (long long)d.TM * H, w.flags, d.T_t, B, H, st, len_text(0, l == d.L - 1)));
       continue;
     }
@@ -601,7 +604,7 @@ static int text_forward16(const mmqg_dims& d, const mmqg_tensors& P, Ws16& w, cu
   }
   // bf16 attention memories: the pipelined persistent path writes the text memory in bf16 directly;
   // every other path produced fp32 rows, converted here (rows beyond T_t / T_v are never read)
-  if (NC <= 1) MMQG_TRY(cvt_f32_bf16_2d(w.m_txt, H, w.m_txt16, H, (long long)B * d.TM, H, H, st));
+  if (NC <= 1 && !persist_text(d)) MMQG_TRY(cvt_f32_bf16_2d(w.m_txt, H, w.m_txt16, H, (long long)B * d.TM, H, H, st));
   // decoder state slab 0 := encoder final state (train.py:169)
   const size_t n = (size_t)B * H;
   for (int l = 0; l < d.L; ++l) {
@@ -877,8 +880,10 @@ static int greedy_decode_bf16_on(const mmqg_dims& d, const mmqg_tensors& P, cons
         MMQG_TRY(Tc(w.hs_dec[l - 1] + (size_t)(t + 1) * B * H, H, false, w.wd_cat[l] + H, 2 * H, false, B, G, H, acts, G)
                      .second(hprev, H, w.wd_cat[l], 2 * H, H).bias(w.bsum_dec[l]).run(st));
       }
+      PreSpec fwd_only;
+      fwd_only.no_save = 1;          // decoding has no backward pass: the activated gates are not kept
       MMQG_TRY(lstm_pointwise_fwd_bf16(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
-                                       w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st));
+                                       w.hs_dec[l] + (size_t)(t + 1) * B * H, H, nullptr, 0, B, H, st, DropSpec(), fwd_only));
     }
     }
     const b16* htop = w.hs_dec[d.L - 1] + (size_t)(t + 1) * B * H;

@@ -20,6 +20,7 @@ struct PreSpec {
   long long stride = 0;
   const float* bias = nullptr;
   int add_gates = 0;
+  int no_save = 0;      // forward-only caller: the activated gates need not be written back (honoured by the vectorised bf16 kernel)
 };
 int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
                        int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, PreSpec ps = PreSpec());

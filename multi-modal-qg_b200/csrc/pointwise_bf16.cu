@@ -75,6 +75,37 @@ __global__ void lstm_pointwise_fwd_bf16_kernel(float* __restrict__ gates, int ld
         __float2bfloat16_rn(h * drop_scale(dr.seed + (dr.ctr ? *dr.ctr : 0ull), dr.sid, dr.base + (unsigned long long)idx, dr.p, 1.0f / (1.0f - dr.p)));
 }
 
+// The plain case (pre-activations in `gates`, no dropout) four units per thread with 16-byte accesses; no_save: the activated
+// gates are not written back (forward-only callers: greedy / sampling decode have no backward pass to feed).
+__global__ void lstm_pointwise_fwd_bf16_v4_kernel(float* __restrict__ gates, int ldg, const float* __restrict__ c_prev, int ldcp,
+                                                  float* __restrict__ c_out, int ldc, bf16* __restrict__ h_out, int ldh,
+                                                  float* __restrict__ h2, int ldh2, int B, int H, int no_save) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int H4 = H >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H4) return;
+  const int b = idx / H4, j = (idx - b * H4) * 4;
+  float* g = gates + (size_t)b * ldg + j;
+  const float4 pi = *reinterpret_cast<const float4*>(g), pf = *reinterpret_cast<const float4*>(g + H),
+               pg = *reinterpret_cast<const float4*>(g + 2 * H), po = *reinterpret_cast<const float4*>(g + 3 * H);
+  const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + (size_t)b * ldcp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 i = make_float4(sigm(pi.x), sigm(pi.y), sigm(pi.z), sigm(pi.w)), f = make_float4(sigm(pf.x), sigm(pf.y), sigm(pf.z), sigm(pf.w)),
+               gg = make_float4(tanhf(pg.x), tanhf(pg.y), tanhf(pg.z), tanhf(pg.w)), o = make_float4(sigm(po.x), sigm(po.y), sigm(po.z), sigm(po.w));
+  const float4 c = make_float4(f.x * cp.x + i.x * gg.x, f.y * cp.y + i.y * gg.y, f.z * cp.z + i.z * gg.z, f.w * cp.w + i.w * gg.w);
+  const float4 h = make_float4(o.x * tanhf(c.x), o.y * tanhf(c.y), o.z * tanhf(c.z), o.w * tanhf(c.w));
+  if (!no_save) {
+    *reinterpret_cast<float4*>(g) = i; *reinterpret_cast<float4*>(g + H) = f;
+    *reinterpret_cast<float4*>(g + 2 * H) = gg; *reinterpret_cast<float4*>(g + 3 * H) = o;
+  }
+  *reinterpret_cast<float4*>(c_out + (size_t)b * ldc + j) = c;
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(h_out + (size_t)b * ldh + j) = u;
+  if (h2) *reinterpret_cast<float4*>(h2 + (size_t)b * ldh2 + j) = h;
+}
+
 __global__ void lstm_pointwise_bwd_bf16_kernel(const float* __restrict__ acts, int ldg, const float* __restrict__ c_prev,
                                                int ldcp, const float* __restrict__ c_new, int ldc,
                                                const float* __restrict__ dh0, int ldh0, int n0, long long s0,
@@ -377,6 +408,14 @@ int lstm_pointwise_fwd_bf16(float* gates, int ldg, const float* c_prev, int ldcp
   MMQG_REQUIRE(gates && c_out && h_out && B > 0 && H > 0, "lstm_pointwise_fwd_bf16: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (c_prev ? 10 : 9) + 2.0 * n + (h2 ? 4.0 * n : 0));
+  auto al = [](const void* p, int a) { return reinterpret_cast<uintptr_t>(p) % a == 0; };
+  if (!ps.part && !dr.out && H % 4 == 0 && ldg % 4 == 0 && ldc % 4 == 0 && ldh % 4 == 0 && (!c_prev || ldcp % 4 == 0) && (!h2 || ldh2 % 4 == 0) &&
+      al(gates, 16) && al(c_out, 16) && al(h_out, 8) && (!c_prev || al(c_prev, 16)) && (!h2 || al(h2, 16))) {
+    MMQG_CUDA(launch_k(lstm_pointwise_fwd_bf16_v4_kernel, dim3(ceil_div(n / 4, 256)), dim3(256), 0, st, gates, ldg, c_prev, ldcp, c_out, ldc,
+                       reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H, ps.no_save));
+    MMQG_LAUNCH_CHECK();
+    return 0;
+  }
   MMQG_CUDA(launch_k(lstm_pointwise_fwd_bf16_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, gates, ldg, c_prev, ldcp, c_out, ldc,
                      reinterpret_cast<bf16*>(h_out), ldh, h2, ldh2, B, H, dr, ps));
   MMQG_LAUNCH_CHECK();

@@ -16,7 +16,14 @@ class GradReducer:
     the cooperative persistent kernels are waiting for.  The sum is then formed in bf16 (relative error per element
     ~2^-8 * sqrt(world)); fp32 is exact up to summation order.  CUDA buckets only."""
 
-    def __init__(self, engine, world_size, group=None, comm_dtype=torch.float32):
+    def __init__(self, engine, world_size, group=None, comm_dtype=torch.float32, schedule="overlap"):
+        """schedule: "overlap" = one all-reduce per gradient group, started where the group becomes final, under the rest of
+        the backward; "late" = ONE all-reduce of the whole flat gradient buffer after the last group is final (nothing
+        competes with the cooperative persistent kernels for SMs; the wire time is exposed instead)."""
+        assert schedule in ("overlap", "late")
+        self.schedule = schedule
+        self.flat = getattr(engine, "flat_grads", None)
+        assert schedule == "overlap" or self.flat is not None, "the late schedule reduces engine.flat_grads"
         self.buckets = engine.grad_buckets
         self.world = world_size
         self.group = group
@@ -30,6 +37,7 @@ class GradReducer:
             self._lib = _cabi.lib()
             self._check = _cabi.check
             self.stage = [torch.empty(b.numel(), dtype=torch.bfloat16, device=b.device) for b in self.buckets]
+            self.stage_flat = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=self.flat.device) if schedule == "late" else None
         if self.buckets[0].is_cuda:
             # ready events the library records where each gradient group becomes final, and the
             # stream the all-reduces are issued from (so they are ordered after the event only,
@@ -50,6 +58,19 @@ class GradReducer:
     def after_backward(self):
         """After engine.backward_events(): start the all-reduce of every group, each behind its ready event on
         the side stream (loss head, decoder, video, text layers top to bottom, shared embedding)."""
+        if self.schedule == "late":
+            for e in self.events:
+                self.side.wait_event(e)
+            with torch.cuda.stream(self.side):
+                if self.stage is None:
+                    self.works.append(dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                else:
+                    b, s = self.flat, self.stage_flat
+                    sp = torch.cuda.current_stream().cuda_stream
+                    self._check(self._lib.mmqg_pack_bf16(b.data_ptr(), s.data_ptr(), b.numel(), sp))
+                    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=self.group, async_op=True).wait()   # stream-level wait
+                    self._check(self._lib.mmqg_unpack_bf16(s.data_ptr(), b.data_ptr(), b.numel(), sp))
+            return
         for i in range(len(self.buckets)):
             self.side.wait_event(self.events[i])
             with torch.cuda.stream(self.side):

@@ -25,6 +25,19 @@ def test_dp_two_gpus_matches_single_gpu(mode):
     assert out.stdout.count("dp world=2") == 4, out.stdout
 
 
+@pytest.mark.parametrize("comm", ["fp32", "bf16"])
+def test_dp_two_gpus_late_schedule(comm):
+    """GradReducer(schedule="late"): one all-reduce of the flat gradient buffer after the backward; eager and graph."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29544" if comm == "fp32" else "29545", os.path.join(ROOT, "tools", "check_dp.py"), "--mode", "bf16",
+           "--grad-comm", comm, "--reduce", "late"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("dp world=2") == 2, out.stdout
+
+
 def test_dp_two_gpus_bf16_gradient_exchange():
     """GradReducer(comm_dtype=bfloat16): buckets packed to bf16 (mmqg_pack_bf16), all-reduced, unpacked; eager and graph."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
