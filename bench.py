@@ -54,9 +54,10 @@ def parse():
     ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16", "auto"],
                     help="N > 1: element type of the gradient all-reduce (fp32 = exact sums; bf16 = buckets rounded to bf16 for the "
                          "exchange, half the NVLink bytes; auto = bf16 in bf16 mode)")
-    ap.add_argument("--reduce", default=os.environ.get("MMQG_REDUCE", "overlap"), choices=["overlap", "late"],
-                    help="N > 1: overlap = one all-reduce per gradient group under the rest of the backward; late = one all-reduce "
-                         "of the flat gradient buffer after the backward")
+    ap.add_argument("--reduce", default=os.environ.get("MMQG_REDUCE", "multimem"), choices=["overlap", "late", "multimem"],
+                    help="N > 1: overlap = one NCCL all-reduce per gradient group under the rest of the backward; late = one all-reduce "
+                         "of the flat gradient buffer after the backward; multimem = per group, our own reduce kernel over NVSwitch "
+                         "multicast memory (mmqg_allreduce_multimem; fp32 sums; falls back to overlap on every rank if any rank has no multicast mapping)")
     return ap.parse_args()
 
 
@@ -456,7 +457,23 @@ def main():
     pinned = {k: v.pin_memory() for k, v in host.items()}
     dbatch = eng.to_device(host)
     comm_bf16 = args.grad_comm == "bf16" or (args.grad_comm == "auto" and args.mode == "bf16")
-    reducer = GradReducer(eng, world, comm_dtype=torch.bfloat16 if comm_bf16 else torch.float32, schedule=args.reduce) if world > 1 else None
+    reducer = None
+    if world > 1:
+        import torch.distributed as dist
+        if args.reduce == "multimem" and comm_bf16:
+            args.reduce = "overlap"            # the multimem kernel sums in fp32
+        if args.reduce == "multimem":          # needs NVSwitch multicast on every rank: agree, else NCCL
+            ok = torch.ones(1, device=dev)
+            try:
+                reducer = GradReducer(eng, world, schedule="multimem")
+            except Exception as e:             # noqa: BLE001
+                print(f"[bench rank {rank}] multimem all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr, flush=True)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) == 0.0:
+                args.reduce, reducer = "overlap", None
+        if reducer is None:
+            reducer = GradReducer(eng, world, comm_dtype=torch.bfloat16 if comm_bf16 else torch.float32, schedule=args.reduce)
     gscale = 1.0 / world
 
     if args.adam:

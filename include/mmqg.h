@@ -385,6 +385,13 @@ int mmqg_conv_bwd_x(const float* dz, const float* w, float* dxn, int N, int Cin,
 int mmqg_pack_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 int mmqg_unpack_bf16(const void* src_bf16, float* dst, long long n, void* stream);
 
+/* In-place all-reduce (sum) of a gradient bucket that lives in NVSwitch multicast memory (the reference has
+ * no exchange step).  mc = MULTICAST address of the bucket (the same symmetric allocation mapped on every rank, 16-byte
+ * aligned), n floats (multiple of 4); signal_pads = device array of `world` pointers to the ranks' signal pads (peer-mapped,
+ * >= ctas * world * 4 bytes each, zero between calls).  Every rank makes the same sequence of calls with the same n and ctas.
+ * One kernel of `ctas` CTAs: barrier across ranks, multimem.ld_reduce + multimem.st over the rank's slice, barrier. */
+int mmqg_allreduce_multimem(float* mc, long long n, void* const* signal_pads, int rank, int world, int ctas, void* stream);
+
 /* out(n) = sum_m X(m,n)  (bias gradients). */
 int mmqg_colsum(const float* X, int ldx, float* out, int M, int N, float beta, void* stream);
 

@@ -93,6 +93,7 @@ SYMBOLS = {
     "mmqg_bn_maxpool_fwd": (_i, [_fp] * 5 + [_i] * 5 + [_fp]),
     "mmqg_maxpool_bwd": (_i, [_fp] * 3 + [_i] * 5 + [_fp]),
     "mmqg_bn_relu_bwd": (_i, [_fp] * 7 + [_i] * 4 + [_fp]),
+    "mmqg_allreduce_multimem": (_i, [_fp, _ll, _fp, _i, _i, _i, _fp]),
     "mmqg_bn_relu_pool_bwd": (_i, [_fp] * 6 + [_i] + [_fp] * 2 + [_i] * 4 + [_fp]),
     "mmqg_conv_bwd_w": (_i, [_fp] * 6 + [_i] * 7 + [_fp]),
     "mmqg_conv_bwd_x": (_i, [_fp] * 3 + [_i] * 7 + [_fp]),

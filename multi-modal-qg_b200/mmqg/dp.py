@@ -19,9 +19,16 @@ class GradReducer:
     def __init__(self, engine, world_size, group=None, comm_dtype=torch.float32, schedule="overlap"):
         """schedule: "overlap" = one all-reduce per gradient group, started where the group becomes final, under the rest of
         the backward; "late" = ONE all-reduce of the whole flat gradient buffer after the last group is final (nothing
-        competes with the cooperative persistent kernels for SMs; the wire time is exposed instead)."""
-        assert schedule in ("overlap", "late")
+        competes with the cooperative persistent kernels for SMs; the wire time is exposed instead); "multimem" = per group like
+        "overlap", but with our own reduce kernel over NVSwitch multicast memory instead of NCCL (mmqg_allreduce_multimem: the
+        engine's flat gradient buffer moves into a symmetric allocation; fp32 sums; needs multicast support)."""
+        assert schedule != "multimem" or comm_dtype == torch.float32, "the multimem kernel sums in fp32"
+        assert schedule in ("overlap", "late", "multimem")
         self.schedule = schedule
+        self.mm = None
+        if schedule == "multimem":
+            self.mm = _MultimemBuckets(engine, world_size, group)      # moves engine.flat_grads into symmetric memory
+            schedule = "overlap"
         self.flat = getattr(engine, "flat_grads", None)
         assert schedule == "overlap" or self.flat is not None, "the late schedule reduces engine.flat_grads"
         self.buckets = engine.grad_buckets
@@ -58,6 +65,12 @@ class GradReducer:
     def after_backward(self):
         """After engine.backward_events(): start the all-reduce of every group, each behind its ready event on
         the side stream (loss head, decoder, video, text layers top to bottom, shared embedding)."""
+        if self.mm is not None:      # our own reduce kernel over NVSwitch multicast memory, one launch per group behind its event
+            for i in range(len(self.buckets)):
+                self.side.wait_event(self.events[i])
+                with torch.cuda.stream(self.side):
+                    self.mm.all_reduce(i)
+            return
         if self.schedule == "late":
             for e in self.events:
                 self.side.wait_event(e)
@@ -90,6 +103,39 @@ class GradReducer:
         self.works.clear()
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
+
+
+class _MultimemBuckets:
+    """The engine's flat gradient buffer in symmetric memory (torch.distributed._symmetric_memory: every rank's copy mapped
+    on every rank + one NVSwitch multicast address for all of them) and the launcher of mmqg_allreduce_multimem per bucket."""
+
+    def __init__(self, engine, world_size, group=None):
+        import os
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _cabi
+        pg = group if group is not None else dist.group.WORLD
+        name = pg.group_name
+        try:
+            symm_mem.enable_symm_mem_for_group(name)
+        except Exception:
+            pass
+        flat = symm_mem.empty(engine.flat_grads.numel(), dtype=torch.float32, device=engine.flat_grads.device)
+        self.hdl = symm_mem.rendezvous(flat, name)
+        if not self.hdl.multicast_ptr:
+            raise _cabi.MmqgError("multimem all-reduce: no multicast mapping for the gradient buffer (needs NVSwitch + driver support)")
+        assert self.hdl.signal_pad_size >= 64 * world_size * 4
+        engine.use_flat_grads(flat)
+        self.engine, self.rank, self.world = engine, self.hdl.rank, self.hdl.world_size
+        # CTAs per launch: few, so that the kernel fits beside the two cooperative 64-CTA recurrent kernels (B200, N=8, cfg-2:
+        # 8 -> 5.63 ms per step, 16 -> 5.67, 32 -> 5.72; NCCL 5.83)
+        self.ctas = int(os.environ.get("MMQG_MM_CTAS", "8"))
+        self._lib, self._check = _cabi.lib(), _cabi.check
+        dist.barrier(group=pg)
+
+    def all_reduce(self, i):
+        lo, hi = self.engine.bucket_range[i]
+        self._check(self._lib.mmqg_allreduce_multimem(self.hdl.multicast_ptr + 4 * lo, hi - lo, self.hdl.signal_pad_ptrs_dev,
+                                                      self.rank, self.world, self.ctas, torch.cuda.current_stream().cuda_stream))
 
 
 def shard_batch(batch: dict, rank: int, world: int) -> dict:

@@ -56,6 +56,8 @@ class TrainEngine:
             self.params[n].copy_(params[n].detach().to(self.device, torch.float32))
             self.grads[n] = self.flat_grads[o:o + k].view(shape)
         self.grad_buckets = [self.flat_grads[lo:hi] for lo, hi in bucket_range]
+        self.bucket_range = bucket_range
+        self._shapes = shapes
         self._adam = None
         self._cd = _cabi.c_dims(dims)
         self._cp = _cabi.c_tensors(self.params, dims.L)
@@ -68,6 +70,19 @@ class TrainEngine:
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._greedy_ws = None
         self.seed = 0          # base dropout seed; the library adds the number of forward calls made so far
+
+    def use_flat_grads(self, flat):
+        """Move the gradients into a caller-provided flat fp32 buffer of the same length (e.g. a symmetric-memory
+        allocation the multimem all-reduce works on, mmqg.dp.GradReducer(schedule="multimem")): self.grads,
+        self.grad_buckets and the C-ABI struct are rebuilt as views of it."""
+        assert flat.numel() == self.flat_grads.numel() and flat.dtype == torch.float32 and flat.is_cuda and flat.is_contiguous()
+        flat.zero_()
+        self.flat_grads = flat
+        for n, shape in self._shapes.items():
+            o, k = self.offsets[n], int(torch.Size(shape).numel())
+            self.grads[n] = flat[o:o + k].view(shape)
+        self.grad_buckets = [flat[lo:hi] for lo, hi in self.bucket_range]
+        self._cg = _cabi.c_tensors(self.grads, self.d.L)
 
     # -- batches -------------------------------------------------------------------------
     LENGTH_KEYS = ("ctx_len", "tgt_len", "n_frames")

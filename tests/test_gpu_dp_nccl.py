@@ -38,6 +38,20 @@ def test_dp_two_gpus_late_schedule(comm):
     assert out.stdout.count("dp world=2") == 2, out.stdout
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_dp_two_gpus_multimem_allreduce(mode):
+    """GradReducer(schedule="multimem"): gradients in symmetric memory, one mmqg_allreduce_multimem launch per group (barrier
+    over the peers' signal pads, multimem.ld_reduce / multimem.st over NVSwitch multicast memory); eager and graph."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29546" if mode == "fp32" else "29547", os.path.join(ROOT, "tools", "check_dp.py"), "--mode", mode,
+           "--reduce", "multimem"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("dp world=2") == 2, out.stdout
+
+
 def test_dp_two_gpus_bf16_gradient_exchange():
     """GradReducer(comm_dtype=bfloat16): buckets packed to bf16 (mmqg_pack_bf16), all-reduced, unpacked; eager and graph."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:

@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", default="fp32")
     ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"], help="element type of the gradient all-reduce")
-    ap.add_argument("--reduce", default="overlap", choices=["overlap", "late"], help="GradReducer schedule")
+    ap.add_argument("--reduce", default="overlap", choices=["overlap", "late", "multimem"], help="GradReducer schedule")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -42,7 +42,7 @@ def main():
     local_batch = eng.to_device(shard_batch(gbatch, rank, world))
     graph = None
     # the bf16 exchange lives on the event-driven path only (after_backward); on_phase() always sums in fp32
-    for overlap in (("events", "graph") if args.grad_comm == "bf16" or args.reduce == "late" else ("events", "graph", True, False)):
+    for overlap in (("events", "graph") if args.grad_comm == "bf16" or args.reduce != "overlap" else ("events", "graph", True, False)):
         if overlap == "events":                     # event-driven overlap (mmqg_train_backward_events)
             loss = eng.step_dp(local_batch, red, 1.0 / world)
             red.finish()
