@@ -3,9 +3,9 @@
 // as the fallback for every other kernel size / stride / channel count.
 //
 //   forward / input gradient : one thread = 4 consecutive pixels of one row, all output channels.  The layer's weights sit in
-//       __constant__ memory and every loop is unrolled, so each FFMA takes its weight as a constant-bank operand: no
-//       shared-memory or register traffic for weights at all, and the 6-pixel input window of a (channel, row) is loaded once
-//       for 12 * Cout FMAs.
+//       __constant__ memory and every loop is unrolled, so the weights reach the FFMAs through the uniform datapath (SASS: LDCU
+//       into uniform registers, ~1 per 6 FFMAs): no shared-memory traffic and no per-thread registers for weights, and the
+//       6-pixel input window of a (channel, row) is loaded once for 12 * Cout FMAs.
 //   weight gradient : persistent blocks walk (image, 8-row) tiles; the tile of the (normalised) input and of d z is staged in
 //       shared memory ONCE (each tensor is read exactly once from HBM, against Cin times before), warp (ci, ky) keeps its
 //       Cout x 3 partial sums in registers over all tiles of the block and the lanes run over the tile's pixels; one
