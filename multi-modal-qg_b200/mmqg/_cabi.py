@@ -6,7 +6,7 @@ import os
 from .dims import Dims
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmmqg.so")
+LIB_PATH = os.environ.get("MMQG_LIB") or os.path.join(HERE, "libmmqg.so")      # MMQG_LIB: an alternative in-tree build (A/B runs)
 MAX_LAYERS = 4
 MODE_FP32, MODE_BF16, MODE_FP32_TC = 0, 1, 2
 
