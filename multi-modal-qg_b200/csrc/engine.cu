@@ -48,6 +48,7 @@ struct Ws {
   float *dh_rec[MMQG_MAX_LAYERS], *dc[MMQG_MAX_LAYERS], *dx_above, *dq_h, *dctx_all, *dm_txt, *dm_vid, *de_dec;
   float *dh_rec_enc, *dh_rec_vid, *dx_text, *dc_v;
   float *xcat;
+  void *x3_hs, *x3_dg;                // h_t / dG_t of the current recurrent step as bf16 [hi | lo], written by the cell kernels
   float* pre_part;                    // split-K partial pre-activations of one recurrent step (tensor-core parity mode)
   void *x3_arena, *x3_sa, *x3_sb;     // MMQG_MODE_FP32_TC: split copies (gemm_f32x3.cu)
   size_t x3_arena_bytes, x3_sa_bytes, x3_sb_bytes;
@@ -136,6 +137,8 @@ static Ws carve(const mmqg_dims& d, int T_q, void* base, bool tc = false) {
     size_t sb = std::max(f32x3_split_bytes(1, std::max<long long>(X0, H), NB), f32x3_split_bytes(1, d.F_v, B));
     w.x3_sb_bytes = sb + 4096;
     w.pre_part = c.take<float>((size_t)kPreSplitMax * B * std::max(G, Gv));
+    w.x3_hs = c.take<char>((size_t)B * 2 * std::max(H, (size_t)d.H_v) * 2);
+    w.x3_dg = c.take<char>((size_t)B * 2 * std::max(G, Gv) * 2);
     w.x3_arena = c.take<char>(w.x3_arena_bytes);
     w.x3_sa = c.take<char>(w.x3_sa_bytes);
     w.x3_sb = c.take<char>(w.x3_sb_bytes);
@@ -172,6 +175,7 @@ static thread_local bool g32_tc = false;
 struct GemmCall {
   mmqg_gemm_args a;
   bool b_const = false;
+  const void* a_split = nullptr;
   GemmCall(const float* A, int lda, bool tA, const float* Bm, int ldb, bool tB, int M, int N, int K, float* C, int ldc) {
     a = mmqg_gemm_args{};
     a.A = A; a.lda = lda; a.transA = tA; a.B = Bm; a.ldb = ldb; a.transB = tB;
@@ -185,7 +189,12 @@ struct GemmCall {
   GemmCall& bias(const float* b) { a.bias = b; return *this; }
   GemmCall& split(int s, long long stride) { a.split_k = s; a.c_split_stride = stride; return *this; }
   GemmCall& w() { b_const = true; return *this; }      // B (and B2) are parameters: constant during the call
-  int run(cudaStream_t st) { return g32_tc ? gemm_f32x3(a, b_const, st) : gemm_f32(a, st); }
+  GemmCall& presplit(const void* p) { a_split = p; return *this; }   // tensor-core parity mode: A already split by its producer kernel
+  int run(cudaStream_t st) {
+    if (!g32_tc) return gemm_f32(a, st);
+    if (a_split) f32x3_presplit_a(a_split);
+    return gemm_f32x3(a, b_const, st);
+  }
 };
 
 // Tensor-core parity mode: the (B x 4H) pre-activation product of one recurrent step is issued split-K so that ~128 SMs
@@ -254,9 +263,11 @@ static int encoder_forward(const mmqg_dims& d, const mmqg_tensors& P, const mmqg
       PreSpec ps;
       if (t > 0) {
         GemmCall g(w.hs_text[l] + (size_t)t * B * H, H, false, P.text_w_hh[l], H, true, B, G, H, acts, G);
+        if (g32_tc && H % 8 == 0) g.presplit(w.x3_hs);      // h_{t-1} as [hi | lo], written by the cell kernel of step t-1
         if (g32_tc) MMQG_TRY(step_pre_tc(g, w.pre_part, B, G, nullptr, true, &ps, st));
         else MMQG_TRY(g.accumulate(true).w().run(st));
       }
+      if (g32_tc && H % 8 == 0 && t + 1 < d.T_t) ps.h_split = w.x3_hs;
       MMQG_TRY(lstm_pointwise_fwd(acts, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr, H,
                                   w.cs_text[l] + (size_t)(t + 1) * B * H, H, w.hs_text[l] + (size_t)(t + 1) * B * H, H,
                                   l == d.L - 1 ? w.m_txt + (size_t)t * H : nullptr, d.TM * H, B, H, st, ps));
@@ -452,6 +463,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
   const int B = d.B, H = d.H, G = 4 * d.H, E = d.E, Q = d.E + d.H, C = d.H + d.H_a + d.H_v, X0 = E + C;
   const int R = d.T_q * B, Sp = w.S_pad, L = d.L;
   const int kSplit = g32_tc ? kSplitMax : 4;
+  const bool x3dg = g32_tc && d.H % 2 == 0;      // the cell-gradient kernels also write dG as bf16 [hi | lo] (4H % 8 == 0)
   const long long ps = (long long)B * H;       // split-K partial stride for (B,H) products
   const AttnShape as = attn_shape(d);
 
@@ -484,12 +496,13 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
                                        (unsigned long long)t * B * H, g32_drop_p, st));
         }
         MMQG_TRY(lstm_pointwise_bwd(acts, G, w.cs_dec[l] + (size_t)t * B * H, H, w.cs_dec[l] + (size_t)(t + 1) * B * H, H,
-                                    dh0, H, kSplit, ps, dh1, H, n1, ps, dh2, H, w.dc[l], H, last ? 1 : 0, B, H, st));
-        MMQG_TRY(GemmCall(acts, G, false, P.dec_w_hh[l], H, false, B, H, G, w.dh_rec[l], H).split(kSplit, ps).w().run(st));
+                                    dh0, H, kSplit, ps, dh1, H, n1, ps, dh2, H, w.dc[l], H, last ? 1 : 0, B, H, st, x3dg ? w.x3_dg : nullptr));
+        const void* dgs = x3dg ? w.x3_dg : nullptr;       // dG_l(t) as [hi | lo], shared by the products below
+        MMQG_TRY(GemmCall(acts, G, false, P.dec_w_hh[l], H, false, B, H, G, w.dh_rec[l], H).split(kSplit, ps).w().presplit(dgs).run(st));
         if (l > 0)
-          MMQG_TRY(GemmCall(acts, G, false, P.dec_w_ih[l], H, false, B, H, G, w.dx_above, H).split(kSplit, ps).w().run(st));
+          MMQG_TRY(GemmCall(acts, G, false, P.dec_w_ih[l], H, false, B, H, G, w.dx_above, H).split(kSplit, ps).w().presplit(dgs).run(st));
         else
-          MMQG_TRY(GemmCall(acts, G, false, P.dec_w_ih[0] + E, X0, false, B, C, G, w.dctx_all + (size_t)t * B * C, C).w().run(st));
+          MMQG_TRY(GemmCall(acts, G, false, P.dec_w_ih[0] + E, X0, false, B, C, G, w.dctx_all + (size_t)t * B * C, C).w().presplit(dgs).run(st));
       }
       // dS(t) goes to its own buffer: the softmax weights are needed again by the hoisted
       // memory gradients (attn_dmem) after the loop.
@@ -576,9 +589,10 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
       const int ldh2 = l == L - 1 ? d.TM * H : H;
       MMQG_TRY(lstm_pointwise_bwd(acts, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr, H,
                                   w.cs_text[l] + (size_t)(t + 1) * B * H, H, dh0, H, kSplit, ps, dh1, H, kSplit, ps, dh2,
-                                  ldh2, w.dc[l], H, 0, B, H, st));
+                                  ldh2, w.dc[l], H, 0, B, H, st, x3dg && t > 0 ? w.x3_dg : nullptr));
       if (t > 0)
-        MMQG_TRY(GemmCall(acts, G, false, P.text_w_hh[l], H, false, B, H, G, w.dh_rec_enc, H).split(kSplit, ps).w().run(st));
+        MMQG_TRY(GemmCall(acts, G, false, P.text_w_hh[l], H, false, B, H, G, w.dh_rec_enc, H).split(kSplit, ps).w()
+                     .presplit(x3dg ? w.x3_dg : nullptr).run(st));
     }
     const float* dG = w.acts_text[l];
     const float* X = l == 0 ? w.x0_text : (g32_drop_p > 0.f ? w.xdrop_text[l - 1] : w.hs_text[l - 1] + (size_t)B * H);

@@ -85,6 +85,8 @@ struct X3Ctx {
   std::vector<X3Ent> ents;
 };
 static thread_local X3Ctx tl_x3;
+static thread_local const void* tl_presplit_a = nullptr;
+void f32x3_presplit_a(const void* a_split) { tl_presplit_a = a_split; }
 
 void f32x3_bind(void* arena, size_t arena_bytes, void* sa, size_t sa_bytes, void* sb, size_t sb_bytes) {
   X3Ctx& c = tl_x3;
@@ -137,8 +139,15 @@ int gemm_f32x3(const mmqg_gemm_args& a, bool b_const, cudaStream_t st) {
   long long ldA, ldB;
   const size_t ea = split_elems(amn, a.M, a.K, a.K2, &KcA, &ldA);
   const size_t eb = split_elems(bmn, a.N, a.K, a.K2, &KcB, &ldB);
-  MMQG_REQUIRE(ea <= c.sa_elems, "gemm_f32x3: A split needs %zu elements, scratch holds %zu", ea, c.sa_elems);
-  MMQG_TRY(run_split(amn, a.A, a.lda, a.K, a.A2, a.lda2, a.K2, a.M, c.sa, KcA, ldA, 0, st));
+  const bf16* A_hi = c.sa;
+  if (tl_presplit_a) {      // the producer kernel wrote [hi | lo] itself
+    A_hi = reinterpret_cast<const bf16*>(tl_presplit_a);
+    tl_presplit_a = nullptr;
+    MMQG_REQUIRE(!amn && a.K2 == 0 && a.K % 8 == 0, "gemm_f32x3: pre-split A needs a K-contiguous single operand with K %% 8 == 0");
+  } else {
+    MMQG_REQUIRE(ea <= c.sa_elems, "gemm_f32x3: A split needs %zu elements, scratch holds %zu", ea, c.sa_elems);
+    MMQG_TRY(run_split(amn, a.A, a.lda, a.K, a.A2, a.lda2, a.K2, a.M, c.sa, KcA, ldA, 0, st));
+  }
   bf16* sbp = nullptr;
   if (b_const) {
     for (const X3Ent& e : c.ents)
@@ -163,7 +172,6 @@ int gemm_f32x3(const mmqg_gemm_args& a, bool b_const, cudaStream_t st) {
   g.C = a.C; g.ldc = a.ldc; g.c_bf16 = 0;
   g.Cin = a.Cin; g.ldcin = a.ldcin; g.bias = a.bias; g.M = a.M; g.N = a.N; g.alpha = a.alpha; g.beta = a.beta;
   g.split_k = a.split_k; g.c_split_stride = a.c_split_stride;
-  const bf16* A_hi = c.sa;
   const bf16* B_lo = sbp;
   const bf16* B_hi = bmn ? sbp + (long long)KcB * ldB : sbp + KcB;
   g.A = A_hi; g.B = B_lo; g.K = 2 * KcA;            // hi*lo + lo*hi

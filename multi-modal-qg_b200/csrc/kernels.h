@@ -10,6 +10,8 @@ int gemm_bf16(const mmqg_gemm_bf16_args& a, cudaStream_t st);
 // C-ABI call and their split copy is cached in the arena bound by f32x3_bind (which also forgets the previous call's copies)
 int gemm_f32x3(const mmqg_gemm_args& a, bool b_const, cudaStream_t st);
 void f32x3_bind(void* arena, size_t arena_bytes, void* sa, size_t sa_bytes, void* sb, size_t sb_bytes);
+// the NEXT gemm_f32x3 call takes its A operand already split ([hi | lo], K contiguous, pitch 2*K, K % 8 == 0, no second pair)
+void f32x3_presplit_a(const void* a_split);
 size_t f32x3_split_bytes(int mn, long long n, long long K);
 
 // Pre-activations handed to the forward cell kernel as split-K partial sums: pre = (gates if
@@ -20,6 +22,8 @@ struct PreSpec {
   long long stride = 0;
   const float* bias = nullptr;
   int add_gates = 0;
+  void* h_split = nullptr;   // fp32 cell kernel (tensor-core parity mode): h also as bf16 [hi(H) | lo(H)] rows of pitch 2H = the next
+                             // step's pre-split A operand (gemm_f32x3.cu), saving that step's split launch
   int no_save = 0;      // forward-only caller: the activated gates need not be written back (honoured by the vectorised bf16 kernel)
 };
 int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
@@ -27,7 +31,7 @@ int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, flo
 int lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                        const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,
                        const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, int B, int H,
-                       cudaStream_t st);
+                       cudaStream_t st, void* dg_split = nullptr);      // dg_split: d pre-activations also as bf16 [hi(4H) | lo(4H)], pitch 8H
 int embedding_gather(const float* emb, const int64_t* idx, float* out, int ldo, int N, int E, int V, cudaStream_t st);
 int embedding_scatter_add(float* demb, const int64_t* idx, const float* dx, int N, int E, int V, cudaStream_t st);
 int nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_stride, float* nll, int R, int V,

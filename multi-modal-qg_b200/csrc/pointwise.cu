@@ -3,6 +3,7 @@
 //   embedding gather/scatter  : encoder.py:96, decoder.py:75 and embedding_dense_backward
 //   nll_rows / argmax_rows    : train.py:174 (CrossEntropyLoss), train.py:107-108 (greedy)
 //   colsum                    : bias gradients
+#include <cuda_bf16.h>
 #include "kernels.h"
 
 namespace mmqg {
@@ -49,13 +50,20 @@ __global__ void lstm_pointwise_fwd_kernel(float* __restrict__ gates, int ldg, co
   c_out[(size_t)b * ldc + j] = c;
   h_out[(size_t)b * ldh + j] = h;
   if (h2) h2[(size_t)b * ldh2 + j] = h;
+  if (ps.h_split) {
+    __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(ps.h_split) + (size_t)b * 2 * H;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(h);
+    sp[j] = hi;
+    sp[H + j] = __float2bfloat16_rn(h - __bfloat162float(hi));
+  }
 }
 
 __global__ void lstm_pointwise_bwd_kernel(float* __restrict__ acts, int ldg, const float* __restrict__ c_prev,
                                           int ldcp, const float* __restrict__ c_new, int ldc,
                                           const float* __restrict__ dh0, int ldh0, int n0, long long s0,
                                           const float* __restrict__ dh1, int ldh1, int n1, long long s1, const float* __restrict__ dh2,
-                                          int ldh2, float* __restrict__ dc, int lddc, int dc_is_zero, int B, int H) {
+                                          int ldh2, float* __restrict__ dc, int lddc, int dc_is_zero, int B, int H,
+                                          __nv_bfloat16* __restrict__ dg_split) {
   pdl_launch_dependents();
   pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,11 +80,19 @@ __global__ void lstm_pointwise_bwd_kernel(float* __restrict__ acts, int ldg, con
   float cp = c_prev ? c_prev[(size_t)b * ldcp + j] : 0.f;
   float tc = tanhf(c_new[(size_t)b * ldc + j]);
   float dct = (dc_is_zero ? 0.f : dc[(size_t)b * lddc + j]) + dh * o * (1.f - tc * tc);
-  a[j] = dct * gg * i * (1.f - i);
-  a[H + j] = dct * cp * f * (1.f - f);
-  a[2 * H + j] = dct * i * (1.f - gg * gg);
-  a[3 * H + j] = dh * tc * o * (1.f - o);
+  const float dg[4] = {dct * gg * i * (1.f - i), dct * cp * f * (1.f - f), dct * i * (1.f - gg * gg), dh * tc * o * (1.f - o)};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) a[q * H + j] = dg[q];
   dc[(size_t)b * lddc + j] = dct * f;
+  if (dg_split) {      // [hi(4H) | lo(4H)] rows of pitch 8H: the pre-split A operand of dG . W (gemm_f32x3.cu)
+    __nv_bfloat16* sp = dg_split + (size_t)b * 8 * H;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(dg[q]);
+      sp[q * H + j] = hi;
+      sp[4 * H + q * H + j] = __float2bfloat16_rn(dg[q] - __bfloat162float(hi));
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -332,12 +348,12 @@ int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, flo
 int lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                        const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,
                        const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, int B, int H,
-                       cudaStream_t st) {
+                       cudaStream_t st, void* dg_split) {
   MMQG_REQUIRE(acts && c_new && dc && B > 0 && H > 0, "lstm_pointwise_bwd: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (10 + (c_prev ? 1 : 0) + (dh0 ? n0 : 0) + (dh1 ? n1 : 0) + (dh2 ? 1 : 0)));
   MMQG_CUDA(launch_k(lstm_pointwise_bwd_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, acts, ldg, c_prev, ldcp, c_new, ldc, dh0, ldh0, n0, s0,
-                     dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, B, H));
+                     dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, B, H, reinterpret_cast<__nv_bfloat16*>(dg_split)));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
