@@ -93,7 +93,7 @@ typedef struct {
    * per-sample loop (train.py:153-177) on each sample with its own lengths: encoder states
    * start from zero at the sample's first real token, memory rows beyond the length are the
    * zero padding of train.py:155-160, the loss sums over the sample's own target steps.
-   * Train path in MMQG_MODE_BF16 with the persistent recurrent kernels only. */
+   * All three modes (MMQG_MODE_BF16: shapes the persistent recurrent kernels take). */
   const int* ctx_len;
   const int* tgt_len;
   const int* n_frames;

@@ -48,6 +48,8 @@ struct Ws {
   float *dh_rec[MMQG_MAX_LAYERS], *dc[MMQG_MAX_LAYERS], *dx_above, *dq_h, *dctx_all, *dm_txt, *dm_vid, *de_dec;
   float *dh_rec_enc, *dh_rec_vid, *dx_text, *dc_v;
   float *xcat;
+  int *shift_t, *shift_v;             // per-sample lengths (mmqg_batch.ctx_len / n_frames): first live step of each sample
+  float *row_w, *frames_tm;           // loss-row weights (T_q*B); right-aligned time-major copy of the frames (T_v*B, F_v)
   void *x3_hs, *x3_dg;                // h_t / dG_t of the current recurrent step as bf16 [hi | lo], written by the cell kernels
   float* pre_part;                    // split-K partial pre-activations of one recurrent step (tensor-core parity mode)
   void *x3_arena, *x3_sa, *x3_sb;     // MMQG_MODE_FP32_TC: split copies (gemm_f32x3.cu)
@@ -122,6 +124,9 @@ static Ws carve(const mmqg_dims& d, int T_q, void* base, bool tc = false) {
   w.dc_v = c.take<float>(B * d.H_v);
   w.xcat = c.take<float>(B * X0);
   for (int l = 0; l + 1 < d.L; ++l) { w.xdrop_text[l] = c.take<float>((size_t)d.T_t * B * H); w.hdrop_dec[l] = c.take<float>(R * H); }
+  w.shift_t = c.take<int>(B); w.shift_v = c.take<int>(B);
+  w.row_w = c.take<float>(R);
+  w.frames_tm = c.take<float>((size_t)d.T_v * B * d.F_v);
   if (tc) {
     // constant operands: every GEMM weight once per layout (forward (N,K) and backward (K,N) roles), column slices padded
     auto ent = [](size_t r, size_t cc) { return 4 * (r + 8) * (cc + 16) + 512; };
@@ -217,6 +222,15 @@ static thread_local float g32_drop_p = 0.f;
 static thread_local unsigned long long g32_drop_seed = 0;
 static const int kSidText32 = 10, kSidDec32 = 20;
 
+// per-sample lengths of the current call (mmqg_batch.ctx_len / tgt_len / n_frames, NULL = uniform): sequences are right-aligned
+// in time inside the fixed (T, B) layout, exactly as in the bf16 mode
+static thread_local bool g32_len = false;
+static LenSpec len32(const int* shift, int t, int mem_shift) {
+  LenSpec l;
+  if (g32_len) { l.shift = shift; l.t_base = t; l.mem_shift = mem_shift; }
+  return l;
+}
+
 static AttnShape attn_shape(const mmqg_dims& d) { return AttnShape{d.B, d.TM, d.AM, d.H, d.H_a, d.H_v, d.T_t, d.T_v}; }
 
 // ----------------------------------------------------------------------------------------
@@ -226,6 +240,12 @@ static int encoder_forward(const mmqg_dims& d, const mmqg_tensors& P, const mmqg
   const int B = d.B, H = d.H, G = 4 * d.H, Hv = d.H_v, Gv = 4 * d.H_v;
   // Memories are (B,TM|AM,*) like the reference's padded tensors (train.py:155-160), but the
   // padding rows are never read (the context sums stop at T_t / T_v), so they are not zeroed.
+  if (g32_len) {      // rows beyond a sample's own length ARE read (the context sums run over T_t / T_v rows): zero padding of train.py:155-160
+    MMQG_TRY(audio_pad(bt.audio, w.m_aud, bt.n_frames, B, d.T_v, d.AM, d.H_a, st));
+    MMQG_CUDA(cudaMemsetAsync(w.m_vid, 0, sizeof(float) * (size_t)B * d.AM * Hv, st));
+    MMQG_CUDA(cudaMemsetAsync(w.m_txt, 0, sizeof(float) * (size_t)B * d.TM * H, st));
+    MMQG_TRY(frames_to_time_major_f32(bt.frames, w.frames_tm, w.shift_v, B, d.T_v, d.F_v, st));
+  } else
   MMQG_CUDA(cudaMemcpy2DAsync(w.m_aud, sizeof(float) * (size_t)d.AM * d.H_a, bt.audio,
                               sizeof(float) * (size_t)d.T_v * d.H_a, sizeof(float) * (size_t)d.T_v * d.H_a, B,
                               cudaMemcpyDeviceToDevice, st));
@@ -235,7 +255,8 @@ static int encoder_forward(const mmqg_dims& d, const mmqg_tensors& P, const mmqg
     StepGemmScope step_scope;
     PdlScope pdl_scope(g32_tc && pdl_enabled());
     float* acts = w.acts_v + (size_t)t * B * Gv;
-    GemmCall g(bt.frames + (size_t)t * d.F_v, d.T_v * d.F_v, false, P.vid_w_ih, d.F_v, true, B, Gv, d.F_v, acts, Gv);
+    GemmCall g(g32_len ? w.frames_tm + (size_t)t * B * d.F_v : bt.frames + (size_t)t * d.F_v, g32_len ? d.F_v : d.T_v * d.F_v, false,
+               P.vid_w_ih, d.F_v, true, B, Gv, d.F_v, acts, Gv);
     g.bias(w.bsum_vid);
     if (t > 0) g.second(w.hs_v + (size_t)t * B * Hv, Hv, P.vid_w_hh, Hv, Hv);
     PreSpec ps;
@@ -243,7 +264,7 @@ static int encoder_forward(const mmqg_dims& d, const mmqg_tensors& P, const mmqg
     else MMQG_TRY(g.w().run(st));
     MMQG_TRY(lstm_pointwise_fwd(acts, Gv, t > 0 ? w.cs_v + (size_t)t * B * Hv : nullptr, Hv,
                                 w.cs_v + (size_t)(t + 1) * B * Hv, Hv, w.hs_v + (size_t)(t + 1) * B * Hv, Hv,
-                                w.m_vid + (size_t)t * Hv, d.AM * Hv, B, Hv, st, ps));
+                                g32_len ? w.m_vid : w.m_vid + (size_t)t * Hv, d.AM * Hv, B, Hv, st, ps, len32(w.shift_v, t, 1)));
   }
   // text LSTM stack
   MMQG_TRY(embedding_gather(P.emb, w.idx_ctx, w.x0_text, d.E, d.T_t * B, d.E, d.V, st));
@@ -270,7 +291,8 @@ static int encoder_forward(const mmqg_dims& d, const mmqg_tensors& P, const mmqg
       if (g32_tc && H % 8 == 0 && t + 1 < d.T_t) ps.h_split = w.x3_hs;
       MMQG_TRY(lstm_pointwise_fwd(acts, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr, H,
                                   w.cs_text[l] + (size_t)(t + 1) * B * H, H, w.hs_text[l] + (size_t)(t + 1) * B * H, H,
-                                  l == d.L - 1 ? w.m_txt + (size_t)t * H : nullptr, d.TM * H, B, H, st, ps));
+                                  l == d.L - 1 ? (g32_len ? w.m_txt : w.m_txt + (size_t)t * H) : nullptr, d.TM * H, B, H, st, ps,
+                                  len32(w.shift_t, t, 1)));
     }
   }
   return 0;
@@ -333,7 +355,7 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
                               dropout_p, seed, as_stream(stream));
   g32_drop_p = dropout_p;
   g32_drop_seed = seed;
-  MMQG_REQUIRE(!batch->ctx_len && !batch->tgt_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
+  g32_len = batch->ctx_len || batch->tgt_len || batch->n_frames;
   g32_tc = mode == MMQG_MODE_FP32_TC;
   Ws w = carve(d, d.T_q, workspace, g32_tc);
   if (g32_tc) f32x3_bind(w.x3_arena, w.x3_arena_bytes, w.x3_sa, w.x3_sa_bytes, w.x3_sb, w.x3_sb_bytes);
@@ -345,7 +367,8 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   const int R = d.T_q * B, Sp = w.S_pad;
 
   if (dropout_p > 0.f) MMQG_TRY(bump_counter(w.seed_ctr, st));     // this call's masks: seed + (calls so far)
-  MMQG_TRY(build_indices(batch->context, batch->target, w.idx_ctx, w.idx_dec, w.tgt_tm, B, d.T_t, d.T_q, st));
+  if (g32_len) MMQG_TRY(prep_lengths(batch->ctx_len, batch->tgt_len, batch->n_frames, w.shift_t, w.shift_v, w.row_w, B, d.T_t, d.T_v, d.T_q, st));
+  MMQG_TRY(build_indices(batch->context, batch->target, w.idx_ctx, w.idx_dec, w.tgt_tm, B, d.T_t, d.T_q, st, g32_len ? w.shift_t : nullptr));
   MMQG_TRY(encoder_forward(d, P, *batch, w, st));
   MMQG_TRY(handoff_state(d, w, st));
   MMQG_TRY(pack_attention(d, P, w, st));
@@ -393,7 +416,7 @@ int mmqg_train_forward(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   for (int r0 = 0, first = 1; r0 < R; r0 += w.Rc, first = 0) {
     const int rc = R - r0 < w.Rc ? R - r0 : w.Rc;
     MMQG_TRY(GemmCall(htop + (size_t)r0 * H, H, false, P.out_w, H, true, rc, d.V, H, w.logits, d.V).bias(P.out_b).w().run(st));
-    MMQG_TRY(nll_rows(w.logits, d.V, w.tgt_tm + r0, 1, w.nll + r0, rc, d.V, dscale, st));
+    MMQG_TRY(nll_rows(w.logits, d.V, w.tgt_tm + r0, 1, w.nll + r0, rc, d.V, dscale, st, g32_len ? w.row_w + r0 : nullptr));
     if (want_grads) {
       MMQG_TRY(GemmCall(w.logits, d.V, false, P.out_w, H, false, rc, H, d.V, w.dhtop + (size_t)r0 * H, H).w().run(st));
       MMQG_TRY(GemmCall(w.logits, d.V, true, htop + (size_t)r0 * H, H, false, d.V, H, rc, grads->out_w, H)
@@ -451,7 +474,7 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
     return train_backward_bf16(d, *params, *batch, workspace, workspace_bytes, *grads, phase, dropout_p, seed, as_stream(stream));
   g32_drop_p = dropout_p;
   g32_drop_seed = seed;
-  MMQG_REQUIRE(!batch->ctx_len && !batch->tgt_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
+  g32_len = batch->ctx_len || batch->tgt_len || batch->n_frames;      // shift_t / shift_v / row_w were prepared by the forward call
   g32_tc = mode == MMQG_MODE_FP32_TC;
   Ws w = carve(d, d.T_q, workspace, g32_tc);
   if (g32_tc) f32x3_bind(w.x3_arena, w.x3_arena_bytes, w.x3_sa, w.x3_sa_bytes, w.x3_sb, w.x3_sb_bytes);
@@ -554,8 +577,8 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
       float* acts = w.acts_v + (size_t)t * B * Gv;
       MMQG_TRY(lstm_pointwise_bwd(acts, Gv, t > 0 ? w.cs_v + (size_t)t * B * Hv : nullptr, Hv,
                                   w.cs_v + (size_t)(t + 1) * B * Hv, Hv, last ? nullptr : w.dh_rec_vid, Hv, kSplit, pv,
-                                  nullptr, 0, 0, 0, w.dm_vid + (size_t)t * Hv, d.AM * Hv, w.dc_v, Hv, last ? 1 : 0, B, Hv,
-                                  st));
+                                  nullptr, 0, 0, 0, g32_len ? w.dm_vid : w.dm_vid + (size_t)t * Hv, d.AM * Hv, w.dc_v, Hv, last ? 1 : 0, B, Hv,
+                                  st, nullptr, len32(w.shift_v, t, 1)));
       if (t > 0)
         MMQG_TRY(GemmCall(acts, Gv, false, P.vid_w_hh, Hv, false, B, Hv, Gv, w.dh_rec_vid, Hv).split(kSplit, pv).w().run(st));
     }
@@ -565,8 +588,8 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
     else
       MMQG_CUDA(cudaMemsetAsync(Gd.vid_w_hh, 0, sizeof(float) * (size_t)Gv * Hv, st));
     for (int t = 0; t < d.T_v; ++t)
-      MMQG_TRY(GemmCall(w.acts_v + (size_t)t * B * Gv, Gv, true, batch->frames + (size_t)t * d.F_v, d.T_v * d.F_v, false,
-                        Gv, d.F_v, B, Gd.vid_w_ih, d.F_v).accumulate(t > 0).run(st));
+      MMQG_TRY(GemmCall(w.acts_v + (size_t)t * B * Gv, Gv, true, g32_len ? w.frames_tm + (size_t)t * B * d.F_v : batch->frames + (size_t)t * d.F_v,
+                        g32_len ? d.F_v : d.T_v * d.F_v, false, Gv, d.F_v, B, Gd.vid_w_ih, d.F_v).accumulate(t > 0).run(st));
     MMQG_TRY(colsum(w.acts_v, Gv, Gd.vid_b_ih, Gd.vid_b_hh, d.T_v * B, Gv, 0.f, st));
     return 0;
   }
@@ -585,11 +608,11 @@ int mmqg_train_backward(const mmqg_dims* dp, const mmqg_tensors* params, const m
       // initial state (train.py:169), plus, for the top layer, the step-0 attention query.
       const float* dh0 = last ? w.dh_rec[l] : w.dh_rec_enc;
       const float* dh1 = (last && l == L - 1) ? w.dq_h : nullptr;
-      const float* dh2 = l == L - 1 ? w.dm_txt + (size_t)t * H : w.dx_text + (size_t)t * B * H;
+      const float* dh2 = l == L - 1 ? (g32_len ? w.dm_txt : w.dm_txt + (size_t)t * H) : w.dx_text + (size_t)t * B * H;
       const int ldh2 = l == L - 1 ? d.TM * H : H;
       MMQG_TRY(lstm_pointwise_bwd(acts, G, t > 0 ? w.cs_text[l] + (size_t)t * B * H : nullptr, H,
                                   w.cs_text[l] + (size_t)(t + 1) * B * H, H, dh0, H, kSplit, ps, dh1, H, kSplit, ps, dh2,
-                                  ldh2, w.dc[l], H, 0, B, H, st, x3dg && t > 0 ? w.x3_dg : nullptr));
+                                  ldh2, w.dc[l], H, 0, B, H, st, x3dg && t > 0 ? w.x3_dg : nullptr, len32(w.shift_t, t, l == L - 1 ? 1 : 0)));
       if (t > 0)
         MMQG_TRY(GemmCall(acts, G, false, P.text_w_hh[l], H, false, B, H, G, w.dh_rec_enc, H).split(kSplit, ps).w()
                      .presplit(x3dg ? w.x3_dg : nullptr).run(st));
@@ -636,7 +659,7 @@ static int decode_impl(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   MMQG_REQUIRE(mode == MMQG_MODE_FP32 || mode == MMQG_MODE_BF16 || mode == MMQG_MODE_FP32_TC, "unknown mode %d", mode);
   if (mode == MMQG_MODE_BF16)
     return greedy_decode_bf16(d, *params, *batch, workspace, workspace_bytes, tokens_out, max_len, as_stream(stream), sample, seed);
-  MMQG_REQUIRE(!batch->ctx_len && !batch->n_frames, "per-sample lengths are supported in the bf16 mode only");
+  g32_len = batch->ctx_len || batch->n_frames;
   g32_drop_p = 0.f;      // decoding is eval mode: no dropout
   g32_tc = mode == MMQG_MODE_FP32_TC;
   Ws w = carve(d, max_len, workspace, g32_tc);
@@ -647,7 +670,8 @@ static int decode_impl(const mmqg_dims* dp, const mmqg_tensors* params, const mm
   const mmqg_tensors& P = *params;
   const int B = d.B, H = d.H, G = 4 * d.H, E = d.E, Q = d.E + d.H, C = d.H + d.H_a + d.H_v, X0 = E + C, Sp = w.S_pad;
 
-  MMQG_TRY(build_indices(batch->context, nullptr, w.idx_ctx, nullptr, nullptr, B, d.T_t, 0, st));
+  if (g32_len) MMQG_TRY(prep_lengths(batch->ctx_len, nullptr, batch->n_frames, w.shift_t, w.shift_v, w.row_w, B, d.T_t, d.T_v, 1, st));
+  MMQG_TRY(build_indices(batch->context, nullptr, w.idx_ctx, nullptr, nullptr, B, d.T_t, 0, st, g32_len ? w.shift_t : nullptr));
   MMQG_TRY(encoder_forward(d, P, *batch, w, st));
   MMQG_TRY(handoff_state(d, w, st));
   MMQG_TRY(pack_attention(d, P, w, st));

@@ -14,6 +14,15 @@ void f32x3_bind(void* arena, size_t arena_bytes, void* sa, size_t sa_bytes, void
 void f32x3_presplit_a(const void* a_split);
 size_t f32x3_split_bytes(int mn, long long n, long long K);
 
+// Variable-length batches in the recurrent kernels (persistent kernels: rows of a launch; fp32 cell kernels: t_base = the step): sample (row) m is right-aligned in time,
+// its steps t_base + t < shift[m] are masked (state held at zero, no gradient); with mem_shift the
+// batch-major memory output (forward) / external gradient input (backward) is indexed by the
+// sample's own position t_base + t - shift[m] instead of the time step.
+struct LenSpec {
+  const int* shift = nullptr;
+  int t_base = 0;
+  int mem_shift = 0;
+};
 // Pre-activations handed to the forward cell kernel as split-K partial sums: pre = (gates if
 // add_gates) + bias + sum_k part[k*stride + b*ld + .]; the activated gates still land in `gates`.
 struct PreSpec {
@@ -27,15 +36,17 @@ struct PreSpec {
   int no_save = 0;      // forward-only caller: the activated gates need not be written back (honoured by the vectorised bf16 kernel)
 };
 int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
-                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, PreSpec ps = PreSpec());
+                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, PreSpec ps = PreSpec(), LenSpec len = LenSpec());
 int lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                        const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,
                        const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, int B, int H,
-                       cudaStream_t st, void* dg_split = nullptr);      // dg_split: d pre-activations also as bf16 [hi(4H) | lo(4H)], pitch 8H
+                       cudaStream_t st, void* dg_split = nullptr,       // dg_split: d pre-activations also as bf16 [hi(4H) | lo(4H)], pitch 8H
+                       LenSpec len = LenSpec());
 int embedding_gather(const float* emb, const int64_t* idx, float* out, int ldo, int N, int E, int V, cudaStream_t st);
 int embedding_scatter_add(float* demb, const int64_t* idx, const float* dx, int N, int E, int V, cudaStream_t st);
 int nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_stride, float* nll, int R, int V,
-             float scale, cudaStream_t st);
+             float scale, cudaStream_t st, const float* row_w = nullptr);     // row_w: per-row loss weight (0 beyond a sample's target length)
+int frames_to_time_major_f32(const float* frames, float* out, const int* shift_v, int B, int T_v, int F, cudaStream_t st);
 int argmax_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int64_t* tokens2, int R, int V,
                 cudaStream_t st);
 int sample_rows(const float* logits, int ldl, int64_t* tokens, long long tok_stride, int64_t* tokens2, int R, int V,
@@ -108,15 +119,6 @@ bool lstm_persist_fwd_ok(int B, int H);     // forward kernel alone (two m-tiles
 int lstm_persist_fwd_ctas(int B, int H);    // CTAs of one forward launch
 int device_sms();
 int pack_whh(const float* w_hh, void* fwd_packed, void* bwd_packed, int H, cudaStream_t st);
-// Variable-length batches in the persistent recurrent kernels: sample (row) m is right-aligned in time,
-// its steps t_base + t < shift[m] are masked (state held at zero, no gradient); with mem_shift the
-// batch-major memory output (forward) / external gradient input (backward) is indexed by the
-// sample's own position t_base + t - shift[m] instead of the time step.
-struct LenSpec {
-  const int* shift = nullptr;
-  int t_base = 0;
-  int mem_shift = 0;
-};
 extern thread_local int tl_ktag;      // debug: tag of the next persistent recurrent launch (lstm_persist.cu)
 int sum_partials(const float* a, int na, const float* b, int nb, long long stride, float* y, int n, cudaStream_t st);
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,

@@ -22,13 +22,27 @@ int set_err(int code, const char* fmt, ...) {
 // ----------------------------------------------------------------------------------------
 __global__ void lstm_pointwise_fwd_kernel(float* __restrict__ gates, int ldg, const float* __restrict__ c_prev,
                                           int ldcp, float* __restrict__ c_out, int ldc, float* __restrict__ h_out,
-                                          int ldh, float* __restrict__ h2, int ldh2, int B, int H, PreSpec ps) {
+                                          int ldh, float* __restrict__ h2, int ldh2, int B, int H, PreSpec ps, LenSpec len) {
   pdl_launch_dependents();
   pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, j = idx % H;
   float* g = gates + (size_t)b * ldg;
+  if (len.shift) {       // right-aligned variable-length batch: the steps before a sample's first one hold the zero state
+    const int sh = len.shift[b];
+    if (len.t_base < sh) {     // zero gates make the backward kernel return zero gradients for this (step, sample) by itself
+      g[j] = 0.f; g[H + j] = 0.f; g[2 * H + j] = 0.f; g[3 * H + j] = 0.f;
+      c_out[(size_t)b * ldc + j] = 0.f;
+      h_out[(size_t)b * ldh + j] = 0.f;
+      if (ps.h_split) {
+        __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(ps.h_split) + (size_t)b * 2 * H;
+        sp[j] = __float2bfloat16_rn(0.f); sp[H + j] = __float2bfloat16_rn(0.f);
+      }
+      return;
+    }
+    if (len.mem_shift && h2) h2 += (size_t)(len.t_base - sh) * H;      // memory row = the sample's own position (h2 = row 0)
+  }
   float pre[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) pre[q] = (ps.n_part == 0 || ps.add_gates) ? g[q * H + j] : 0.f;
@@ -63,12 +77,26 @@ __global__ void lstm_pointwise_bwd_kernel(float* __restrict__ acts, int ldg, con
                                           const float* __restrict__ dh0, int ldh0, int n0, long long s0,
                                           const float* __restrict__ dh1, int ldh1, int n1, long long s1, const float* __restrict__ dh2,
                                           int ldh2, float* __restrict__ dc, int lddc, int dc_is_zero, int B, int H,
-                                          __nv_bfloat16* __restrict__ dg_split) {
+                                          __nv_bfloat16* __restrict__ dg_split, LenSpec len) {
   pdl_launch_dependents();
   pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, j = idx % H;
+  if (len.shift) {
+    const int sh = len.shift[b];
+    if (len.t_base < sh) {     // masked step: no gradient flows through it or out of it
+      float* a0 = acts + (size_t)b * ldg;
+      a0[j] = 0.f; a0[H + j] = 0.f; a0[2 * H + j] = 0.f; a0[3 * H + j] = 0.f;
+      dc[(size_t)b * lddc + j] = 0.f;
+      if (dg_split) {
+        __nv_bfloat16* sp = dg_split + (size_t)b * 8 * H;
+        for (int q = 0; q < 8; ++q) sp[q * H + j] = __float2bfloat16_rn(0.f);
+      }
+      return;
+    }
+    if (len.mem_shift && dh2) dh2 += (size_t)(len.t_base - sh) * H;     // external gradient row = the sample's own position
+  }
   float dh = 0.f;
   if (dh0)
     for (int s = 0; s < n0; ++s) dh += dh0[(size_t)s * s0 + (size_t)b * ldh0 + j];
@@ -149,9 +177,12 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 
 __global__ void __launch_bounds__(256) nll_rows_kernel(float* __restrict__ logits, int ldl,
                                                        const int64_t* __restrict__ targets, long long tgt_stride,
-                                                       float* __restrict__ nll, int R, int V, float scale) {
+                                                       float* __restrict__ nll, int R, int V, float scale,
+                                                       const float* __restrict__ row_w) {
   __shared__ float sh[8];
   int r = blockIdx.x;
+  const float rw = row_w ? row_w[r] : 1.f;
+  scale *= rw;
   float* x = logits + (size_t)r * ldl;
   float m = -INFINITY;
   for (int v = threadIdx.x; v < V; v += 256) m = fmaxf(m, x[v]);
@@ -162,8 +193,8 @@ __global__ void __launch_bounds__(256) nll_rows_kernel(float* __restrict__ logit
   float lse = m + logf(s);
   long long t = targets[(size_t)r * tgt_stride];
   t = t < 0 ? 0 : (t >= V ? V - 1 : t);
-  if (threadIdx.x == 0) nll[r] = lse - x[t];
-  if (scale != 0.f) {
+  if (threadIdx.x == 0) nll[r] = rw * (lse - x[t]);
+  if (scale != 0.f || row_w) {
     __syncthreads();
     for (int v = threadIdx.x; v < V; v += 256) {
       float p = expf(x[v] - lse);
@@ -335,12 +366,12 @@ __global__ void __launch_bounds__(256) sum_scale_kernel(const float* __restrict_
 
 // ---------------------------------------------------------------------------- host wrappers
 int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, float* c_out, int ldc, float* h_out,
-                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, PreSpec ps) {
+                       int ldh, float* h2, int ldh2, int B, int H, cudaStream_t st, PreSpec ps, LenSpec len) {
   MMQG_REQUIRE(gates && c_out && h_out && B > 0 && H > 0, "lstm_pointwise_fwd: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (c_prev ? 11 : 10) + (h2 ? 4.0 * n : 0));
   MMQG_CUDA(launch_k(lstm_pointwise_fwd_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, gates, ldg, c_prev, ldcp, c_out, ldc, h_out, ldh, h2,
-                     ldh2, B, H, ps));
+                     ldh2, B, H, ps, len));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -348,12 +379,12 @@ int lstm_pointwise_fwd(float* gates, int ldg, const float* c_prev, int ldcp, flo
 int lstm_pointwise_bwd(float* acts, int ldg, const float* c_prev, int ldcp, const float* c_new, int ldc,
                        const float* dh0, int ldh0, int n0, long long s0, const float* dh1, int ldh1, int n1, long long s1,
                        const float* dh2, int ldh2, float* dc, int lddc, int dc_is_zero, int B, int H,
-                       cudaStream_t st, void* dg_split) {
+                       cudaStream_t st, void* dg_split, LenSpec len) {
   MMQG_REQUIRE(acts && c_new && dc && B > 0 && H > 0, "lstm_pointwise_bwd: bad args");
   int n = B * H;
   MMQG_PROBE(KC_POINTWISE, 0, 4.0 * n * (10 + (c_prev ? 1 : 0) + (dh0 ? n0 : 0) + (dh1 ? n1 : 0) + (dh2 ? 1 : 0)));
   MMQG_CUDA(launch_k(lstm_pointwise_bwd_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, acts, ldg, c_prev, ldcp, c_new, ldc, dh0, ldh0, n0, s0,
-                     dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, B, H, reinterpret_cast<__nv_bfloat16*>(dg_split)));
+                     dh1, ldh1, n1, s1, dh2, ldh2, dc, lddc, dc_is_zero, B, H, reinterpret_cast<__nv_bfloat16*>(dg_split), len));
   MMQG_LAUNCH_CHECK();
   return 0;
 }
@@ -375,10 +406,10 @@ int embedding_scatter_add(float* demb, const int64_t* idx, const float* dx, int 
 }
 
 int nll_rows(float* logits, int ldl, const int64_t* targets, long long tgt_stride, float* nll, int R, int V,
-             float scale, cudaStream_t st) {
+             float scale, cudaStream_t st, const float* row_w) {
   MMQG_REQUIRE(logits && targets && nll && R > 0 && V > 0, "nll_rows: bad args");
   MMQG_PROBE(KC_LOSS, 0, 4.0 * R * V * (scale != 0.f ? 2 : 1));
-  nll_rows_kernel<<<R, 256, 0, st>>>(logits, ldl, targets, tgt_stride, nll, R, V, scale);
+  nll_rows_kernel<<<R, 256, 0, st>>>(logits, ldl, targets, tgt_stride, nll, R, V, scale, row_w);
   MMQG_LAUNCH_CHECK();
   return 0;
 }

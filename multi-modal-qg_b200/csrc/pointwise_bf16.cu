@@ -267,6 +267,21 @@ int frames_to_time_major_bf16(const float* frames, void* out, const int* shift_v
   MMQG_LAUNCH_CHECK();
   return 0;
 }
+// fp32 twin (parity modes): frames (B, T_v, F) -> (T_v*B, F) time-major, right-aligned by shift_v (zeros before)
+__global__ void frames_tm_f32_kernel(const float* __restrict__ frames, float* __restrict__ out, const int* __restrict__ shift_v, int B,
+                                     int T_v, int F) {
+  const int row = blockIdx.x;                 // t*B + b
+  const int t = row / B, b = row % B;
+  const int sh = shift_v ? shift_v[b] : 0;
+  float* dst = out + (size_t)row * F;
+  const float* src = frames + ((size_t)b * T_v + (t - sh)) * F;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) dst[f] = t < sh ? 0.f : src[f];
+}
+int frames_to_time_major_f32(const float* frames, float* out, const int* shift_v, int B, int T_v, int F, cudaStream_t st) {
+  frames_tm_f32_kernel<<<B * T_v, 256, 0, st>>>(frames, out, shift_v, B, T_v, F);
+  MMQG_LAUNCH_CHECK();
+  return 0;
+}
 // audio (B, T_v, H_a) -> zero-padded memory (B, AM, H_a); rows >= n_frames[b] are zero (train.py:156)
 __global__ void audio_pad_kernel(const float* __restrict__ audio, float* __restrict__ m_aud, const int* __restrict__ n_frames, int B,
                                  int T_v, int AM, int H_a) {

@@ -250,16 +250,6 @@ def test_bf16_variable_lengths_match_per_sample_oracle(eng_mod, T_t, chunks, mon
         assert rel(g_full[k], eng.grads[k]) < 1e-4, k
 
 
-def test_fp32_mode_rejects_lengths(eng_mod):
-    from mmqg import _cabi
-    d = Dims(B=2, T_t=3, T_v=2, T_q=2, V=11, E=10, H=12, L=2, H_a=6, H_v=12, F_v=10, TM=4, AM=3)
-    eng = eng_mod.TrainEngine(d, make_params(d), mode="fp32")
-    b = make_batch(d)
-    b["ctx_len"] = torch.tensor([2, 3], dtype=torch.int32)
-    with pytest.raises(_cabi.MmqgError):
-        eng.step(eng.to_device(b))
-
-
 def test_bf16_greedy_decode_with_lengths(eng_mod):
     """Greedy decode honours ctx_len / n_frames: each row equals the oracle run on that sample alone,
     cut to its own lengths (up to the first near-tie)."""

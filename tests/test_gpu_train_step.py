@@ -177,3 +177,64 @@ def test_fp32_step_with_dropout_matches_oracle_with_same_masks(eng_mod, cfg, mod
         assert worst[0] < TOL, worst
     loss_nodrop, _ = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
     assert abs(loss - float(loss_nodrop)) > 1e-4 * abs(loss)      # the masks do act
+
+
+@pytest.mark.parametrize("mode", MODES32)
+def test_fp32_variable_lengths_match_per_sample_oracle(eng_mod, mode):
+    """mmqg_batch.ctx_len / tgt_len / n_frames in the parity modes: the batched step equals the reference's per-sample loop
+    with every sample cut to its own lengths (the reference is batch-1; its DataLoader cannot batch unequal samples), at the
+    north-star 1e-3 bar; explicit full lengths equal no lengths."""
+    from oracle import mmqg_oracle as O
+    T_t = 13
+    d = Dims(B=10, T_t=T_t, T_v=4, T_q=5, V=300, E=52, H=64, L=2, H_a=24, H_v=64, F_v=40, TM=T_t + 3, AM=6)
+    params = make_params(d, seed=101)
+    batch = make_batch(d, seed=102)
+    g = torch.Generator().manual_seed(5)
+    batch["ctx_len"] = torch.randint(1, T_t + 1, (d.B,), generator=g, dtype=torch.int32)
+    batch["tgt_len"] = torch.randint(1, d.T_q + 1, (d.B,), generator=g, dtype=torch.int32)
+    batch["n_frames"] = torch.randint(1, d.T_v + 1, (d.B,), generator=g, dtype=torch.int32)
+    batch["ctx_len"][0], batch["tgt_len"][0], batch["n_frames"][0] = T_t, d.T_q, d.T_v      # one full-length sample
+    batch["ctx_len"][1], batch["tgt_len"][1], batch["n_frames"][1] = 1, 1, 1                # and one minimal
+    plain = {k: v for k, v in batch.items() if k not in ("ctx_len", "tgt_len", "n_frames")}
+    loss_ref, grads_ref = O.loss_and_grads(params, batch, d.L, d.TM, d.AM, torch.float64)
+    loss_full, _ = O.loss_and_grads(params, plain, d.L, d.TM, d.AM, torch.float64)
+    assert abs(float(loss_ref) - float(loss_full)) > 0.05 * abs(float(loss_full))           # the lengths matter
+    eng = eng_mod.TrainEngine(d, params, mode=mode)
+    loss = float(eng.step(eng.to_device(batch)))
+    torch.cuda.synchronize()
+    assert abs(loss - float(loss_ref)) < TOL * abs(float(loss_ref)), (loss, float(loss_ref), float(loss_full))
+    worst = max((rel(eng.grads[k], g), k) for k, g in grads_ref.items())
+    print(f"{mode} varlen: loss rel err {abs(loss - float(loss_ref)) / abs(float(loss_ref)):.2e}; worst grad {worst}")
+    assert worst[0] < TOL, worst
+    full = dict(batch)
+    full["ctx_len"] = torch.full((d.B,), T_t, dtype=torch.int32)
+    full["tgt_len"] = torch.full((d.B,), d.T_q, dtype=torch.int32)
+    full["n_frames"] = torch.full((d.B,), d.T_v, dtype=torch.int32)
+    l_full = float(eng.step(eng.to_device(full)))
+    g_full = {k: v.clone() for k, v in eng.grads.items()}
+    l_plain = float(eng.step(eng.to_device(plain)))
+    torch.cuda.synchronize()
+    assert abs(l_full - l_plain) < 1e-5 * abs(l_plain)
+    for k in g_full:
+        assert rel(g_full[k], eng.grads[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("mode", MODES32)
+def test_fp32_greedy_decode_with_lengths(eng_mod, mode):
+    """Greedy decode honours ctx_len / n_frames: each row equals the oracle run on that sample alone, cut to its own lengths."""
+    from oracle import mmqg_oracle as O
+    d = Dims(B=8, T_t=14, T_v=4, T_q=5, V=400, E=52, H=64, L=2, H_a=24, H_v=64, F_v=40, TM=16, AM=6)
+    params = make_params(d, seed=111, bias_scale=0.1, out_weight_scale=10.0)
+    batch = make_batch(d, seed=112)
+    g = torch.Generator().manual_seed(9)
+    batch["ctx_len"] = torch.randint(1, d.T_t + 1, (d.B,), generator=g, dtype=torch.int32)
+    batch["n_frames"] = torch.randint(1, d.T_v + 1, (d.B,), generator=g, dtype=torch.int32)
+    eng = eng_mod.TrainEngine(d, params, mode=mode)
+    toks = eng.greedy(eng.to_device(batch), 6).cpu()
+    for b in range(d.B):
+        cl, nf = int(batch["ctx_len"][b]), int(batch["n_frames"][b])
+        one = {"context": batch["context"][b:b + 1, :cl], "target": batch["target"][b:b + 1],
+               "frames": batch["frames"][b:b + 1, :nf], "audio": batch["audio"][b:b + 1, :nf]}
+        ref, margins = O.greedy_decode(params, one, d.L, d.TM, d.AM, 6, torch.float64, return_margins=True)
+        diff = (toks[b] != ref[0]).nonzero()
+        assert diff.numel() == 0 or float(margins[0, int(diff[0])]) < 1e-4, (b, toks[b], ref[0], margins[0])
