@@ -71,6 +71,10 @@ class GradReducer:
                 with torch.cuda.stream(self.side):
                     self.mm.all_reduce(i)
             return
+        if self.side is None:        # CPU buckets (gloo tests): no streams or events, reduce in place
+            for t in ([self.flat] if self.schedule == "late" else self.buckets):
+                self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            return
         if self.schedule == "late":
             for e in self.events:
                 self.side.wait_event(e)

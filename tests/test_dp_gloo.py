@@ -21,20 +21,21 @@ class _FakeEngine:
     def __init__(self, shapes, L):
         from mmqg.engine import grad_group
         self.grads, self.grad_buckets = {}, []
+        offs, total, ranges = {}, 0, []
         for g in range(4 + L):
-            names = [n for n in shapes if grad_group(n, L) == g]
-            offs, total = {}, 0
-            for n in names:
+            lo = total
+            for n in [n for n in shapes if grad_group(n, L) == g]:
                 offs[n] = total
                 total += (int(torch.tensor(shapes[n]).prod()) + 63) // 64 * 64
-            flat = torch.zeros(total, dtype=torch.float32)
-            for n in names:
-                numel = int(torch.tensor(shapes[n]).prod())
-                self.grads[n] = flat[offs[n]:offs[n] + numel].view(shapes[n])
-            self.grad_buckets.append(flat)
+            ranges.append((lo, total))
+        self.flat_grads = torch.zeros(total, dtype=torch.float32)      # one flat buffer, buckets = consecutive ranges of it
+        for n, o in offs.items():
+            numel = int(torch.tensor(shapes[n]).prod())
+            self.grads[n] = self.flat_grads[o:o + numel].view(shapes[n])
+        self.grad_buckets = [self.flat_grads[lo:hi] for lo, hi in ranges]
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, schedule="overlap"):
     for p in (ROOT, os.path.join(ROOT, "multi-modal-qg_b200")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -55,9 +56,12 @@ def _worker(rank, world, port, ret):
     scale = (dg.B // world) / dg.B
     for k, g in grads_l.items():
         eng.grads[k].copy_((scale * g).float())
-    red = GradReducer(eng, world)
-    for phase in range(4):                       # backward phases: loss head, decoder, video, text layers + embedding
-        red.on_phase(phase)
+    red = GradReducer(eng, world, schedule=schedule)
+    if schedule == "late":                       # one all-reduce of the flat buffer after the backward
+        red.after_backward()
+    else:
+        for phase in range(4):                   # backward phases: loss head, decoder, video, text layers + embedding
+            red.on_phase(phase)
     red.finish()
     loss_g, grads_g = O.loss_and_grads(params, gbatch, dg.L, dg.TM, dg.AM, torch.float64)
     worst = max(O.rel_err(eng.grads[k], g) for k, g in grads_g.items())
@@ -69,12 +73,13 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_dp_two_ranks_match_global_batch():
+@pytest.mark.parametrize("schedule", ["overlap", "late"])
+def test_dp_two_ranks_match_global_batch(schedule):
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    port = 29500 + os.getpid() % 2000 + (7 if schedule == "late" else 0)
+    mp.spawn(_worker, args=(world, port, ret, schedule), nprocs=world, join=True)
     assert ret["worst"] < 1e-5, dict(ret)
     assert ret["loss_err"] < 1e-12
 
