@@ -169,6 +169,13 @@ struct LstmFwdP {
   LenSpec len;
 };
 
+// CL = 2 (MMQG_FWD_MC=1): the two CTAs of a (2,1,1) cluster -- neighbouring unit slices of one m-tile, which read the SAME
+// 128 KB h_{t-1} tile -- each issue half of its eight 16 KB boxes as a cluster-multicast TMA load, so the tile leaves L2 once
+// per pair instead of once per CTA.  A box may be written into the peer's ring slot as soon as the issuing CTA has seen the
+// step's arrival counter complete: the peer publishes h_{t-1} only after its step-(t-1) MMAs (the last readers of that slot)
+// have committed.  Every CTA arms its own eight mbarriers for the full tile; a complete_tx that lands before the expect_tx
+// leaves the transaction count negative until it is armed.
+template <int CL>
 __global__ void __launch_bounds__(160, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, LstmFwdP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -196,6 +203,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  if (CL > 1) cluster_sync_all();             // the peer's mbarriers exist before a multicast load can signal them
 
   if (warp == 4) {
     if (elect_one()) {
@@ -214,7 +223,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         if (tr) { const long long g = gtime(); atomicMin((unsigned long long*)&tr[t * 8 + 0], (unsigned long long)g); atomicMax((unsigned long long*)&tr[t * 8 + 1], (unsigned long long)g); }
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_expect_tx(&a_full[kb], 16384);
-          tma_load_2d(sA + kb * 16384, &tmH, &a_full[kb], kb * 64, t * B + mt * 128);
+          if (CL == 1) tma_load_2d(sA + kb * 16384, &tmH, &a_full[kb], kb * 64, t * B + mt * 128);
+          else if ((uint32_t)(kb & (CL - 1)) == crank)
+            tma_load_2d_mc(sA + kb * 16384, &tmH, &a_full[kb], kb * 64, t * B + mt * 128, (uint16_t)((1u << CL) - 1u));
         }
         if (t == 0) mbar_wait(&w_full, 0);
         else mbar_wait(&tmem_free, (t - 1) & 1);                    // epilogue has drained the accumulator
@@ -359,6 +370,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 64);
   }
+  if (CL > 1) cluster_sync_all();             // nobody leaves while a peer's multicast load may still target its ring
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -810,15 +822,6 @@ struct LstmBwd4Smem {
   static constexpr int XBUF = 3 * XSRC;             // three peers
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
@@ -1216,6 +1219,31 @@ static int launch_coop(Kern kern, dim3 grid, int threads, size_t smem, const CUt
   return 0;
 }
 
+// Launch with a (CLX,1,1) cluster AND the cooperative attribute: the clusters of one launch still wait on
+// each other through the global arrival counters, so the whole grid must be co-resident.
+template <typename Kern, typename P>
+static cudaError_t launch_coop_cluster(Kern kern, int clx, dim3 grid, int threads, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1,
+                                       const P& p, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = clx;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  // Profiling aid: Nsight Compute refuses a launch that is both cooperative and clustered (LaunchFailed).  Under ncu the
+  // kernels of a process are serialised anyway, so MMQG_NCU=1 drops the cooperative attribute (attr[0]) for its runs only.
+  static const bool ncu = []() { const char* e = getenv("MMQG_NCU"); return e && e[0] == '1'; }();
+  cfg.attrs = ncu ? attr + 1 : attr;
+  cfg.numAttrs = ncu ? 1 : 2;
+  return cudaLaunchKernelEx(&cfg, kern, m0, m1, p);
+}
+
 // gates: (T*B,4H) fp32 pre-gates -> activated gates.  wp_fwd: pack_whh forward layout.  hs slab 0 must be zeros.
 int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, float* mem, void* mem16, long long mem_ld,
                          uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st, DropSpec dr, bool zero_flags, LenSpec len) {
@@ -1227,7 +1255,8 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
   const size_t smem = (size_t)p.KB * (8192 + 16384) + 4 * STG_WARP * sizeof(float) + 1024;
   static bool attr = false;
   if (!attr) {
-    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 16384) + 4 * STG_WARP * sizeof(float) + 1024));
+    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 16384) + 4 * STG_WARP * sizeof(float) + 1024));
+    MMQG_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (8192 + 16384) + 4 * STG_WARP * sizeof(float) + 1024));
     attr = true;
   }
   if (zero_flags) MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(T + 1) * p.n_mt, st));
@@ -1246,34 +1275,16 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
     return 0;
   }
   MMQG_PROBE(KC_LSTM_PERSIST, fl, 0);
-  MMQG_TRY(launch_coop(lstm_seq_fwd_kernel, dim3(p.n_slices, p.n_mt), 160, smem, tmW, tmH, p, st));
+  // MMQG_FWD_MC=1: pairs of unit slices as (2,1,1) clusters sharing the h_{t-1} tile by multicast TMA (read per call: A/B runs)
+  const char* mc = getenv("MMQG_FWD_MC");
+  if (mc && mc[0] == '1' && p.n_slices % 2 == 0 && p.KB % 2 == 0 && !g_lstm_trace) {
+    MMQG_CUDA(launch_coop_cluster(lstm_seq_fwd_kernel<2>, 2, dim3(p.n_slices, p.n_mt), 160, smem, tmW, tmH, p, st));
+    MMQG_LAUNCH_CHECK();
+    return 0;
+  }
+  MMQG_TRY(launch_coop(lstm_seq_fwd_kernel<1>, dim3(p.n_slices, p.n_mt), 160, smem, tmW, tmH, p, st));
   MMQG_LAUNCH_CHECK();
   return 0;
-}
-
-// Launch with a (4,1,1) cluster AND the cooperative attribute: the clusters of one launch still wait on
-// each other through the global arrival counters, so the whole grid must be co-resident.
-template <typename Kern, typename P>
-static cudaError_t launch_coop_cluster4(Kern kern, dim3 grid, int threads, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1,
-                                        const P& p, cudaStream_t st) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  attr[1].id = cudaLaunchAttributeClusterDimension;
-  attr[1].val.clusterDim.x = 4;
-  attr[1].val.clusterDim.y = 1;
-  attr[1].val.clusterDim.z = 1;
-  // Profiling aid: Nsight Compute refuses a launch that is both cooperative and clustered (LaunchFailed).  Under ncu the
-  // kernels of a process are serialised anyway, so MMQG_NCU=1 drops the cooperative attribute (attr[0]) for its runs only.
-  static const bool ncu = []() { const char* e = getenv("MMQG_NCU"); return e && e[0] == '1'; }();
-  cfg.attrs = ncu ? attr + 1 : attr;
-  cfg.numAttrs = ncu ? 1 : 2;
-  return cudaLaunchKernelEx(&cfg, kern, m0, m1, p);
 }
 
 static size_t bwd4_smem_bytes(int H) {
@@ -1325,7 +1336,7 @@ int lstm_seq_bwd_persist(const float* acts, const float* cs, void* dg, const voi
     if (zero_flags) MMQG_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)T * p.n_mt, st));
     const double fl4 = 2.0 * (T - 1) * B * 4.0 * H * H;
     MMQG_PROBE(KC_LSTM_PERSIST, fl4, 0);
-    const cudaError_t le = launch_coop_cluster4(lstm_seq_bwd4_kernel, dim3(p.n_slices, p.n_mt), 192, bwd4_smem_bytes(H), tmW4, tmG4, p, st);
+    const cudaError_t le = launch_coop_cluster(lstm_seq_bwd4_kernel, 4, dim3(p.n_slices, p.n_mt), 192, bwd4_smem_bytes(H), tmW4, tmG4, p, st);
     if (le == cudaSuccess) {
       MMQG_LAUNCH_CHECK();
       return 0;
