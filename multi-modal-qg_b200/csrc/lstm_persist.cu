@@ -167,6 +167,7 @@ struct LstmFwdP {
   long long* ktrace; int ktag;   // debug: kernel-level timeline (see mmqg_debug_ktrace)
   DropSpec dr;         // dr.out: optional dropped bf16 copy of h_t, (T*B, H) rows t*B+b (input of the next layer)
   LenSpec len;
+  int dbg_nosave;      // timing experiments only (MMQG_DEBUG_NOSAVE=1): the activated gates / c_t are not saved for the backward pass
 };
 
 // CL = 2 (MMQG_FWD_MC=1): the two CTAs of a (2,1,1) cluster -- neighbouring unit slices of one m-tile, which read the SAME
@@ -324,13 +325,17 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       // copy) is off the critical path and overlaps the wait for the next step
       {
         float4 tmp[4];
+        if (!p.dbg_nosave) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          row_to_coop(stg, lane, acc + g * 16, tmp);
-          coop_stg(gbase + g * H, G, rows_valid, lane, tmp);
+          for (int g = 0; g < 4; ++g) {
+            row_to_coop(stg, lane, acc + g * 16, tmp);
+            coop_stg(gbase + g * H, G, rows_valid, lane, tmp);
+          }
         }
-        row_to_coop(stg, lane, c, tmp);
-        coop_stg(p.cs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid, lane, tmp);
+        if (!p.dbg_nosave || t == p.T - 1) {
+          row_to_coop(stg, lane, c, tmp);
+          coop_stg(p.cs + ((size_t)(t + 1) * B + m0w) * H + j0, H, rows_valid, lane, tmp);
+        }
         const bool shifted = p.len.shift && p.len.mem_shift;      // memory row = the sample's own position
         if (p.mem) {
           row_to_coop(stg, lane, hv, tmp);
@@ -1249,6 +1254,7 @@ int lstm_seq_fwd_persist(float* gates, float* cs, void* hs, const void* wp_fwd, 
                          uint32_t* flags, int T, int B, int H, int load_c0, cudaStream_t st, DropSpec dr, bool zero_flags, LenSpec len) {
   MMQG_REQUIRE(lstm_persist_fwd_ok(B, H), "lstm_seq_fwd_persist: shape B=%d H=%d not supported", B, H);
   LstmFwdP p{gates, cs, reinterpret_cast<bf16*>(hs), mem, reinterpret_cast<bf16*>(mem16), mem_ld, flags, T, B, H, ceil_div(B, 128), H / 16, H / 64, load_c0, g_lstm_trace, g_ktrace, tl_ktag, dr, len};
+  { const char* e = getenv("MMQG_DEBUG_NOSAVE"); p.dbg_nosave = e && e[0] == '1'; }
   CUtensorMap tmW, tmH;
   MMQG_TRY(make_tmap_bf16_2d(&tmW, wp_fwd, 4 * (uint64_t)H, H, H, 64, 64));
   MMQG_TRY(make_tmap_bf16_2d(&tmH, hs, (uint64_t)(T + 1) * B, H, H, 128, 64));
