@@ -1,5 +1,5 @@
-mkdir -p gpurun_out/r2final
-O=gpurun_out/r2final
+mkdir -p gpurun_out/r2final2
+O=gpurun_out/r2final2
 timeout 1500 python -m pytest tests -x -q -m gpu > $O/pt.log 2>&1; echo "rc=$?" >> $O/pt.log; tail -4 $O/pt.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "rc=$?" >> $O/smoke.log; tail -6 $O/smoke.log
 timeout 400 python bench.py > $O/bench.json 2> $O/bench.err; python -c "
